@@ -1,0 +1,676 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM convolution for sm_100a (B200).
+//
+// One persistent, warp-specialised kernel serves both entry points:
+//   saspa_gemm_bf16          D[M,N] = epi(A[M,K] . B[N,K]^T)           (Linear, 1x1 conv, im2col'd conv)
+//   saspa_conv2d_igemm_bf16  NHWC stride-1 "same" conv, ksize 1|3, optional 2-source channel concat
+// They replace the cuBLAS/cuDNN calls under diffusers' UNet2DConditionModel / ControlNetModel /
+// AutoencoderKL forward (reference: pipe(**pipe_args), run_aug/run_aug.py:278) and the filter nets
+// (all_utils/utils.py:361 WSDAN_CAL, :152-164 CLIP).
+//
+// Structure per CTA (192 threads, 1 CTA / SM, grid = min(tiles, #SM)):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor (2-D for GEMM, 4-D NHWC boxes for conv: the 3x3 taps are
+//              nine shifted boxes and TMA's out-of-bounds zero fill IS the conv padding) into a
+//              STAGES-deep ring of 128B-swizzled smem tiles, signalled by mbarrier complete_tx.
+//   warp 1   : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::f16
+//              (128 x BN x 16 per instruction, fp32 accumulate in TMEM), tcgen05.commit frees smem
+//              stages and publishes the accumulator.  Two accumulator buffers (columns 0 / 256) let the
+//              epilogue of tile i overlap the main loop of tile i+1.
+//   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 (one output row per thread), fused bias / per-image
+//              row bias (time embedding) / activation / GEGLU / alpha / residual, 16-byte stores.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/saspa_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int NUM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;  // column offset between the two accumulator buffers
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles;
+  int mode;  // 0 = GEMM, 1 = implicit conv
+  // conv geometry
+  int n_img, H, W, c0, c1, ksize;
+  int bw, bh, bn;
+  int tiles_x, tiles_y;
+  // epilogue
+  const float* bias;
+  const float* row_bias;
+  int rows_per_group;
+  int act;
+  float alpha;
+  const __nv_bfloat16* residual;
+  int ld_res;
+  float beta;
+  int out_fp32;
+  void* D;
+  int ldd;
+  int n_out;   // valid output columns (N, or N/2 for GEGLU)
+  int vec_ok;  // 16-byte vector path allowed for residual loads / stores
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must trap (the launch then fails loudly) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("saspa gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// bf16 x bf16 -> fp32, A and B K-major, M = 128, N = BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) /*D fp32*/ | (1u << 7) /*A bf16*/ | (1u << 10) /*B bf16*/ | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case SASPA_ACT_SILU: return silu_f(v);
+    case SASPA_ACT_GELU: return gelu_erf_f(v);
+    case SASPA_ACT_RELU: return fmaxf(v, 0.0f);
+    case SASPA_ACT_QUICKGELU: return quick_gelu_f(v);
+    default: return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int cchunks = (p.mode == 1) ? (p.c0 + p.c1 + BK - 1) / BK : 0;
+  const int num_kb = (p.mode == 1) ? p.ksize * p.ksize * cchunks : (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.mode == 1 && p.c1 > 0) tma_prefetch_desc(&tmA1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        int x0 = 0, y0 = 0, n0 = 0;
+        if (p.mode == 1) {
+          int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
+          int ty = r % p.tiles_y, tn = r / p.tiles_y;
+          x0 = tx * p.bw;
+          y0 = ty * p.bh;
+          n0 = tn * p.bn;
+        }
+        const int pad = p.ksize >> 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          int kB;
+          if (p.mode == 0) {
+            kB = kb * BK;
+            tma_load_2d(&tmA0, a_dst, &full[stage], kB, m_blk * BM);
+          } else {
+            int tap = kb / cchunks, cc = kb - tap * cchunks;
+            int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+            int c = cc * BK;
+            kB = tap * (p.c0 + p.c1) + c;
+            if (c < p.c0)
+              tma_load_4d(&tmA0, a_dst, &full[stage], c, x0 + kx - pad, y0 + ky - pad, n0);
+            else
+              tma_load_4d(&tmA1, a_dst, &full[stage], c - p.c0, x0 + kx - pad, y0 + ky - pad, n0);
+          }
+          tma_load_2d(&tmB, b_dst, &full[stage], kB, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * A_BYTES));
+          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * C::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B along K inside the 128B swizzle atom = +2 in the 16-byte start-address field
+            tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool geglu = (p.act == SASPA_ACT_GEGLU);
+    constexpr int OUT_BN = BN;  // columns of output per tile (BN/2 when GEGLU)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int r = q * 32 + lane;
+      long long pix;
+      bool row_ok;
+      int group;
+      if (p.mode == 0) {
+        pix = (long long)m_blk * BM + r;
+        row_ok = pix < p.M;
+        group = p.row_bias ? (int)(pix / p.rows_per_group) : 0;
+      } else {
+        int tx = m_blk % p.tiles_x, rr = m_blk / p.tiles_x;
+        int ty = rr % p.tiles_y, tn = rr / p.tiles_y;
+        int lx = r % p.bw, t2 = r / p.bw;
+        int ly = t2 % p.bh, ln = t2 / p.bh;
+        int x = tx * p.bw + lx, y = ty * p.bh + ly, n = tn * p.bn + ln;
+        row_ok = (x < p.W) && (y < p.H) && (n < p.n_img);
+        pix = ((long long)n * p.H + y) * p.W + x;
+        group = n;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+      const int out_bn = geglu ? OUT_BN / 2 : OUT_BN;
+      const int col_base_in = n_blk * BN;       // column in the (interleaved) weight / bias space
+      const int col_base_out = n_blk * out_bn;  // column in the output
+#pragma unroll 1
+      for (int c0 = 0; c0 < out_bn; c0 += 32) {
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+        uint32_t v[32];
+        tc_ld32(t_row + c0, v);
+        uint32_t g[32];
+        if (geglu) tc_ld32(t_row + c0 + OUT_BN / 2, g);
+        tc_wait_ld();
+        if (col_base_out + c0 >= p.n_out) continue;  // warp-uniform
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            int n = col_base_in + c0 + j;
+            if (n + 3 < p.N) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) f[j + e] += __ldg(p.bias + n + e);
+            }
+          }
+        }
+        if (geglu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float gate = __uint_as_float(g[j]);
+            int n = col_base_in + OUT_BN / 2 + c0 + j;
+            if (p.bias && n < p.N) gate += __ldg(p.bias + n);
+            f[j] = f[j] * gelu_erf_f(gate);
+          }
+        } else {
+          if (p.row_bias && row_ok) {
+            const float* rb = p.row_bias + (size_t)group * p.N;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              int n = col_base_in + c0 + j;
+              if (n + 3 < p.N) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(rb + n));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < p.N) f[j + e] += __ldg(rb + n + e);
+              }
+            }
+          }
+          if (p.act != SASPA_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          }
+        }
+        if (p.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+        }
+        const int n0 = col_base_out + c0;
+        if (row_ok) {
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + (size_t)pix * p.ld_res + n0;
+          if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              f[j + 0] += p.beta * bf16_lo(u.x); f[j + 1] += p.beta * bf16_hi(u.x);
+              f[j + 2] += p.beta * bf16_lo(u.y); f[j + 3] += p.beta * bf16_hi(u.y);
+              f[j + 4] += p.beta * bf16_lo(u.z); f[j + 5] += p.beta * bf16_hi(u.z);
+              f[j + 6] += p.beta * bf16_lo(u.w); f[j + 7] += p.beta * bf16_hi(u.w);
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.n_out) f[j] += p.beta * __bfloat162float(rp[j]);
+          }
+        }
+        if (p.out_fp32) {
+          float* op = reinterpret_cast<float*>(p.D) + (size_t)pix * p.ldd + n0;
+          if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.n_out) op[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)pix * p.ldd + n0;
+          if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(f[j], f[j + 1]);
+              u.y = pack_bf16(f[j + 2], f[j + 3]);
+              u.z = pack_bf16(f[j + 4], f[j + 5]);
+              u.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(op + j) = u;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.n_out) op[j] = __float2bfloat16(f[j]);
+          }
+        }
+        }  // row_ok
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// rank-2 bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
+int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return SASPA_ERR_DRIVER;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    saspa_set_error("cuTensorMapEncodeTiled(2d rows=%lld cols=%lld ld=%lld box_rows=%d) failed: %d", rows, cols, ld, box_rows, (int)r);
+    return SASPA_ERR_DRIVER;
+  }
+  return SASPA_OK;
+}
+
+// rank-4 NHWC bf16 activation [n, h, w, c] with pixel stride ld (elements); box = [bn, bh, bw, 64].
+int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, long long ld, int bn, int bh, int bw) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return SASPA_ERR_DRIVER;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    saspa_set_error("cuTensorMapEncodeTiled(nhwc n=%d h=%d w=%d c=%d ld=%lld box=%d,%d,%d) failed: %d", n, h, w, c, ld, bn, bh, bw, (int)r);
+    return SASPA_ERR_DRIVER;
+  }
+  return SASPA_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    SASPA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  int total = p.num_m_tiles * p.num_n_tiles;
+  int grid = total < saspa_num_sms() ? total : saspa_num_sms();
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a0, a1, b, p);
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+
+// Tile width along N.  SD channel counts are multiples of 320 -> 160 tiles them exactly; the VAE /
+// ResNets are powers of two; GEGLU needs value|gate halves in one tile (256 = 128 + 128).
+int pick_bn(int N, int act) {
+  if (act == SASPA_ACT_GEGLU) return 256;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N % 160 == 0 && N % 256 != 0) return 160;
+  if (N <= 128) return 128;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  // general: minimise padded columns, prefer the wider tile
+  int best = 256, best_waste = (ceil_div(N, 256) * 256 - N);
+  const int cands[3] = {160, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int waste = ceil_div(N, cands[i]) * cands[i] - N;
+    if (waste < best_waste) {
+      best = cands[i];
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+
+int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p, cudaStream_t stream) {
+  switch (bn) {
+    case 32: return launch<32>(a0, a1, b, p, stream);
+    case 64: return launch<64>(a0, a1, b, p, stream);
+    case 128: return launch<128>(a0, a1, b, p, stream);
+    case 160: return launch<160>(a0, a1, b, p, stream);
+    case 256: return launch<256>(a0, a1, b, p, stream);
+  }
+  saspa_set_error("internal: no kernel for BN=%d", bn);
+  return SASPA_ERR_UNSUPPORTED;
+}
+
+int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
+  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0};
+  if (!ep) ep = &kDefault;
+  p.bias = ep->bias;
+  p.row_bias = ep->row_bias;
+  p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+  p.act = ep->act;
+  p.alpha = ep->alpha;
+  p.residual = static_cast<const __nv_bfloat16*>(ep->residual);
+  p.ld_res = ep->ld_res;
+  p.beta = ep->beta;
+  p.out_fp32 = ep->out_fp32;
+  p.D = D;
+  p.ldd = ldd;
+  p.n_out = (ep->act == SASPA_ACT_GEGLU) ? N / 2 : N;
+  SASPA_CHECK_ARG(ep->act >= SASPA_ACT_NONE && ep->act <= SASPA_ACT_GEGLU, "epilogue: unknown activation %d", ep->act);
+  SASPA_CHECK_ARG(!(ep->act == SASPA_ACT_GEGLU && (N % 256 != 0)), "GEGLU epilogue needs N %% 256 == 0 (tile-interleaved weights), got %d", N);
+  SASPA_CHECK_ARG(!(ep->act == SASPA_ACT_GEGLU && ep->row_bias), "GEGLU epilogue does not take a row_bias");
+  const int esz = ep->out_fp32 ? 4 : 2;
+  bool vec = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && (((size_t)ldd * esz) % 16 == 0);
+  if (ep->residual) vec = vec && ((reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0) && (ep->ld_res % 8 == 0);
+  if (ep->bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0);
+  if (ep->row_bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0) && (N % 4 == 0);
+  p.vec_ok = vec ? 1 : 0;
+  // the float4 bias loads assume 16-byte aligned bias pointers; fall back is per-element only when n+3 >= N
+  SASPA_CHECK_ARG(!ep->bias || (reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "epilogue: bias must be 16-byte aligned");
+  SASPA_CHECK_ARG(!ep->row_bias || ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0 && N % 4 == 0),
+                  "epilogue: row_bias must be 16-byte aligned with N %% 4 == 0");
+  return SASPA_OK;
+}
+
+}  // namespace
+
+extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
+                               const saspa_epilogue* ep, cudaStream_t stream) {
+  SASPA_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "saspa_gemm_bf16: negative dims");
+  if (M == 0 || N == 0) return SASPA_OK;
+  SASPA_CHECK_ARG(A && B && D, "saspa_gemm_bf16: null pointer");
+  SASPA_CHECK_ARG(K > 0, "saspa_gemm_bf16: K must be positive");
+  SASPA_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "saspa_gemm_bf16: lda/ldb must be >= K and multiples of 8 (lda=%d ldb=%d K=%d)", lda, ldb, K);
+  SASPA_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0, "saspa_gemm_bf16: A/B must be 16-byte aligned");
+  GemmParams p = {};
+  int rc = fill_epilogue(p, ep, N, D, ldd);
+  if (rc) return rc;
+  const int bn = pick_bn(N, p.act);
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.mode = 0;
+  p.num_m_tiles = ceil_div(M, BM);
+  p.num_n_tiles = ceil_div(N, bn);
+  CUtensorMap tmA, tmB;
+  if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
+  if ((rc = encode_2d(&tmB, B, N, K, ldb, bn))) return rc;
+  return dispatch(bn, tmA, tmA, tmB, p, stream);
+}
+
+extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int h, int w,
+                                       const void* weight, int ksize, void* out, int ldo, int cout, const saspa_epilogue* ep,
+                                       cudaStream_t stream) {
+  SASPA_CHECK_ARG(n >= 0 && h >= 0 && w >= 0 && cout >= 0, "saspa_conv2d_igemm_bf16: negative dims");
+  if (n == 0 || h == 0 || w == 0 || cout == 0) return SASPA_OK;
+  SASPA_CHECK_ARG(x0 && weight && out, "saspa_conv2d_igemm_bf16: null pointer");
+  SASPA_CHECK_ARG(ksize == 1 || ksize == 3, "saspa_conv2d_igemm_bf16: ksize must be 1 or 3, got %d", ksize);
+  if (!x1) c1 = 0;
+  SASPA_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0, "saspa_conv2d_igemm_bf16: channel counts must be multiples of 8 (c0=%d c1=%d)", c0, c1);
+  SASPA_CHECK_ARG(c1 == 0 || c0 % BK == 0, "saspa_conv2d_igemm_bf16: c0 must be a multiple of 64 when a second source is given (c0=%d)", c0);
+  SASPA_CHECK_ARG(ldx0 % 8 == 0 && ldx0 >= c0 && (c1 == 0 || (ldx1 % 8 == 0 && ldx1 >= c1)), "saspa_conv2d_igemm_bf16: bad pixel strides");
+  SASPA_CHECK_ARG((reinterpret_cast<uintptr_t>(x0) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                      (c1 == 0 || (reinterpret_cast<uintptr_t>(x1) & 15) == 0),
+                  "saspa_conv2d_igemm_bf16: 16-byte alignment required");
+  GemmParams p = {};
+  int rc = fill_epilogue(p, ep, cout, out, ldo);
+  if (rc) return rc;
+  const int bn_tile = pick_bn(cout, p.act);
+  // M tile = bw x bh x bnimg = 128 output pixels; minimise padded work, tie-break towards square tiles.
+  int best_bw = 0, best_bh = 0, best_bi = 0;
+  long long best_cost = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    int bh = 128 / bw;
+    int bi = 1;
+    // shrink bh to the image height (power of two) and spill into the batch dimension
+    while (bh > 1 && bh / 2 >= h) {
+      bh >>= 1;
+      bi <<= 1;
+    }
+    if (bw > 1 && bw / 2 >= w) continue;  // a narrower box covers the row just as well
+    long long cost = (long long)ceil_div(w, bw) * bw * ceil_div(h, bh) * bh * ceil_div(n, bi) * bi;
+    long long halo = (long long)(bw + 2) * (bh + 2);  // L2 traffic proxy
+    long long score = cost * 1024 + halo;
+    if (best_cost < 0 || score < best_cost) {
+      best_cost = score;
+      best_bw = bw;
+      best_bh = bh;
+      best_bi = bi;
+    }
+  }
+  p.mode = 1;
+  p.n_img = n;
+  p.H = h;
+  p.W = w;
+  p.c0 = c0;
+  p.c1 = c1;
+  p.ksize = ksize;
+  p.bw = best_bw;
+  p.bh = best_bh;
+  p.bn = best_bi;
+  p.tiles_x = ceil_div(w, p.bw);
+  p.tiles_y = ceil_div(h, p.bh);
+  const int tiles_n = ceil_div(n, p.bn);
+  p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+  p.num_n_tiles = ceil_div(cout, bn_tile);
+  p.N = cout;
+  p.K = ksize * ksize * (c0 + c1);
+  p.M = n * h * w;
+  CUtensorMap tmA0, tmA1, tmB;
+  if ((rc = encode_nhwc(&tmA0, x0, n, h, w, c0, ldx0, p.bn, p.bh, p.bw))) return rc;
+  if (c1 > 0) {
+    if ((rc = encode_nhwc(&tmA1, x1, n, h, w, c1, ldx1, p.bn, p.bh, p.bw))) return rc;
+  } else {
+    tmA1 = tmA0;
+  }
+  if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile))) return rc;
+  return dispatch(bn_tile, tmA0, tmA1, tmB, p, stream);
+}

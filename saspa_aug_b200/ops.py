@@ -1,0 +1,438 @@
+"""Thin torch-tensor wrappers over the C ABI (include/saspa_b200.h).
+
+torch is plumbing only: it owns device memory and the current stream.  Every function
+here enqueues hand-written sm_100a kernels from libsaspa_b200.so on
+``torch.cuda.current_stream()`` and raises ``SaspaError`` on failure -- there is no
+eager/PyTorch fallback.  ``LAUNCHES`` counts kernel launches issued through this module
+(bench.py reports it as ``gpu_launches``)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_SILU, Epilogue, LinComb, SaspaError, check
+
+LAUNCHES = 0  # kernels launched via this module (host-side count)
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise SaspaError("saspa_aug_b200.ops: tensors must live on a CUDA device (no CPU fallback exists)")
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+# ------------------------------------------------------------------------------------------------
+# Canny
+# ------------------------------------------------------------------------------------------------
+def canny(img: torch.Tensor, low: int, high: int, out_channels: int = 1, want_ctrl: bool = False):
+    """img u8 [n,h,w,c] (c in {1,3}) -> (edges u8 [n,h,w] or [n,h,w,3], ctrl bf16 [n,h,w,3] | None)."""
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.dim() == 4 and img.is_contiguous()
+    n, h, w, c = img.shape
+    lib = _lib.load()
+    ws_bytes = lib.saspa_canny_workspace_bytes(n, h, w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+    shape = (n, h, w) if out_channels == 1 else (n, h, w, out_channels)
+    out = torch.empty(shape, dtype=torch.uint8, device=img.device)
+    ctrl = torch.empty((n, h, w, 3), dtype=BF16, device=img.device) if want_ctrl else None
+    check(
+        lib.saspa_canny_u8(_ptr(img), n, h, w, c, int(low), int(high), _ptr(out), out_channels, _ptr(ctrl), _ptr(ws), ws_bytes, _stream()),
+        "saspa_canny_u8",
+    )
+    _count(3)
+    return out, ctrl
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM / conv
+# ------------------------------------------------------------------------------------------------
+def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alpha=1.0, residual=None, ld_res=0, beta=1.0, out_fp32=False):
+    ep = Epilogue()
+    ep.bias = _ptr(bias)
+    ep.row_bias = _ptr(row_bias)
+    ep.rows_per_group = int(rows_per_group)
+    ep.act = int(act)
+    ep.alpha = float(alpha)
+    ep.residual = _ptr(residual)
+    ep.ld_res = int(ld_res) if residual is not None else 0
+    ep.beta = float(beta)
+    ep.out_fp32 = 1 if out_fp32 else 0
+    return ep
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, row_bias=None, rows_per_group=1,
+         act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False) -> torch.Tensor:
+    """out[M,N'] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 2-D views with unit inner stride."""
+    _need_cuda(a, b)
+    assert a.dtype == BF16 and b.dtype == BF16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    assert out.stride(1) == 1 and out.shape == (M, n_out)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.stride(1) == 1 and residual.shape == (M, n_out)
+    ep = make_epilogue(bias, row_bias, rows_per_group, act, alpha, residual, residual.stride(0) if residual is not None else 0, beta,
+                       out.dtype == torch.float32)
+    check(
+        _lib.load().saspa_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, ctypes.byref(ep), _stream()),
+        "saspa_gemm_bf16",
+    )
+    _count()
+    return out
+
+
+def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optional[torch.Tensor] = None, *, x1: Optional[torch.Tensor] = None,
+                 bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False) -> torch.Tensor:
+    """Stride-1 same-padded conv on NHWC bf16 views [n,h,w,c] (channel stride 1, dense n/h/w strides);
+    weight bf16 [cout, ksize*ksize*(c0+c1)]."""
+    _need_cuda(x, weight)
+    n, h, w, c0 = x.shape
+    assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    c1 = 0
+    if x1 is not None:
+        assert x1.shape[:3] == x.shape[:3] and x1.stride(3) == 1 and x1.stride(1) == w * x1.stride(2) and x1.stride(0) == h * x1.stride(1)
+        c1 = x1.shape[3]
+    cout = weight.shape[0]
+    assert weight.dtype == BF16 and weight.is_contiguous() and weight.shape[1] == ksize * ksize * (c0 + c1)
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.float32 if out_fp32 else BF16, device=x.device)
+    assert out.stride(3) == 1 and out.stride(1) == w * out.stride(2) and out.stride(0) == h * out.stride(1)
+    ld_res = 0
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == w * residual.stride(2)
+        ld_res = residual.stride(2)
+    ep = make_epilogue(bias, row_bias, h * w, act, alpha, residual, ld_res, beta, out.dtype == torch.float32)
+    check(
+        _lib.load().saspa_conv2d_igemm_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
+                                            _ptr(weight), ksize, _ptr(out), out.stride(2), cout, ctypes.byref(ep), _stream()),
+        "saspa_conv2d_igemm_bf16",
+    )
+    _count()
+    return out
+
+
+def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, oh: int, ow: int, kpad: int) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    cols = torch.empty((n * oh * ow, kpad), dtype=BF16, device=x.device)
+    check(
+        _lib.load().saspa_im2col_bf16(_ptr(x), x.stride(2), n, h, w, c, kh, kw, stride, pad_top, pad_left, oh, ow, _ptr(cols), kpad, _stream()),
+        "saspa_im2col_bf16",
+    )
+    _count()
+    return cols
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / elementwise
+# ------------------------------------------------------------------------------------------------
+def groupnorm(x: torch.Tensor, groups: int, eps: float, gamma, beta, act=ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [n, hw, c] view (channel stride 1, dense hw) -> same shape."""
+    _need_cuda(x)
+    n, hw, c = x.shape
+    assert x.dtype == BF16 and x.stride(2) == 1 and x.stride(0) == hw * x.stride(1)
+    if out is None:
+        out = torch.empty((n, hw, c), dtype=BF16, device=x.device)
+    assert out.stride(2) == 1 and out.stride(0) == hw * out.stride(1)
+    ws = torch.empty(2 * n * groups, dtype=torch.float64, device=x.device)
+    check(
+        _lib.load().saspa_groupnorm_nhwc_bf16(_ptr(x), x.stride(1), n, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta), int(act), _ptr(out),
+                                              out.stride(1), _ptr(ws), _stream()),
+        "saspa_groupnorm_nhwc_bf16",
+    )
+    _count(3)
+    return out
+
+
+def layernorm(x: torch.Tensor, eps: float, gamma, beta, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    rows, c = x.shape
+    assert x.dtype == BF16 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((rows, c), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_layernorm_bf16(_ptr(x), x.stride(0), rows, c, float(eps), _ptr(gamma), _ptr(beta), _ptr(out), out.stride(0), _stream()),
+          "saspa_layernorm_bf16")
+    _count()
+    return out
+
+
+def act(x: torch.Tensor, kind: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().saspa_act_bf16(_ptr(x), _ptr(out), x.numel(), int(kind), _stream()), "saspa_act_bf16")
+    _count()
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(a, b)
+    rows, c = a.shape
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1 and b.shape == a.shape
+    if out is None:
+        out = torch.empty((rows, c), dtype=BF16, device=a.device)
+    check(_lib.load().saspa_add_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), rows, c, _stream()), "saspa_add_bf16")
+    _count()
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_upsample_nearest2x_bf16(_ptr(x), n, h, w, c, _ptr(y), _stream()), "saspa_upsample_nearest2x_bf16")
+    _count()
+    return y
+
+
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None, pad_c: Optional[int] = None) -> torch.Tensor:
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        cc = pad_c or c
+        out = torch.zeros((n, h, w, cc), dtype=BF16, device=x.device) if cc != c else torch.empty((n, h, w, c), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_nchw_f32_to_nhwc_bf16(_ptr(x), n, c, h, w, _ptr(out), out.stride(2), float(scale), _stream()), "saspa_nchw_f32_to_nhwc_bf16")
+    _count()
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, cc = x.shape
+    c = c or cc
+    assert x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.load().saspa_nhwc_to_nchw_f32(_ptr(x), x.stride(2), 1 if x.dtype == torch.float32 else 0, n, c, h, w, _ptr(y), _stream()),
+          "saspa_nhwc_to_nchw_f32")
+    _count()
+    return y
+
+
+def pool2d(x: torch.Tensor, k: int, stride: int, pad: int, is_max: bool) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    assert x.dtype == BF16 and x.is_contiguous()
+    oh = (h + 2 * pad - k) // stride + 1
+    ow = (w + 2 * pad - k) // stride + 1
+    y = torch.empty((n, oh, ow, c), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_pool2d_nhwc_bf16(_ptr(x), n, h, w, c, k, stride, pad, 1 if is_max else 0, _ptr(y), oh, ow, _stream()), "saspa_pool2d_nhwc_bf16")
+    _count()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
+    """q [b,tq,heads*d], k/v [b,tkv,heads*d] bf16 views (inner stride 1, dense token stride) -> [b,tq,heads*d]."""
+    _need_cuda(q, k, v)
+    b, tq, hd = q.shape
+    tkv = k.shape[1]
+    d = hd // heads
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert q.stride(0) == tq * q.stride(1) and k.stride(0) == tkv * k.stride(1) and v.stride(0) == tkv * v.stride(1)
+    if scale is None:
+        scale = d ** -0.5
+    if out is None:
+        out = torch.empty((b, tq, hd), dtype=BF16, device=q.device)
+    assert out.stride(2) == 1 and out.stride(0) == tq * out.stride(1)
+    check(
+        _lib.load().saspa_attention_bf16(_ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(out), out.stride(1), b, heads, tq,
+                                         tkv, d, float(scale), _stream()),
+        "saspa_attention_bf16",
+    )
+    _count()
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    rows, cols = x.shape
+    assert x.dtype == BF16 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_softmax_rows_bf16(_ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, cols, float(scale), _stream()), "saspa_softmax_rows_bf16")
+    _count()
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """x bf16 [batch, rows, cols] (inner stride 1) -> contiguous [batch, cols, rows]."""
+    _need_cuda(x)
+    b, rows, cols = x.shape
+    assert x.dtype == BF16 and x.stride(2) == 1
+    y = torch.empty((b, cols, rows), dtype=BF16, device=x.device)
+    check(_lib.load().saspa_transpose_bf16(_ptr(x), x.stride(1), x.stride(0), _ptr(y), rows, cols * rows, b, rows, cols, _stream()), "saspa_transpose_bf16")
+    _count()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# denoising-loop glue
+# ------------------------------------------------------------------------------------------------
+def timestep_sinusoid(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0) -> torch.Tensor:
+    _need_cuda(t)
+    assert t.dtype == torch.float32 and t.dim() == 1
+    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    check(_lib.load().saspa_timestep_sinusoid_bf16(_ptr(t), t.shape[0], dim, 1 if flip_sin_to_cos else 0, float(freq_shift), _ptr(out), _stream()),
+          "saspa_timestep_sinusoid_bf16")
+    _count()
+    return out
+
+
+def cfg_sched_step(eps_uncond, eps_cond, guidance: float, inputs, outputs, coef) -> None:
+    """outputs[j] = sum_i coef[j][i] * in_i with in = [x, cfg(eps), *history]; ``inputs`` = [x, None, hist...]
+    (slot 1 is the CFG-combined eps, produced inside the kernel)."""
+    _need_cuda(eps_cond)
+    lc = LinComb()
+    n_in, n_out = len(inputs), len(outputs)
+    assert 2 <= n_in <= 8 and 1 <= n_out <= 4 and len(coef) == n_out and all(len(r) == n_in for r in coef)
+    count = eps_cond.numel()
+    for i, t in enumerate(inputs):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == count
+        lc.inp[i] = _ptr(t)
+    for j, t in enumerate(outputs):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == count
+        lc.out[j] = _ptr(t)
+    for j in range(n_out):
+        for i in range(n_in):
+            lc.coef[j * n_in + i] = float(coef[j][i])
+    lc.n_in, lc.n_out = n_in, n_out
+    assert eps_cond.dtype == torch.float32 and eps_cond.is_contiguous()
+    if eps_uncond is not None:
+        assert eps_uncond.dtype == torch.float32 and eps_uncond.is_contiguous() and eps_uncond.numel() == count
+    check(_lib.load().saspa_cfg_sched_step(_ptr(eps_uncond), _ptr(eps_cond), float(guidance), ctypes.byref(lc), count, _stream()), "saspa_cfg_sched_step")
+    _count()
+
+
+def vae_quantize_u8(x: torch.Tensor) -> torch.Tensor:
+    """x [n,h,w,c>=3] (bf16|fp32, channel stride 1) -> u8 [n,h,w,3]."""
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.load().saspa_vae_quantize_u8(_ptr(x), x.stride(2), 1 if x.dtype == torch.float32 else 0, n * h * w, _ptr(out), _stream()), "saspa_vae_quantize_u8")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# filter side
+# ------------------------------------------------------------------------------------------------
+_COEFF_CACHE: dict = {}
+
+
+def _pil_coeffs(in_size: int, out_size: int, filt: int, device):
+    key = (in_size, out_size, filt, str(device))
+    if key not in _COEFF_CACHE:
+        lib = _lib.load()
+        ks = lib.saspa_pil_ksize(in_size, out_size, filt)
+        bounds = (ctypes.c_int32 * (2 * out_size))()
+        coeffs = (ctypes.c_int32 * (ks * out_size))()
+        kso = ctypes.c_int(0)
+        check(lib.saspa_pil_coeffs_host(in_size, out_size, filt, ctypes.byref(kso), bounds, coeffs, ks * out_size), "saspa_pil_coeffs_host")
+        b = torch.tensor(list(bounds), dtype=torch.int32).to(device)
+        c = torch.tensor(list(coeffs), dtype=torch.int32).to(device)
+        _COEFF_CACHE[key] = (b, c, kso.value)
+    return _COEFF_CACHE[key]
+
+
+def resize_pil(img: torch.Tensor, out_h: int, out_w: int, filt: str) -> torch.Tensor:
+    """img u8 [n,h,w,c] -> u8 [n,out_h,out_w,c]; bit-exact PIL Image.resize(bilinear|bicubic)."""
+    _need_cuda(img)
+    n, h, w, c = img.shape
+    assert img.dtype == torch.uint8 and img.is_contiguous()
+    f = {"bilinear": 0, "bicubic": 1}[filt]
+    bx, cx, kx = _pil_coeffs(w, out_w, f, img.device)
+    by, cy, ky = _pil_coeffs(h, out_h, f, img.device)
+    tmp = torch.empty((n, h, out_w, c), dtype=torch.uint8, device=img.device)
+    out = torch.empty((n, out_h, out_w, c), dtype=torch.uint8, device=img.device)
+    check(_lib.load().saspa_resize_pil_u8(_ptr(img), n, h, w, c, _ptr(tmp), _ptr(out), out_h, out_w, _ptr(bx), _ptr(cx), kx, _ptr(by), _ptr(cy), ky, _stream()),
+          "saspa_resize_pil_u8")
+    _count(2)
+    return out
+
+
+def crop_normalize(img: torch.Tensor, crop_y: int, crop_x: int, crop_h: int, crop_w: int, mean, std, out_c: int = 8) -> torch.Tensor:
+    _need_cuda(img)
+    n, h, w, c = img.shape
+    assert img.dtype == torch.uint8 and c == 3 and img.is_contiguous()
+    out = torch.empty((n, crop_h, crop_w, out_c), dtype=BF16, device=img.device)
+    check(_lib.load().saspa_crop_normalize_bf16(_ptr(img), n, h, w, crop_y, crop_x, crop_h, crop_w, *[float(m) for m in mean], *[float(s) for s in std],
+                                                _ptr(out), out_c, _stream()), "saspa_crop_normalize_bf16")
+    _count()
+    return out
+
+
+def bap_head(feat: torch.Tensor, att: torch.Tensor) -> torch.Tensor:
+    """feat bf16 [n,hw,c], att bf16 [n,hw,m] -> fp32 [n, m*c] (sign-sqrt, L2-normalised, x100)."""
+    _need_cuda(feat, att)
+    n, hw, c = feat.shape
+    m = att.shape[2]
+    assert feat.stride(2) == 1 and att.stride(2) == 1 and feat.stride(0) == hw * feat.stride(1) and att.stride(0) == hw * att.stride(1)
+    fm = torch.empty((n, m * c), dtype=torch.float32, device=feat.device)
+    sq = torch.empty((n,), dtype=torch.float32, device=feat.device)
+    check(_lib.load().saspa_bap_head(_ptr(feat), feat.stride(1), _ptr(att), att.stride(1), n, hw, c, m, _ptr(fm), _ptr(sq), _stream()), "saspa_bap_head")
+    _count(3)
+    return fm
+
+
+def fc_f32(x: torch.Tensor, w: torch.Tensor, bias) -> torch.Tensor:
+    _need_cuda(x, w)
+    n, k = x.shape
+    classes = w.shape[0]
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous() and w.shape[1] == k
+    out = torch.empty((n, classes), dtype=torch.float32, device=x.device)
+    check(_lib.load().saspa_fc_f32(_ptr(x), _ptr(w), _ptr(bias), n, k, classes, _ptr(out), _stream()), "saspa_fc_f32")
+    _count((n + 7) // 8)
+    return out
+
+
+def topk_contains(logits: torch.Tensor, labels: torch.Tensor, k: int):
+    _need_cuda(logits, labels)
+    n, classes = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int32
+    keep = torch.empty((n,), dtype=torch.uint8, device=logits.device)
+    margin = torch.empty((n,), dtype=torch.float32, device=logits.device)
+    check(_lib.load().saspa_topk_contains(_ptr(logits), n, classes, _ptr(labels), int(k), _ptr(keep), _ptr(margin), _stream()), "saspa_topk_contains")
+    _count()
+    return keep, margin
+
+
+def clip_score_argmax(img: torch.Tensor, txt: torch.Tensor, logit_scale: float):
+    _need_cuda(img, txt)
+    n, d = img.shape
+    p = txt.shape[0]
+    assert img.dtype == torch.float32 and txt.dtype == torch.float32 and img.is_contiguous() and txt.is_contiguous()
+    logits = torch.empty((n, p), dtype=torch.float32, device=img.device)
+    arg = torch.empty((n,), dtype=torch.int32, device=img.device)
+    check(_lib.load().saspa_clip_score_argmax(_ptr(img), _ptr(txt), n, p, d, float(logit_scale), _ptr(logits), _ptr(arg), _stream()), "saspa_clip_score_argmax")
+    _count()
+    return logits, arg
