@@ -1,0 +1,54 @@
+"""GPU parity: fused attention vs torch fp32 softmax(QK^T/sqrt(d))V on the same bf16 inputs.
+Tolerance 2e-2 absolute on outputs of O(1) magnitude (P is rounded to bf16 before the PV product)."""
+import pytest
+import torch
+
+from saspa_aug_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _ref(q, k, v, heads, scale=None):
+    b, tq, hd = q.shape
+    d = hd // heads
+    qf, kf, vf = (t.float().view(b, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * (scale if scale is not None else d ** -0.5)
+    return (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(b, tq, hd)
+
+
+@pytest.mark.parametrize("cfg", [  # b, heads, tq, tkv, d
+    (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (4, 8, 256, 256, 160), (4, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80),
+    (3, 8, 256, 77, 160), (2, 8, 64, 77, 160), (2, 12, 77, 77, 64), (1, 8, 5632, 5632, 40), (2, 5, 100, 131, 64), (2, 16, 257, 257, 64),
+    (7, 8, 50, 50, 64), (2, 4, 200, 200, 128)])
+def test_attention(cuda_device, cfg):
+    b, heads, tq, tkv, d = cfg
+    q, k, v = _rand((b, tq, heads * d), 1), _rand((b, tkv, heads * d), 2), _rand((b, tkv, heads * d), 3)
+    got = ops.attention(q, k, v, heads)
+    ref = _ref(q, k, v, heads)
+    err = (got.float() - ref).abs().max().item()
+    assert torch.isfinite(got.float()).all() and err < 2e-2, err
+
+
+def test_attention_fused_qkv_view_and_peaked_scores(cuda_device):
+    b, t, heads, d = 2, 1024, 8, 80
+    qkv = _rand((b, t, 3 * heads * d), 4, 3.0)  # large logits -> peaked softmax
+    q, k, v = qkv[..., : heads * d], qkv[..., heads * d : 2 * heads * d], qkv[..., 2 * heads * d :]
+    out = torch.zeros((b, t, 2 * heads * d), dtype=torch.bfloat16, device="cuda")
+    ops.attention(q, k, v, heads, out=out[..., : heads * d])
+    ref = _ref(q, k, v, heads)
+    assert (out[..., : heads * d].float() - ref).abs().max().item() < 6e-2
+    assert out[..., heads * d :].abs().max() == 0
+
+
+def test_softmax_rows_and_transpose(cuda_device):
+    x = _rand((300, 4096), 5, 4.0)
+    got = ops.softmax_rows(x, 0.044)
+    ref = torch.softmax(x.float() * 0.044, dim=-1)
+    assert (got.float() - ref).abs().max().item() < 2e-3
+    t = _rand((3, 100, 72), 6)
+    assert torch.equal(ops.transpose(t), t.transpose(1, 2).contiguous())

@@ -1,0 +1,119 @@
+"""GPU parity for the HBM-bound glue kernels vs plain PyTorch fp32 references (tolerances: bf16 rounding)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from saspa_aug_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0, shift=0.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale + shift).to(torch.bfloat16).cuda()
+
+
+def _close(got, ref, atol, rtol=1e-2):
+    got = got.float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    assert not bad.any(), f"max err {err.max().item():.4g} at {int(bad.sum())} elements"
+
+
+@pytest.mark.parametrize("cfg", [(2, 4096, 320, 1e-5), (3, 1024, 640, 1e-5), (2, 256, 1280, 1e-6), (2, 64, 2560, 1e-5), (2, 1024, 1920, 1e-5),
+                                 (2, 1024, 960, 1e-5), (1, 16384, 128, 1e-6), (5, 77, 512, 1e-6), (2, 100, 256, 1e-6)])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_SILU])
+def test_groupnorm(cuda_device, cfg, act):
+    n, hw, c, eps = cfg
+    x = _rand((n, hw, c), 1, 2.0, 0.7)
+    gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    got = ops.groupnorm(x, 32, eps, gamma, beta, act)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps)
+    if act == ops.ACT_SILU:
+        ref = F.silu(ref)
+    _close(got, ref.permute(0, 2, 1), 2e-2)
+
+
+def test_groupnorm_strided_into_concat_buffer(cuda_device):
+    n, hw, c = 2, 256, 640
+    buf = _rand((n, hw, 1920), 2)
+    x = buf[:, :, 1280:]
+    out = torch.zeros((n, hw, 960), dtype=torch.bfloat16, device="cuda")
+    ops.groupnorm(x, 32, 1e-5, None, None, ops.ACT_NONE, out=out[:, :, :640])
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, None, None, 1e-5).permute(0, 2, 1)
+    _close(out[:, :, :640], ref, 2e-2)
+    assert out[:, :, 640:].abs().max() == 0
+
+
+@pytest.mark.parametrize("rc", [(8192, 320), (2048, 640), (512, 1280), (154, 768), (77, 512), (10, 1024), (33, 2048)])
+def test_layernorm(cuda_device, rc):
+    rows, c = rc
+    x = _rand((rows, c), 3, 3.0, -0.5)
+    gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    got = ops.layernorm(x, 1e-5, gamma, beta)
+    _close(got, F.layer_norm(x.float(), (c,), gamma, beta, 1e-5), 2e-2)
+
+
+def test_act_add_upsample_pool(cuda_device):
+    x = _rand((3, 16, 16, 64), 4)
+    _close(ops.act(x, ops.ACT_SILU), F.silu(x.float()), 1e-2)
+    _close(ops.act(x, ops.ACT_GELU), F.gelu(x.float()), 1e-2)
+    y = _rand((3 * 256, 64), 5)
+    _close(ops.add(x.view(-1, 64), y), x.view(-1, 64).float() + y.float(), 2e-2)
+    up = ops.upsample_nearest2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    x2 = _rand((2, 112, 112, 64), 6)
+    mp = ops.pool2d(x2, 3, 2, 1, True)
+    assert torch.equal(mp.float(), F.max_pool2d(x2.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+    ap = ops.pool2d(x2, 2, 2, 0, False)
+    _close(ap, F.avg_pool2d(x2.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1), 1e-2)
+
+
+def test_latent_layout_casts(cuda_device):
+    x = torch.randn(3, 4, 64, 64, device="cuda")
+    y = ops.nchw_f32_to_nhwc_bf16(x, scale=0.5, pad_c=8)
+    assert y.shape == (3, 64, 64, 8)
+    assert torch.equal(y[..., :4].float(), (x * 0.5).to(torch.bfloat16).float().permute(0, 2, 3, 1))
+    assert y[..., 4:].abs().max() == 0
+    z = torch.randn(3, 64, 64, 8, device="cuda")
+    back = ops.nhwc_to_nchw_f32(z, c=4)
+    assert torch.equal(back, z[..., :4].permute(0, 3, 1, 2).contiguous())
+
+
+def test_timestep_sinusoid(cuda_device):
+    t = torch.tensor([941.0, 1.0, 500.0, 48.0], device="cuda")
+    got = ops.timestep_sinusoid(t, 320, True, 0.0)
+    half = 160
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    arg = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)
+    _close(got, ref, 1e-2)
+
+
+def test_cfg_sched_step(cuda_device):
+    n = 3 * 4 * 64 * 64
+    x, eu, ec, h0 = (torch.randn(n, device="cuda") for _ in range(4))
+    o0, o1 = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    coef = [[0.9, -0.3, 0.1], [0.0, 1.0, 0.0]]
+    ops.cfg_sched_step(eu, ec, 7.5, [x, None, h0], [o0, o1], coef)
+    e = eu + 7.5 * (ec - eu)
+    assert torch.allclose(o0, 0.9 * x - 0.3 * e + 0.1 * h0, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(o1, e, atol=1e-6)
+    ops.cfg_sched_step(None, ec, 0.0, [x, None], [o0], [[1.0, 2.0]])
+    assert torch.allclose(o0, x + 2 * ec, atol=1e-6)
+
+
+def test_vae_quantize(cuda_device):
+    x = torch.randn(2, 32, 32, 8, device="cuda") * 0.8
+    x[0, 0, 0, :3] = torch.tensor([0.0, 1 / 255.0 - 1.0, 3.0])  # exact .5 tie, in-range, clamp
+    got = ops.vae_quantize_u8(x)
+    ref = np.round((x[..., :3] / 2 + 0.5).clamp(0, 1).cpu().numpy() * 255).astype(np.uint8)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    xb = x.to(torch.bfloat16)
+    refb = np.round((xb[..., :3].float() / 2 + 0.5).clamp(0, 1).cpu().numpy() * 255).astype(np.uint8)
+    assert np.array_equal(ops.vae_quantize_u8(xb).cpu().numpy(), refb)

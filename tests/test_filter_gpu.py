@@ -1,0 +1,78 @@
+"""GPU parity for the filter-side kernels: bit-exact PIL resize (integer), heads vs torch fp32."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import clib
+from saspa_aug_b200 import ops
+from saspa_aug_b200.synthetic import synthetic_source
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_resize_pil_bit_exact_vs_oracle_and_golden(cuda_device):
+    gold = json.load(open(os.path.join(G, "resize_golden.json")))
+    for rec in gold["cases"][:6]:
+        img = synthetic_source(rec["seed"], rec["h"], rec["w"], rec["kind"])
+        t = torch.from_numpy(img[None]).cuda()
+        a = ops.resize_pil(t, 256, 256, "bilinear")[0].cpu().numpy()
+        assert hashlib.sha256(a.tobytes()).hexdigest() == rec["bilinear_256"]["sha256"]
+        sh = rec["bicubic_224"]["shape"]
+        b = ops.resize_pil(t, sh[0], sh[1], "bicubic")[0].cpu().numpy()
+        assert hashlib.sha256(b.tobytes()).hexdigest() == rec["bicubic_224"]["sha256"]
+    imgs = np.stack([synthetic_source(s, 300, 200, "noise") for s in range(3)])
+    got = ops.resize_pil(torch.from_numpy(imgs).cuda(), 224, 150, "bicubic").cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], clib.pil_resize(imgs[i], 224, 150, "bicubic"))
+    up = ops.resize_pil(torch.from_numpy(imgs).cuda(), 600, 640, "bilinear").cpu().numpy()
+    assert np.array_equal(up[1], clib.pil_resize(imgs[1], 600, 640, "bilinear"))
+
+
+def test_crop_normalize(cuda_device):
+    img = torch.from_numpy(np.stack([synthetic_source(s, 256, 256, "noise") for s in range(2)])).cuda()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    got = ops.crop_normalize(img, 16, 16, 224, 224, mean, std, out_c=8)
+    x = img[:, 16:240, 16:240].float() / 255.0
+    ref = ((x - torch.tensor(mean, device="cuda")) / torch.tensor(std, device="cuda")).to(torch.bfloat16)
+    assert torch.equal(got[..., :3], ref) and got[..., 3:].abs().max() == 0
+
+
+def test_bap_fc_topk(cuda_device):
+    n, hw, c, m, classes = 5, 196, 2048, 32, 100
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn((n, hw, c), generator=g).relu().to(torch.bfloat16).cuda()
+    att = torch.randn((n, hw, m), generator=g).relu().to(torch.bfloat16).cuda()
+    fm = ops.bap_head(feat, att)
+    p = torch.einsum("nhm,nhc->nmc", att.float(), feat.float()) / hw
+    p = torch.sign(p) * torch.sqrt(p.abs() + 1e-6)
+    ref = F.normalize(p.reshape(n, -1), dim=-1) * 100.0
+    assert (fm - ref).abs().max().item() < 1e-3
+    w = torch.randn((classes, m * c), generator=g).cuda() * 0.01
+    b = torch.randn(classes, generator=g).cuda()
+    logits = ops.fc_f32(fm, w, b)
+    refl = fm @ w.t() + b
+    assert (logits - refl).abs().max().item() < 1e-2
+    labels = torch.tensor([3, 50, 99, 0, 7], dtype=torch.int32, device="cuda")
+    keep, margin = ops.topk_contains(logits, labels, 10)
+    top = logits.topk(10)[1]
+    refk = torch.tensor([int(labels[i].item() in top[i].tolist()) for i in range(n)], dtype=torch.uint8, device="cuda")
+    assert torch.equal(keep, refk)
+    # ties: equal logits -> lower index wins, as torch.topk
+    tie = torch.zeros((2, 20), device="cuda")
+    k2, _ = ops.topk_contains(tie, torch.tensor([9, 10], dtype=torch.int32, device="cuda"), 10)
+    assert k2.tolist() == [1, 0]
+
+
+def test_clip_score_argmax(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    img, txt = torch.randn((33, 1024), generator=g).cuda(), torch.randn((7, 1024), generator=g).cuda()
+    logits, arg = ops.clip_score_argmax(img, txt, 100.0)
+    ref = 100.0 * F.normalize(img, dim=-1) @ F.normalize(txt, dim=-1).t()
+    assert (logits - ref).abs().max().item() < 1e-3
+    assert torch.equal(arg.long(), ref.argmax(-1))
