@@ -82,9 +82,10 @@ int saspa_crop_normalize_bf16(const uint8_t* img, int n, int h, int w, int crop_
  *
  * Epilogue (applied in this order, per output element (row r, col j)):
  *     v = acc + bias[j] + row_bias[r / rows_per_group, j]
- *     v = act(v)                       (SASPA_ACT_*)
+ *     v = act(v)                       (SASPA_ACT_*; skipped here when act_after_residual)
  *     GEGLU: out col j pairs value col j with gate col j + BN/2 of the same tile: v = val * gelu(gate)
  *     v = alpha * v + beta * residual[r, j]
+ *     v = act(v)                       (only when act_after_residual)
  *     out[r, j] = (bf16 | fp32) v
  * ------------------------------------------------------------------------------------------ */
 enum { SASPA_ACT_NONE = 0, SASPA_ACT_SILU = 1, SASPA_ACT_GELU = 2, SASPA_ACT_RELU = 3, SASPA_ACT_QUICKGELU = 4, SASPA_ACT_GEGLU = 5 };
@@ -93,12 +94,15 @@ typedef struct saspa_epilogue {
   const float* bias;       /* [N] or NULL */
   const float* row_bias;   /* [groups, N] or NULL: e.g. the per-image time-embedding projection */
   int rows_per_group;      /* rows (pixels) per row_bias group; ignored when row_bias is NULL */
+  int ld_row_bias;         /* row stride of row_bias in elements (0 -> N): lets one GEMM produce the time-embedding
+                              projections of every ResnetBlock and each conv read its column slice */
   int act;                 /* SASPA_ACT_* */
   float alpha;             /* scale on the activated value (1/output_scale_factor, conditioning_scale, ...) */
   const void* residual;    /* bf16 [M, ld_res] or NULL */
   int ld_res;
   float beta;              /* scale on the residual */
   int out_fp32;            /* 0: bf16 output, 1: fp32 output */
+  int act_after_residual;  /* 0: act before the residual add (diffusers blocks); 1: after it (ResNet bottleneck ReLU) */
 } saspa_epilogue;
 
 /* D[M,N] = epilogue(A[M,K] . B[N,K]^T).  A, B bf16 row-major (K contiguous); lda/ldb/ldd in elements,
@@ -152,7 +156,7 @@ int saspa_pool2d_nhwc_bf16(const void* x, int n, int h, int w, int c, int k, int
  * Replaces F.scaled_dot_product_attention under diffusers' AttnProcessor2_0.
  * ------------------------------------------------------------------------------------------ */
 int saspa_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch,
-                         int heads, int tq, int tkv, int d, float scale, cudaStream_t stream);
+                         int heads, int tq, int tkv, int d, float scale, int causal /* CLIP text tower */, cudaStream_t stream);
 
 /* Row softmax y = softmax(x * scale) (bf16, fp32 math) and batched 2-D transpose: the d = 512 single-head VAE
  * mid-block attention (diffusers models/autoencoders/vae.py UNetMidBlock2D) runs GEMM -> softmax -> GEMM. */

@@ -24,12 +24,14 @@ class Epilogue(Structure):
         ("bias", c_void_p),
         ("row_bias", c_void_p),
         ("rows_per_group", c_int),
+        ("ld_row_bias", c_int),
         ("act", c_int),
         ("alpha", c_float),
         ("residual", c_void_p),
         ("ld_res", c_int),
         ("beta", c_float),
         ("out_fp32", c_int),
+        ("act_after_residual", c_int),
     ]
 
 
@@ -80,7 +82,7 @@ SIGNATURES = {
     "saspa_pool2d_nhwc_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "saspa_attention_bf16": (
         c_int,
-        [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P],
+        [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P],
     ),
     "saspa_softmax_rows_bf16": (c_int, [_P, c_int, _P, c_int, ctypes.c_longlong, c_int, c_float, _P]),
     "saspa_transpose_bf16": (c_int, [_P, c_int, ctypes.c_longlong, _P, c_int, ctypes.c_longlong, c_int, c_int, c_int, _P]),

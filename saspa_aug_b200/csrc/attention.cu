@@ -61,7 +61,7 @@ template <int DP>
 __global__ void __launch_bounds__(ATT_THREADS) flash_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k,
                                                                   int ldk, const __nv_bfloat16* __restrict__ v, int ldv,
                                                                   __nv_bfloat16* __restrict__ o, int ldo, int heads, int tq, int tkv, int d,
-                                                                  float scale_log2) {
+                                                                  float scale_log2, int causal) {
   constexpr int ROWB = DP * 2 + 16;
   constexpr int KS = DP / 16;  // k-steps over the head dim
   constexpr int NT = DP / 8;   // n-tiles of the output
@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_attn_kernel(const __nv_bflo
   load_tile<DP>(reinterpret_cast<__nv_bfloat16*>(sV), vg, ldv, min(BKV, tkv), d, tid);
   cp_async_commit();
 
-  const int n_iter = (tkv + BKV - 1) / BKV;
+  int n_iter = (tkv + BKV - 1) / BKV;
+  if (causal) n_iter = min(n_iter, (min(q0 + BQ, tq) + BKV - 1) / BKV);  // keys beyond the last query row are masked
   uint32_t qf[KS][4];
   float oacc[NT][4];
 #pragma unroll
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_attn_kernel(const __nv_bflo
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         int key = kv0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-        float sv = (key < tkv) ? sacc[nt][e] * scale_log2 : -INFINITY;
+        bool ok = key < tkv;
+        if (causal) ok = ok && (key <= q0 + warp * 16 + (lane >> 2) + (e >> 1) * 8);
+        float sv = ok ? sacc[nt][e] * scale_log2 : -INFINITY;
         sacc[nt][e] = sv;
         mx[e >> 1] = fmaxf(mx[e >> 1], sv);
       }
@@ -153,15 +156,17 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_attn_kernel(const __nv_bflo
       float m_new = fmaxf(m_run[r], mx[r]);
       corr[r] = (m_run[r] == -INFINITY) ? 0.0f : exp2f(m_run[r] - m_new);
       m_run[r] = m_new;
+      if (m_new == -INFINITY) m_new = 0.0f;  // fully masked so far (padding rows): keep exp2 arguments finite
     }
     float rs[2] = {0.0f, 0.0f};
     uint32_t pf[4][4];  // P as A-fragments for 4 k-steps of 16 keys
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      float p0 = exp2f(sacc[nt][0] - m_run[0]);
-      float p1 = exp2f(sacc[nt][1] - m_run[0]);
-      float p2 = exp2f(sacc[nt][2] - m_run[1]);
-      float p3 = exp2f(sacc[nt][3] - m_run[1]);
+      const float mr0 = (m_run[0] == -INFINITY) ? 0.0f : m_run[0], mr1 = (m_run[1] == -INFINITY) ? 0.0f : m_run[1];
+      float p0 = exp2f(sacc[nt][0] - mr0);
+      float p1 = exp2f(sacc[nt][1] - mr0);
+      float p2 = exp2f(sacc[nt][2] - mr1);
+      float p3 = exp2f(sacc[nt][3] - mr1);
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_attn_kernel(const __nv_bflo
 
 template <int DP>
 int launch_flash(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq,
-                 int tkv, int d, float scale, cudaStream_t stream) {
+                 int tkv, int d, float scale, int causal, cudaStream_t stream) {
   constexpr int ROWB = DP * 2 + 16;
   constexpr int SMEM = 5 * 64 * ROWB;
   static bool configured = false;
@@ -226,7 +231,7 @@ int launch_flash(const void* q, int ldq, const void* k, int ldk, const void* v, 
   dim3 grid(ceil_div(tq, BQ), batch * heads);
   flash_attn_kernel<DP><<<grid, ATT_THREADS, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
                                                              static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(o), ldo, heads,
-                                                             tq, tkv, d, scale * 1.4426950408889634f);
+                                                             tq, tkv, d, scale * 1.4426950408889634f, causal);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }
@@ -286,7 +291,7 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ x, long long 
 }  // namespace
 
 extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch,
-                                    int heads, int tq, int tkv, int d, float scale, cudaStream_t stream) {
+                                    int heads, int tq, int tkv, int d, float scale, int causal, cudaStream_t stream) {
   SASPA_CHECK_ARG(batch >= 0 && heads > 0 && tq >= 0 && tkv > 0 && d > 0, "saspa_attention_bf16: bad shape");
   SASPA_CHECK_ARG(d % 8 == 0 && d <= 160, "saspa_attention_bf16: head_dim must be a multiple of 8 and <= 160 (got %d); d=512 runs as GEMM-softmax-GEMM", d);
   SASPA_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "saspa_attention_bf16: row strides must be multiples of 8");
@@ -296,11 +301,11 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
                       (reinterpret_cast<uintptr_t>(o) & 3) == 0,
                   "saspa_attention_bf16: q/k/v must be 16-byte aligned");
   SASPA_CHECK_ARG((long long)batch * heads <= 65535, "saspa_attention_bf16: batch*heads must be <= 65535");
-  if (d <= 48) return launch_flash<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
-  if (d <= 64) return launch_flash<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
-  if (d <= 80) return launch_flash<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
-  if (d <= 128) return launch_flash<128>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
-  return launch_flash<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+  if (d <= 48) return launch_flash<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
+  if (d <= 64) return launch_flash<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
+  if (d <= 80) return launch_flash<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
+  if (d <= 128) return launch_flash<128>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
+  return launch_flash<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
 }
 
 extern "C" int saspa_softmax_rows_bf16(const void* x, int ldx, void* y, int ldy, long long rows, int cols, float scale, cudaStream_t stream) {

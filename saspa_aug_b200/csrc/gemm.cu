@@ -43,7 +43,9 @@ struct GemmParams {
   const float* bias;
   const float* row_bias;
   int rows_per_group;
+  int ld_row_bias;
   int act;
+  int act_post;
   float alpha;
   const __nv_bfloat16* residual;
   int ld_res;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         } else {
           if (p.row_bias && row_ok) {
-            const float* rb = p.row_bias + (size_t)group * p.N;
+            const float* rb = p.row_bias + (size_t)group * p.ld_row_bias;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               int n = col_base_in + c0 + j;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               }
             }
           }
-          if (p.act != SASPA_ACT_NONE) {
+          if (p.act != SASPA_ACT_NONE && !p.act_post) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
           }
@@ -396,6 +398,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             for (int j = 0; j < 32; ++j)
               if (n0 + j < p.n_out) f[j] += p.beta * __bfloat162float(rp[j]);
           }
+        }
+        if (p.act_post) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
         }
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.D) + (size_t)pix * p.ldd + n0;
@@ -550,12 +556,14 @@ int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
 }
 
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
-  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0};
+  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0};
   if (!ep) ep = &kDefault;
   p.bias = ep->bias;
   p.row_bias = ep->row_bias;
   p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+  p.ld_row_bias = ep->ld_row_bias > 0 ? ep->ld_row_bias : N;
   p.act = ep->act;
+  p.act_post = (ep->act_after_residual && ep->act != SASPA_ACT_GEGLU) ? 1 : 0;
   p.alpha = ep->alpha;
   p.residual = static_cast<const __nv_bfloat16*>(ep->residual);
   p.ld_res = ep->ld_res;
@@ -571,12 +579,12 @@ int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int l
   bool vec = ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && (((size_t)ldd * esz) % 16 == 0);
   if (ep->residual) vec = vec && ((reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0) && (ep->ld_res % 8 == 0);
   if (ep->bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0);
-  if (ep->row_bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0) && (N % 4 == 0);
+  if (ep->row_bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0) && (N % 4 == 0) && (p.ld_row_bias % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
   // the float4 bias loads assume 16-byte aligned bias pointers; fall back is per-element only when n+3 >= N
   SASPA_CHECK_ARG(!ep->bias || (reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "epilogue: bias must be 16-byte aligned");
-  SASPA_CHECK_ARG(!ep->row_bias || ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0 && N % 4 == 0),
-                  "epilogue: row_bias must be 16-byte aligned with N %% 4 == 0");
+  SASPA_CHECK_ARG(!ep->row_bias || ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0 && N % 4 == 0 && p.ld_row_bias % 4 == 0),
+                  "epilogue: row_bias must be 16-byte aligned with N %% 4 == 0 and ld_row_bias %% 4 == 0");
   return SASPA_OK;
 }
 

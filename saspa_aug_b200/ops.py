@@ -64,11 +64,14 @@ def canny(img: torch.Tensor, low: int, high: int, out_channels: int = 1, want_ct
 # ------------------------------------------------------------------------------------------------
 # GEMM / conv
 # ------------------------------------------------------------------------------------------------
-def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alpha=1.0, residual=None, ld_res=0, beta=1.0, out_fp32=False):
+def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alpha=1.0, residual=None, ld_res=0, beta=1.0, out_fp32=False,
+                  act_after_residual=False):
     ep = Epilogue()
     ep.bias = _ptr(bias)
     ep.row_bias = _ptr(row_bias)
     ep.rows_per_group = int(rows_per_group)
+    ep.ld_row_bias = int(row_bias.stride(0)) if row_bias is not None else 0
+    ep.act_after_residual = 1 if act_after_residual else 0
     ep.act = int(act)
     ep.alpha = float(alpha)
     ep.residual = _ptr(residual)
@@ -79,7 +82,7 @@ def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alph
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, row_bias=None, rows_per_group=1,
-         act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False) -> torch.Tensor:
+         act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False) -> torch.Tensor:
     """out[M,N'] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 2-D views with unit inner stride."""
     _need_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.dim() == 2 and b.dim() == 2
@@ -94,7 +97,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(1) == 1 and residual.shape == (M, n_out)
     ep = make_epilogue(bias, row_bias, rows_per_group, act, alpha, residual, residual.stride(0) if residual is not None else 0, beta,
-                       out.dtype == torch.float32)
+                       out.dtype == torch.float32, act_after_residual)
     check(
         _lib.load().saspa_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, ctypes.byref(ep), _stream()),
         "saspa_gemm_bf16",
@@ -104,7 +107,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optional[torch.Tensor] = None, *, x1: Optional[torch.Tensor] = None,
-                 bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False) -> torch.Tensor:
+                 bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False) -> torch.Tensor:
     """Stride-1 same-padded conv on NHWC bf16 views [n,h,w,c] (channel stride 1, dense n/h/w strides);
     weight bf16 [cout, ksize*ksize*(c0+c1)]."""
     _need_cuda(x, weight)
@@ -123,7 +126,7 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == w * residual.stride(2)
         ld_res = residual.stride(2)
-    ep = make_epilogue(bias, row_bias, h * w, act, alpha, residual, ld_res, beta, out.dtype == torch.float32)
+    ep = make_epilogue(bias, row_bias, h * w, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual)
     check(
         _lib.load().saspa_conv2d_igemm_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
                                             _ptr(weight), ksize, _ptr(out), out.stride(2), cout, ctypes.byref(ep), _stream()),
@@ -249,7 +252,8 @@ def pool2d(x: torch.Tensor, k: int, stride: int, pad: int, is_max: bool) -> torc
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+              causal: bool = False):
     """q [b,tq,heads*d], k/v [b,tkv,heads*d] bf16 views (inner stride 1, dense token stride) -> [b,tq,heads*d]."""
     _need_cuda(q, k, v)
     b, tq, hd = q.shape
@@ -264,7 +268,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     assert out.stride(2) == 1 and out.stride(0) == tq * out.stride(1)
     check(
         _lib.load().saspa_attention_bf16(_ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(out), out.stride(1), b, heads, tq,
-                                         tkv, d, float(scale), _stream()),
+                                         tkv, d, float(scale), 1 if causal else 0, _stream()),
         "saspa_attention_bf16",
     )
     _count()
