@@ -185,6 +185,13 @@ typedef struct saspa_lincomb {
 } saspa_lincomb;
 int saspa_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc_host, size_t count,
                          cudaStream_t stream);
+/* img2img start (diffusers prepare_latents of StableDiffusionControlNetImg2ImgPipeline): posterior sample of the VAE
+ * encoder moments (fp32 NHWC [n,h,w,2*lc]: mean | logvar) times scaling_factor, then scheduler.add_noise:
+ *   z0 = (mean + exp(0.5*clamp(logvar,-30,20)) * noise_posterior) * scaling;  latents = alpha*z0 + sigma*noise_diffusion
+ * noises / latents / z0_out (optional) are fp32 NCHW [n,lc,h,w]. */
+int saspa_vae_sample_add_noise(const float* moments, const float* noise_posterior, const float* noise_diffusion, float scaling,
+                               float alpha, float sigma, int n, int h, int w, int latent_channels, float* latents, float* z0_out,
+                               cudaStream_t stream);
 /* VAE postprocess (diffusers VaeImageProcessor.postprocess): u8 = round_half_even(clamp(x/2+0.5,0,1)*255).
  * x bf16 or fp32 NHWC [pixels, ldx] (first 3 channels) -> u8 [pixels,3]. */
 int saspa_vae_quantize_u8(const void* x, int ldx, int x_is_fp32, size_t pixels, uint8_t* out, cudaStream_t stream);

@@ -332,11 +332,11 @@ class _Encoder(nn.Module):
         if not torch.is_tensor(t):
             t = torch.tensor([t], dtype=torch.float32, device=sample.device)
         t = t.reshape(-1).expand(sample.shape[0]).float()
-        emb = self.time_embedding(get_timestep_embedding(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift))
+        emb = self.time_embedding(get_timestep_embedding(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift).to(sample.dtype))
         if cfg.addition_embed_type == "text_time":
             text_embeds, time_ids = added_cond["text_embeds"], added_cond["time_ids"]
             tid = get_timestep_embedding(time_ids.flatten(), cfg.addition_time_embed_dim, cfg.flip_sin_to_cos, cfg.freq_shift)
-            tid = tid.reshape(text_embeds.shape[0], -1)
+            tid = tid.reshape(text_embeds.shape[0], -1).to(sample.dtype)
             emb = emb + self.add_embedding(torch.cat([text_embeds, tid], dim=-1))
         return emb
 

@@ -1,0 +1,315 @@
+"""Model configs + diffusers/transformers-keyed state dicts.
+
+The reference builds its pipelines with ``from_pretrained`` of public HF repos (run_aug/run_aug.py:53-72,
+:184-211).  No checkpoints, tokenizer vocabularies or network exist in this environment, so benchmarks and
+parity tests use deterministic, variance-preserving RANDOM weights with the exact key names / shapes of
+those checkpoints; a real ``*.safetensors`` state dict can be passed to the same
+model constructors unchanged.  ``*_shapes`` enumerate (key, shape) from the config; tests load the generated
+dict into the oracle modules with ``strict=True``, which cross-checks the two enumerations.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Iterator, Optional, Tuple
+
+import torch
+
+
+@dataclass
+class UNetConfig:
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    down_block_types: Tuple[str, ...] = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D")
+    up_block_types: Tuple[str, ...] = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D")
+    layers_per_block: int = 2
+    transformer_layers_per_block: Tuple[int, ...] = (1, 1, 1, 1)
+    num_attention_heads: Tuple[int, ...] = (8, 8, 8, 8)
+    cross_attention_dim: int = 768
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    use_linear_projection: bool = False
+    flip_sin_to_cos: bool = True
+    freq_shift: float = 0.0
+    addition_embed_type: Optional[str] = None
+    addition_time_embed_dim: int = 256
+    projection_class_embeddings_input_dim: int = 2816
+    conditioning_embedding_out_channels: Tuple[int, ...] = (16, 32, 96, 256)
+
+    @staticmethod
+    def sd15() -> "UNetConfig":  # runwayml/stable-diffusion-v1-5, lllyasviel/control_v11p_sd15_canny
+        return UNetConfig()
+
+    @staticmethod
+    def sdxl() -> "UNetConfig":  # stabilityai/sdxl-turbo, diffusers/controlnet-canny-sdxl-1.0
+        return UNetConfig(block_out_channels=(320, 640, 1280), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                          up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"), transformer_layers_per_block=(1, 2, 10),
+                          num_attention_heads=(5, 10, 20), cross_attention_dim=2048, use_linear_projection=True, addition_embed_type="text_time")
+
+    @staticmethod
+    def tiny(cross_attention_dim: int = 64) -> "UNetConfig":
+        return UNetConfig(block_out_channels=(64, 128, 128, 128), num_attention_heads=(4, 4, 4, 4), cross_attention_dim=cross_attention_dim,
+                          conditioning_embedding_out_channels=(16, 32, 32, 64))
+
+
+@dataclass
+class VAEConfig:
+    in_channels: int = 3
+    out_channels: int = 3
+    latent_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    scaling_factor: float = 0.18215
+
+    @staticmethod
+    def sd15() -> "VAEConfig":
+        return VAEConfig()
+
+    @staticmethod
+    def sdxl() -> "VAEConfig":  # madebyollin/sdxl-vae-fp16-fix (run_aug/run_aug.py:189)
+        return VAEConfig(scaling_factor=0.13025)
+
+    @staticmethod
+    def tiny() -> "VAEConfig":
+        return VAEConfig(block_out_channels=(32, 64, 64, 64))
+
+
+@dataclass
+class CLIPTextConfig:
+    vocab_size: int = 49408
+    hidden_size: int = 768
+    intermediate_size: int = 3072
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    max_position_embeddings: int = 77
+    hidden_act: str = "quick_gelu"
+    layer_norm_eps: float = 1e-5
+
+    @staticmethod
+    def sd15() -> "CLIPTextConfig":  # openai/clip-vit-large-patch14 text tower
+        return CLIPTextConfig()
+
+    @staticmethod
+    def tiny() -> "CLIPTextConfig":
+        return CLIPTextConfig(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4)
+
+
+Shapes = Iterator[Tuple[str, Tuple[int, ...]]]
+
+
+def _conv(p, cin, cout, k=3) -> Shapes:
+    yield p + ".weight", (cout, cin, k, k)
+    yield p + ".bias", (cout,)
+
+
+def _lin(p, cin, cout, bias=True) -> Shapes:
+    yield p + ".weight", (cout, cin)
+    if bias:
+        yield p + ".bias", (cout,)
+
+
+def _norm(p, c) -> Shapes:
+    yield p + ".weight", (c,)
+    yield p + ".bias", (c,)
+
+
+def _resnet(p, cin, cout, temb) -> Shapes:
+    yield from _norm(p + ".norm1", cin)
+    yield from _conv(p + ".conv1", cin, cout)
+    if temb:
+        yield from _lin(p + ".time_emb_proj", temb, cout)
+    yield from _norm(p + ".norm2", cout)
+    yield from _conv(p + ".conv2", cout, cout)
+    if cin != cout:
+        yield from _conv(p + ".conv_shortcut", cin, cout, 1)
+
+
+def _transformer(p, c, depth, cross, linear) -> Shapes:
+    yield from _norm(p + ".norm", c)
+    if linear:
+        yield from _lin(p + ".proj_in", c, c)
+    else:
+        yield from _conv(p + ".proj_in", c, c, 1)
+    for i in range(depth):
+        q = f"{p}.transformer_blocks.{i}"
+        yield from _norm(q + ".norm1", c)
+        for nm, kin in (("attn1", c), ("attn2", cross)):
+            yield from _lin(f"{q}.{nm}.to_q", c, c, False)
+            yield from _lin(f"{q}.{nm}.to_k", kin, c, False)
+            yield from _lin(f"{q}.{nm}.to_v", kin, c, False)
+            yield from _lin(f"{q}.{nm}.to_out.0", c, c)
+            if nm == "attn1":
+                yield from _norm(q + ".norm2", c)
+        yield from _norm(q + ".norm3", c)
+        yield from _lin(q + ".ff.net.0.proj", c, 8 * c)
+        yield from _lin(q + ".ff.net.2", 4 * c, c)
+    if linear:
+        yield from _lin(p + ".proj_out", c, c)
+    else:
+        yield from _conv(p + ".proj_out", c, c, 1)
+
+
+def _encoder_shapes(cfg: UNetConfig) -> Shapes:
+    c0 = cfg.block_out_channels[0]
+    temb = 4 * c0
+    yield from _conv("conv_in", cfg.in_channels, c0)
+    yield from _lin("time_embedding.linear_1", c0, temb)
+    yield from _lin("time_embedding.linear_2", temb, temb)
+    if cfg.addition_embed_type == "text_time":
+        yield from _lin("add_embedding.linear_1", cfg.projection_class_embeddings_input_dim, temb)
+        yield from _lin("add_embedding.linear_2", temb, temb)
+    cout = c0
+    n = len(cfg.block_out_channels)
+    for i, t in enumerate(cfg.down_block_types):
+        cin, cout = cout, cfg.block_out_channels[i]
+        for j in range(cfg.layers_per_block):
+            yield from _resnet(f"down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, temb)
+            if t.startswith("CrossAttn"):
+                yield from _transformer(f"down_blocks.{i}.attentions.{j}", cout, cfg.transformer_layers_per_block[i], cfg.cross_attention_dim,
+                                        cfg.use_linear_projection)
+        if i != n - 1:
+            yield from _conv(f"down_blocks.{i}.downsamplers.0.conv", cout, cout)
+    cm = cfg.block_out_channels[-1]
+    yield from _resnet("mid_block.resnets.0", cm, cm, temb)
+    yield from _transformer("mid_block.attentions.0", cm, cfg.transformer_layers_per_block[-1], cfg.cross_attention_dim, cfg.use_linear_projection)
+    yield from _resnet("mid_block.resnets.1", cm, cm, temb)
+
+
+def unet_shapes(cfg: UNetConfig) -> Shapes:
+    yield from _encoder_shapes(cfg)
+    temb = 4 * cfg.block_out_channels[0]
+    rev = list(reversed(cfg.block_out_channels))
+    rev_depth = list(reversed(cfg.transformer_layers_per_block))
+    n = len(rev)
+    cout = rev[0]
+    for i, t in enumerate(cfg.up_block_types):
+        prev, cout = cout, rev[i]
+        cin = rev[min(i + 1, n - 1)]
+        L = cfg.layers_per_block + 1
+        for j in range(L):
+            skip = cin if j == L - 1 else cout
+            rin = prev if j == 0 else cout
+            yield from _resnet(f"up_blocks.{i}.resnets.{j}", rin + skip, cout, temb)
+            if t.startswith("CrossAttn"):
+                yield from _transformer(f"up_blocks.{i}.attentions.{j}", cout, rev_depth[i], cfg.cross_attention_dim, cfg.use_linear_projection)
+        if i != n - 1:
+            yield from _conv(f"up_blocks.{i}.upsamplers.0.conv", cout, cout)
+    yield from _norm("conv_norm_out", cfg.block_out_channels[0])
+    yield from _conv("conv_out", cfg.block_out_channels[0], cfg.out_channels)
+
+
+def controlnet_shapes(cfg: UNetConfig) -> Shapes:
+    yield from _encoder_shapes(cfg)
+    bo = cfg.conditioning_embedding_out_channels
+    p = "controlnet_cond_embedding"
+    yield from _conv(p + ".conv_in", 3, bo[0])
+    for i in range(len(bo) - 1):
+        yield from _conv(f"{p}.blocks.{2 * i}", bo[i], bo[i])
+        yield from _conv(f"{p}.blocks.{2 * i + 1}", bo[i], bo[i + 1])
+    yield from _conv(p + ".conv_out", bo[-1], cfg.block_out_channels[0])
+    chans = [cfg.block_out_channels[0]]
+    n = len(cfg.block_out_channels)
+    for i, c in enumerate(cfg.block_out_channels):
+        chans += [c] * cfg.layers_per_block
+        if i != n - 1:
+            chans.append(c)
+    for i, c in enumerate(chans):
+        yield from _conv(f"controlnet_down_blocks.{i}", c, c, 1)
+    yield from _conv("controlnet_mid_block", cfg.block_out_channels[-1], cfg.block_out_channels[-1], 1)
+
+
+def _vae_mid(p, c) -> Shapes:
+    yield from _resnet(p + ".resnets.0", c, c, None)
+    a = p + ".attentions.0"
+    yield from _norm(a + ".group_norm", c)
+    for nm in ("to_q", "to_k", "to_v", "to_out.0"):
+        yield from _lin(f"{a}.{nm}", c, c)
+    yield from _resnet(p + ".resnets.1", c, c, None)
+
+
+def vae_shapes(cfg: VAEConfig) -> Shapes:
+    ch = cfg.block_out_channels
+    yield from _conv("encoder.conv_in", cfg.in_channels, ch[0])
+    cout = ch[0]
+    for i, c in enumerate(ch):
+        cin, cout = cout, c
+        for j in range(cfg.layers_per_block):
+            yield from _resnet(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, None)
+        if i != len(ch) - 1:
+            yield from _conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout)
+    yield from _vae_mid("encoder.mid_block", ch[-1])
+    yield from _norm("encoder.conv_norm_out", ch[-1])
+    yield from _conv("encoder.conv_out", ch[-1], 2 * cfg.latent_channels)
+    yield from _conv("quant_conv", 2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+    yield from _conv("post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+    rev = list(reversed(ch))
+    yield from _conv("decoder.conv_in", cfg.latent_channels, rev[0])
+    yield from _vae_mid("decoder.mid_block", rev[0])
+    cout = rev[0]
+    for i, c in enumerate(rev):
+        cin, cout = cout, c
+        for j in range(cfg.layers_per_block + 1):
+            yield from _resnet(f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, None)
+        if i != len(rev) - 1:
+            yield from _conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout)
+    yield from _norm("decoder.conv_norm_out", rev[-1])
+    yield from _conv("decoder.conv_out", rev[-1], cfg.out_channels)
+
+
+def clip_text_shapes(cfg: CLIPTextConfig) -> Shapes:
+    p = "text_model."
+    yield p + "embeddings.token_embedding.weight", (cfg.vocab_size, cfg.hidden_size)
+    yield p + "embeddings.position_embedding.weight", (cfg.max_position_embeddings, cfg.hidden_size)
+    for i in range(cfg.num_hidden_layers):
+        q = f"{p}encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield from _lin(q + "self_attn." + nm, cfg.hidden_size, cfg.hidden_size)
+        yield from _norm(q + "layer_norm1", cfg.hidden_size)
+        yield from _lin(q + "mlp.fc1", cfg.hidden_size, cfg.intermediate_size)
+        yield from _lin(q + "mlp.fc2", cfg.intermediate_size, cfg.hidden_size)
+        yield from _norm(q + "layer_norm2", cfg.hidden_size)
+    yield from _norm(p + "final_layer_norm", cfg.hidden_size)
+
+
+_RESIDUAL_OUT = ("conv2.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight", "out_proj.weight", "mlp.fc2.weight", "conv3.weight", "c_proj.weight")
+_ZERO_CONV = ("controlnet_down_blocks", "controlnet_mid_block", "controlnet_cond_embedding.conv_out")
+
+
+def random_state_dict(shapes: Shapes, seed: int, zero_conv_std: float = 0.02, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Deterministic variance-preserving init: weights ~ N(0, 1/fan_in) (x 1/sqrt2 on residual-branch
+    output layers), norm scales ~ N(1, .05), biases / norm shifts ~ N(0, .02), embeddings ~ N(0, .02);
+    ControlNet zero-convs are NON-zero (std 0.02) so the residual-injection path is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in shapes:
+        if len(shape) >= 2:
+            if "embedding.weight" in name:
+                std = 0.02
+            else:
+                fan_in = 1
+                for s in shape[1:]:
+                    fan_in *= s
+                std = 1.0 / math.sqrt(fan_in)
+                if name.endswith(_RESIDUAL_OUT):
+                    std /= math.sqrt(2.0)
+                if any(z in name for z in _ZERO_CONV):
+                    std = zero_conv_std
+            t = torch.randn(shape, generator=g) * std
+        elif "norm" in name and name.endswith("weight"):
+            t = 1.0 + 0.05 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        sd[name] = t.to(dtype)
+    return sd
+
+
+def count_params(shapes: Shapes) -> int:
+    tot = 0
+    for _, s in shapes:
+        n = 1
+        for d in s:
+            n *= d
+        tot += n
+    return tot

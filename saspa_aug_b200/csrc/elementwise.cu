@@ -392,6 +392,26 @@ __global__ void cfg_sched_kernel(const float* __restrict__ eu, const float* __re
   }
 }
 
+// img2img start: z0 = (mean + exp(0.5*clamp(logvar,-30,20)) * n_post) * scaling ; latents = a * z0 + s * n_diff
+// moments fp32 NHWC [n,h,w,8] (mean 0:4, logvar 4:8); noises / latents fp32 NCHW [n,4,h,w].
+__global__ void vae_sample_kernel(const float* __restrict__ moments, const float* __restrict__ n_post, const float* __restrict__ n_diff,
+                                  float scaling, float a, float s, int n, int h, int w, int lc, float* __restrict__ latents,
+                                  float* __restrict__ z0_out) {
+  const long long total = (long long)n * lc * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long sp = i % ((long long)h * w);
+    long long t = i / ((long long)h * w);
+    int ch = (int)(t % lc);
+    long long img = t / lc;
+    const float* m = moments + (img * h * w + sp) * (2 * lc);
+    float mean = m[ch];
+    float lv = fminf(fmaxf(m[lc + ch], -30.0f), 20.0f);
+    float z0 = (mean + expf(0.5f * lv) * (n_post ? n_post[i] : 0.0f)) * scaling;
+    if (z0_out) z0_out[i] = z0;
+    latents[i] = a * z0 + s * (n_diff ? n_diff[i] : 0.0f);
+  }
+}
+
 __global__ void vae_quant_kernel(const void* __restrict__ x, int ldx, int is_fp32, size_t pixels, uint8_t* __restrict__ out) {
   const size_t total = pixels * 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -547,6 +567,17 @@ extern "C" int saspa_vae_quantize_u8(const void* x, int ldx, int x_is_fp32, size
   if (pixels == 0) return SASPA_OK;
   SASPA_CHECK_ARG(x && out && ldx >= 3, "saspa_vae_quantize_u8: bad arguments");
   vae_quant_kernel<<<grid_for((long long)pixels * 3, 256), 256, 0, stream>>>(x, ldx, x_is_fp32, pixels, out);
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+
+extern "C" int saspa_vae_sample_add_noise(const float* moments, const float* noise_posterior, const float* noise_diffusion, float scaling,
+                                          float alpha, float sigma, int n, int h, int w, int latent_channels, float* latents, float* z0_out,
+                                          cudaStream_t stream) {
+  if (n <= 0 || h <= 0 || w <= 0) return SASPA_OK;
+  SASPA_CHECK_ARG(moments && latents && latent_channels > 0, "saspa_vae_sample_add_noise: bad arguments");
+  vae_sample_kernel<<<grid_for((long long)n * latent_channels * h * w, 256), 256, 0, stream>>>(moments, noise_posterior, noise_diffusion, scaling, alpha,
+                                                                                             sigma, n, h, w, latent_channels, latents, z0_out);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }

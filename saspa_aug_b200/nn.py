@@ -1,0 +1,562 @@
+"""Model graphs of the denoising path as launch lists over the sm_100a kernels (saspa_aug_b200.ops).
+
+Host-side mirror of the diffusers modules the reference drives through ``pipe(**pipe_args)``
+(run_aug/run_aug.py:278; built at :184-211): UNet2DConditionModel, ControlNetModel, AutoencoderKL,
+CLIPTextModel.  Weights come from a diffusers-keyed state dict and are re-laid out once
+(conv OIHW -> [Cout, kh*kw*Cin] bf16 K-major, fused QKV, tile-interleaved GEGLU).  Activations are NHWC
+bf16; everything below is kernel launches on the current stream -- CUDA-graph capturable, no torch math.
+
+B200-first choices (vs. the diffusers graph):
+  * skip connections are never concatenated: producers write straight into the channel slice of the
+    consumer's concat buffer (all kernels take row strides);
+  * ControlNet residuals are accumulated into the UNet skip tensors by the zero-conv GEMM epilogue
+    (alpha = conditioning_scale, beta = 1) -- the UNet encoder + mid run first, then the ControlNet;
+  * every ResnetBlock time-embedding projection of a model is ONE GEMM per step; each conv1 reads its
+    column slice as a per-image row bias in the epilogue;
+  * the step-invariant work is hoisted: ControlNet conditioning embedding and the cross-attention K/V
+    projections of the text are computed once per image, not once per step.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .layout import conv_weight_kmajor, geglu_interleave
+from .ops import ACT_GEGLU, ACT_NONE, ACT_QUICKGELU, ACT_SILU, BF16
+
+SD = Dict[str, torch.Tensor]
+
+
+def _f32(t, dev):
+    return None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _bf(t, dev):
+    return t.detach().to(device=dev, dtype=BF16).contiguous()
+
+
+def pix2d(x: torch.Tensor) -> torch.Tensor:
+    """NHWC view [n,h,w,c] with dense pixel strides -> 2-D [n*h*w, c] view (row stride = pixel stride)."""
+    n, h, w, c = x.shape
+    return x.as_strided((n * h * w, c), (x.stride(2), 1))
+
+
+def pix3d(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    return x.as_strided((n, h * w, c), (x.stride(0), x.stride(2), 1))
+
+
+class Conv:
+    """Conv2d.  Stride-1 same-padded 1x1/3x3 with Cin % 8 == 0 run as TMA implicit GEMM; everything else
+    (stride 2, Cin in {3,4}, 7x7 stems, asymmetric padding) as im2col + GEMM."""
+
+    def __init__(self, sd: SD, prefix: str, dev, stride: int = 1, padding: Optional[int] = None, weight=None, bias=None):
+        w = sd[prefix + ".weight"] if weight is None else weight
+        b = sd.get(prefix + ".bias") if bias is None else bias
+        if w.dim() == 2:  # Linear used as a 1x1 conv
+            w = w[:, :, None, None]
+        self.cout, self.cin, self.k, _ = w.shape
+        self.stride = stride
+        self.pad = self.k // 2 if padding is None else padding
+        self.bias = _f32(b, dev)
+        self.direct = stride == 1 and self.pad == self.k // 2 and self.k in (1, 3) and self.cin % 8 == 0
+        if self.direct:
+            self.kpad = self.k * self.k * self.cin
+            self.w = _bf(conv_weight_kmajor(w), dev)
+        else:
+            self.kpad = (self.k * self.k * self.cin + 7) // 8 * 8
+            self.w = _bf(conv_weight_kmajor(w, self.kpad), dev)
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, pad_extra_br: int = 0, **epi) -> torch.Tensor:
+        n, h, w, c = x.shape
+        assert c == self.cin, (c, self.cin)
+        if self.direct:
+            return ops.conv2d_igemm(x, self.w, self.k, out=out, bias=self.bias, **epi)
+        oh = (h + 2 * self.pad + pad_extra_br - self.k) // self.stride + 1
+        ow = (w + 2 * self.pad + pad_extra_br - self.k) // self.stride + 1
+        cols = ops.im2col(x, self.k, self.k, self.stride, self.pad, self.pad, oh, ow, self.kpad)
+        if out is None:
+            out = torch.empty((n, oh, ow, self.cout), dtype=torch.float32 if epi.get("out_fp32") else BF16, device=x.device)
+        if "residual" in epi and epi["residual"] is not None:
+            epi["residual"] = pix2d(epi["residual"])
+        if epi.get("row_bias") is not None:
+            epi["rows_per_group"] = oh * ow
+        ops.gemm(cols, self.w, out=pix2d(out), bias=self.bias, **epi)
+        return out
+
+
+class Linear:
+    def __init__(self, sd: SD, prefix: str, dev, weight=None, bias=None):
+        w = sd[prefix + ".weight"] if weight is None else weight
+        b = sd.get(prefix + ".bias") if bias is None else bias
+        self.w = _bf(w, dev)
+        self.bias = _f32(b, dev)
+
+    def __call__(self, x2d: torch.Tensor, out=None, **epi) -> torch.Tensor:
+        return ops.gemm(x2d, self.w, out=out, bias=self.bias, **epi)
+
+
+class Norm:
+    def __init__(self, sd: SD, prefix: str, dev):
+        self.g = _f32(sd[prefix + ".weight"], dev)
+        self.b = _f32(sd[prefix + ".bias"], dev)
+
+
+class ResnetBlock:
+    """diffusers ResnetBlock2D: GN-SiLU-conv3x3 (+time bias) - GN-SiLU-conv3x3 + shortcut."""
+
+    def __init__(self, sd: SD, prefix: str, dev, groups: int, eps: float, temb_registry: Optional[list]):
+        self.groups, self.eps = groups, eps
+        self.norm1 = Norm(sd, prefix + ".norm1", dev)
+        self.conv1 = Conv(sd, prefix + ".conv1", dev)
+        self.norm2 = Norm(sd, prefix + ".norm2", dev)
+        self.conv2 = Conv(sd, prefix + ".conv2", dev)
+        self.shortcut = Conv(sd, prefix + ".conv_shortcut", dev) if prefix + ".conv_shortcut.weight" in sd else None
+        self.temb_slice = None
+        if temb_registry is not None and prefix + ".time_emb_proj.weight" in sd:
+            off = sum(w.shape[0] for w, _ in temb_registry)
+            temb_registry.append((sd[prefix + ".time_emb_proj.weight"], sd[prefix + ".time_emb_proj.bias"]))
+            self.temb_slice = (off, off + self.conv1.cout)
+
+    def __call__(self, x: torch.Tensor, temb_all: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, h, w, cin = x.shape
+        a = ops.groupnorm(pix3d(x), self.groups, self.eps, self.norm1.g, self.norm1.b, ACT_SILU).view(n, h, w, cin)
+        rb = temb_all[:, self.temb_slice[0] : self.temb_slice[1]] if (self.temb_slice is not None and temb_all is not None) else None
+        h1 = self.conv1(a, row_bias=rb)
+        a2 = ops.groupnorm(pix3d(h1), self.groups, self.eps, self.norm2.g, self.norm2.b, ACT_SILU).view(n, h, w, self.conv1.cout)
+        res = self.shortcut(x) if self.shortcut is not None else x
+        return self.conv2(a2, out=out, residual=res, beta=1.0)
+
+
+class TransformerBlock:
+    """diffusers BasicTransformerBlock (self-attn, cross-attn, GEGLU feed-forward; pre-LayerNorm)."""
+
+    def __init__(self, sd: SD, p: str, dev, heads: int):
+        self.heads = heads
+        self.ln1, self.ln2, self.ln3 = Norm(sd, p + ".norm1", dev), Norm(sd, p + ".norm2", dev), Norm(sd, p + ".norm3", dev)
+        self.wqkv = _bf(torch.cat([sd[p + ".attn1.to_q.weight"], sd[p + ".attn1.to_k.weight"], sd[p + ".attn1.to_v.weight"]], 0), dev)
+        self.o1 = Linear(sd, p + ".attn1.to_out.0", dev)
+        self.q2 = Linear(sd, p + ".attn2.to_q", dev)
+        self.wkv2 = _bf(torch.cat([sd[p + ".attn2.to_k.weight"], sd[p + ".attn2.to_v.weight"]], 0), dev)
+        self.o2 = Linear(sd, p + ".attn2.to_out.0", dev)
+        wi, bi = geglu_interleave(sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"])
+        self.ff1 = Linear(sd, "", dev, weight=wi, bias=bi)
+        self.ff2 = Linear(sd, p + ".ff.net.2", dev)
+
+    def text_kv(self, text2d: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Step-invariant K/V projections of the text states [n*77, cross] -> two [n,77,c] views."""
+        kv = ops.gemm(text2d, self.wkv2)
+        c = kv.shape[1] // 2
+        t = kv.shape[0] // n
+        kv3 = kv.view(n, t, 2 * c)
+        return kv3[..., :c], kv3[..., c:]
+
+    def __call__(self, h: torch.Tensor, n: int, kv: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
+        rows, c = h.shape
+        t = rows // n
+        y = ops.layernorm(h, 1e-5, self.ln1.g, self.ln1.b)
+        qkv = ops.gemm(y, self.wqkv).view(n, t, 3 * c)
+        a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads)
+        self.o1(a.view(rows, c), out=h, residual=h, beta=1.0)
+        y = ops.layernorm(h, 1e-5, self.ln2.g, self.ln2.b)
+        q = self.q2(y).view(n, t, c)
+        a = ops.attention(q, kv[0], kv[1], self.heads)
+        self.o2(a.view(rows, c), out=h, residual=h, beta=1.0)
+        y = ops.layernorm(h, 1e-5, self.ln3.g, self.ln3.b)
+        f = self.ff1(y, act=ACT_GEGLU)
+        self.ff2(f, out=h, residual=h, beta=1.0)
+        return h
+
+
+class Transformer2D:
+    def __init__(self, sd: SD, p: str, dev, heads: int, groups: int):
+        self.groups = groups
+        self.norm = Norm(sd, p + ".norm", dev)
+        self.proj_in = Linear(sd, "", dev, weight=sd[p + ".proj_in.weight"].reshape(sd[p + ".proj_in.weight"].shape[0], -1), bias=sd[p + ".proj_in.bias"])
+        self.proj_out = Linear(sd, "", dev, weight=sd[p + ".proj_out.weight"].reshape(sd[p + ".proj_out.weight"].shape[0], -1), bias=sd[p + ".proj_out.bias"])
+        depth = 0
+        while f"{p}.transformer_blocks.{depth}.norm1.weight" in sd:
+            depth += 1
+        self.blocks = [TransformerBlock(sd, f"{p}.transformer_blocks.{i}", dev, heads) for i in range(depth)]
+
+    def text_kv(self, text2d, n):
+        return [b.text_kv(text2d, n) for b in self.blocks]
+
+    def __call__(self, x: torch.Tensor, kvs, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, hh, ww, c = x.shape
+        g = ops.groupnorm(pix3d(x), self.groups, 1e-6, self.norm.g, self.norm.b, ACT_NONE)
+        h = self.proj_in(g.view(n * hh * ww, c))
+        for blk, kv in zip(self.blocks, kvs):
+            h = blk(h, n, kv)
+        if out is None:
+            out = torch.empty((n, hh, ww, c), dtype=BF16, device=x.device)
+        self.proj_out(h, out=pix2d(out), residual=pix2d(x), beta=1.0)
+        return out
+
+
+class Downsample:
+    def __init__(self, sd: SD, p: str, dev, padding: int = 1):
+        self.conv = Conv(sd, p + ".conv", dev, stride=2, padding=padding)
+        self.extra = 1 if padding == 0 else 0  # VAE encoder: F.pad(x, (0,1,0,1)) then valid conv
+
+    def __call__(self, x, out=None):
+        return self.conv(x, out=out, pad_extra_br=self.extra)
+
+
+class Upsample:
+    def __init__(self, sd: SD, p: str, dev):
+        self.conv = Conv(sd, p + ".conv", dev)
+
+    def __call__(self, x, out=None):
+        if not x.is_contiguous():
+            raise ops.SaspaError("Upsample expects a contiguous NHWC tensor")
+        return self.conv(ops.upsample_nearest2x(x), out=out)
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet / ControlNet encoder (shared structure)
+# ------------------------------------------------------------------------------------------------
+class _EncoderBase:
+    def _build_encoder(self, sd: SD, dev, cfg):
+        self.cfg, self.dev = cfg, dev
+        self.temb_registry: list = []
+        g, eps = cfg.norm_num_groups, cfg.norm_eps
+        self.conv_in = Conv(sd, "conv_in", dev)
+        self.t_lin1 = Linear(sd, "time_embedding.linear_1", dev)
+        self.t_lin2 = Linear(sd, "time_embedding.linear_2", dev)
+        self.add_emb = None
+        if cfg.addition_embed_type == "text_time":
+            self.add_emb = (Linear(sd, "add_embedding.linear_1", dev), Linear(sd, "add_embedding.linear_2", dev))
+        self.down = []
+        nlev = len(cfg.block_out_channels)
+        for i, t in enumerate(cfg.down_block_types):
+            blk = {"resnets": [], "attns": [], "down": None}
+            for j in range(cfg.layers_per_block):
+                blk["resnets"].append(ResnetBlock(sd, f"down_blocks.{i}.resnets.{j}", dev, g, eps, self.temb_registry))
+                if t.startswith("CrossAttn"):
+                    blk["attns"].append(Transformer2D(sd, f"down_blocks.{i}.attentions.{j}", dev, cfg.num_attention_heads[i], g))
+            if i != nlev - 1:
+                blk["down"] = Downsample(sd, f"down_blocks.{i}.downsamplers.0", dev)
+            self.down.append(blk)
+        self.mid_res = [ResnetBlock(sd, "mid_block.resnets.0", dev, g, eps, self.temb_registry),
+                        ResnetBlock(sd, "mid_block.resnets.1", dev, g, eps, self.temb_registry)]
+        self.mid_attn = Transformer2D(sd, "mid_block.attentions.0", dev, cfg.num_attention_heads[-1], g)
+
+    def _finish_temb(self, dev):
+        self.temb_w = _bf(torch.cat([w for w, _ in self.temb_registry], 0), dev)
+        self.temb_b = _f32(torch.cat([b for _, b in self.temb_registry], 0), dev)
+
+    def skip_channels(self) -> List[Tuple[int, int]]:
+        """(channels, level) of every skip tensor in production order (conv_in first)."""
+        cfg = self.cfg
+        out = [(cfg.block_out_channels[0], 0)]
+        n = len(cfg.block_out_channels)
+        for i, c in enumerate(cfg.block_out_channels):
+            out += [(c, i)] * cfg.layers_per_block
+            if i != n - 1:
+                out.append((c, i + 1))
+        return out
+
+    def time_embed(self, t: torch.Tensor, added: Optional[dict] = None) -> torch.Tensor:
+        """t fp32 [n] -> fp32 [n, sum(cout of every resnet)]: all time_emb_proj(silu(emb)) in one GEMM."""
+        cfg = self.cfg
+        s = ops.timestep_sinusoid(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift)
+        emb = self.t_lin2(self.t_lin1(s, act=ACT_SILU))
+        if self.add_emb is not None:
+            # SDXL "text_time": emb += add_embedding(cat[pooled text embeds, sinusoid(time_ids)])
+            n = t.shape[0]
+            te = added["text_embeds"]  # bf16 [n, 1280]
+            tid = ops.timestep_sinusoid(added["time_ids"].reshape(-1).float(), cfg.addition_time_embed_dim, cfg.flip_sin_to_cos, cfg.freq_shift)
+            buf = torch.empty((n, te.shape[1] + tid.numel() // n), dtype=BF16, device=t.device)
+            buf[:, : te.shape[1]].copy_(te)  # concatenation = data placement only
+            buf[:, te.shape[1] :].copy_(tid.view(n, -1))
+            emb = self.add_emb[1](self.add_emb[0](buf, act=ACT_SILU), residual=emb, beta=1.0)
+        return ops.gemm(ops.act(emb, ACT_SILU), self.temb_w, bias=self.temb_b, out_fp32=True)
+
+    def text_kv(self, text: torch.Tensor):
+        """text bf16 [n, 77, cross] -> per-attention K/V views (step-invariant)."""
+        n = text.shape[0]
+        t2 = text.reshape(n * text.shape[1], text.shape[2])
+        kv = {"down": [[a.text_kv(t2, n) for a in blk["attns"]] for blk in self.down], "mid": self.mid_attn.text_kv(t2, n)}
+        return kv
+
+    def run_encoder(self, x0: torch.Tensor, temb_all, kv, skip_out: Optional[List[torch.Tensor]], add_after_conv_in=None):
+        """conv_in -> down blocks.  Each produced skip j is written to skip_out[j] (a strided view into the
+        consumer's concat buffer) when given.  Returns (last hidden, list of skip tensors)."""
+        skips = []
+
+        def dst(j):
+            return skip_out[j] if skip_out is not None else None
+
+        x = self.conv_in(x0, out=dst(0), residual=add_after_conv_in, beta=1.0) if add_after_conv_in is not None else self.conv_in(x0, out=dst(0))
+        skips.append(x)
+        for bi, blk in enumerate(self.down):
+            for j, r in enumerate(blk["resnets"]):
+                has_attn = len(blk["attns"]) > 0
+                x = r(x, temb_all, out=None if has_attn else dst(len(skips)))
+                if has_attn:
+                    x = blk["attns"][j](x, kv["down"][bi][j], out=dst(len(skips)))
+                skips.append(x)
+            if blk["down"] is not None:
+                x = blk["down"](x, out=dst(len(skips)))
+                skips.append(x)
+        return x, skips
+
+    def run_mid(self, x, temb_all, kv, out=None):
+        x = self.mid_res[0](x, temb_all)
+        x = self.mid_attn(x, kv["mid"])
+        return self.mid_res[1](x, temb_all, out=out)
+
+
+class UNet(_EncoderBase):
+    def __init__(self, sd: SD, cfg, dev):
+        self._build_encoder(sd, dev, cfg)
+        g, eps = cfg.norm_num_groups, cfg.norm_eps
+        rev_heads = list(reversed(cfg.num_attention_heads))
+        self.up = []
+        nlev = len(cfg.block_out_channels)
+        for i, t in enumerate(cfg.up_block_types):
+            blk = {"resnets": [], "attns": [], "up": None}
+            for j in range(cfg.layers_per_block + 1):
+                blk["resnets"].append(ResnetBlock(sd, f"up_blocks.{i}.resnets.{j}", dev, g, eps, self.temb_registry))
+                if t.startswith("CrossAttn"):
+                    blk["attns"].append(Transformer2D(sd, f"up_blocks.{i}.attentions.{j}", dev, rev_heads[i], g))
+            if i != nlev - 1:
+                blk["up"] = Upsample(sd, f"up_blocks.{i}.upsamplers.0", dev)
+            self.up.append(blk)
+        self.norm_out = Norm(sd, "conv_norm_out", dev)
+        self.conv_out = Conv(sd, "conv_out", dev)
+        self._finish_temb(dev)
+        # concat plan: up resnet r consumes skip[-1-r]; hidden channels = resnet input - skip channels
+        sk = self.skip_channels()
+        self.cat_plan = []  # per up resnet: (hidden_ch, skip_ch, level)
+        r = 0
+        for blk in self.up:
+            for res in blk["resnets"]:
+                sc, lvl = sk[len(sk) - 1 - r]
+                self.cat_plan.append((res.conv1.cin - sc, sc, lvl))
+                r += 1
+
+    def text_kv(self, text):
+        kv = super().text_kv(text)
+        n = text.shape[0]
+        t2 = text.reshape(n * text.shape[1], text.shape[2])
+        kv["up"] = [[a.text_kv(t2, n) for a in blk["attns"]] for blk in self.up]
+        return kv
+
+    def alloc_cat(self, n: int, h: int, w: int):
+        """Concat buffers of the up path; returns (buffers, skip destination views, hidden destination views)."""
+        bufs, skip_dst, hid_dst = [], [None] * len(self.cat_plan), []
+        nsk = len(self.cat_plan)
+        for r, (hc, sc, lvl) in enumerate(self.cat_plan):
+            b = torch.empty((n, h >> lvl, w >> lvl, hc + sc), dtype=BF16, device=self.dev)
+            bufs.append(b)
+            hid_dst.append(b[..., :hc])
+            skip_dst[nsk - 1 - r] = b[..., hc:]
+        return bufs, skip_dst, hid_dst
+
+    def encode(self, x0, temb_all, kv, n, h, w):
+        """UNet encoder + mid block.  Returns state consumed by ``decode`` (and by ControlNet.inject)."""
+        bufs, skip_dst, hid_dst = self.alloc_cat(n, h, w)
+        x, skips = self.run_encoder(x0, temb_all, kv, skip_dst)
+        mid = self.run_mid(x, temb_all, kv, out=hid_dst[0])
+        return {"bufs": bufs, "skips": skips, "hid": hid_dst, "mid": mid}
+
+    def decode(self, st, temb_all, kv) -> torch.Tensor:
+        """Up path + conv_out.  Returns eps fp32 NHWC [n,h,w,out_channels]."""
+        bufs, hid = st["bufs"], st["hid"]
+        r = 0
+        x = None
+        for bi, blk in enumerate(self.up):
+            for j, res in enumerate(blk["resnets"]):
+                last_in_model = (r == len(self.cat_plan) - 1)
+                has_attn = len(blk["attns"]) > 0
+                last_in_block = j == len(blk["resnets"]) - 1
+                nxt = None if (last_in_model or (last_in_block and blk["up"] is not None)) else hid[r + 1]
+                x = res(bufs[r], temb_all, out=None if has_attn else nxt)
+                if has_attn:
+                    x = blk["attns"][j](x, kv["up"][bi][j], out=nxt)
+                r += 1
+            if blk["up"] is not None:
+                x = blk["up"](x, out=hid[r])
+        n, h, w, c = x.shape
+        a = ops.groupnorm(pix3d(x), self.cfg.norm_num_groups, self.cfg.norm_eps, self.norm_out.g, self.norm_out.b, ACT_SILU).view(n, h, w, c)
+        return self.conv_out(a, out_fp32=True)
+
+
+class ControlNet(_EncoderBase):
+    def __init__(self, sd: SD, cfg, dev):
+        self._build_encoder(sd, dev, cfg)
+        self._finish_temb(dev)
+        p = "controlnet_cond_embedding"
+        self.ce_in = Conv(sd, p + ".conv_in", dev)
+        self.ce_blocks = []
+        i = 0
+        while f"{p}.blocks.{i}.weight" in sd:
+            self.ce_blocks.append(Conv(sd, f"{p}.blocks.{i}", dev, stride=2 if i % 2 == 1 else 1))
+            i += 1
+        self.ce_out = Conv(sd, p + ".conv_out", dev)
+        self.zero = []
+        i = 0
+        while f"controlnet_down_blocks.{i}.weight" in sd:
+            self.zero.append(Conv(sd, f"controlnet_down_blocks.{i}", dev))
+            i += 1
+        self.zero_mid = Conv(sd, "controlnet_mid_block", dev)
+
+    def cond_embedding(self, cond: torch.Tensor) -> torch.Tensor:
+        """cond bf16 NHWC [n,H,W,3] in {0,1} -> [n,H/8,W/8,C0]; step-invariant, computed once per image."""
+        x = self.ce_in(cond, act=ACT_SILU)
+        for c in self.ce_blocks:
+            x = c(x, act=ACT_SILU)
+        return self.ce_out(x)
+
+    def inject(self, x0, temb_all, kv, cond_emb, scale: float, unet_state):
+        """ControlNet forward; every zero-conv accumulates `scale * residual` into the UNet's skip tensors /
+        mid output in its epilogue (diffusers: down_block_additional_residuals / mid_block_additional_residual)."""
+        x, outs = self.run_encoder(x0, temb_all, kv, None, add_after_conv_in=cond_emb)
+        x = self.run_mid(x, temb_all, kv)
+        for conv, o, dst in zip(self.zero, outs, unet_state["skips"]):
+            conv(o, out=dst, alpha=scale, residual=dst, beta=1.0)
+        m = unet_state["mid"]
+        self.zero_mid(x, out=m, alpha=scale, residual=m, beta=1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE
+# ------------------------------------------------------------------------------------------------
+class VAEAttention:
+    """Single-head d = C attention of the VAE mid block: GEMM -> row softmax -> GEMM per image."""
+
+    def __init__(self, sd: SD, p: str, dev, groups: int):
+        self.groups = groups
+        self.norm = Norm(sd, p + ".group_norm", dev)
+        self.wqkv = _bf(torch.cat([sd[p + ".to_q.weight"], sd[p + ".to_k.weight"], sd[p + ".to_v.weight"]], 0), dev)
+        self.bqkv = _f32(torch.cat([sd[p + ".to_q.bias"], sd[p + ".to_k.bias"], sd[p + ".to_v.bias"]], 0), dev)
+        self.out = Linear(sd, p + ".to_out.0", dev)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        n, h, w, c = x.shape
+        t = h * w
+        g = ops.groupnorm(pix3d(x), self.groups, 1e-6, self.norm.g, self.norm.b, ACT_NONE)
+        qkv = ops.gemm(g.view(n * t, c), self.wqkv, bias=self.bqkv).view(n, t, 3 * c)
+        o = torch.empty((n, t, c), dtype=BF16, device=x.device)
+        scale = c ** -0.5
+        if c <= 160:
+            ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], 1, out=o)
+        else:
+            vt = ops.transpose(qkv[..., 2 * c :])  # [n, c, t]
+            for i in range(n):
+                s = ops.gemm(qkv[i, :, :c], qkv[i, :, c : 2 * c])  # [t, t]
+                ops.softmax_rows(s, scale, out=s)
+                ops.gemm(s, vt[i], out=o[i])
+        y = torch.empty_like(x) if x.is_contiguous() else torch.empty((n, h, w, c), dtype=BF16, device=x.device)
+        self.out(o.view(n * t, c), out=pix2d(y), residual=pix2d(x), beta=1.0)
+        return y
+
+
+class _VAEStage:
+    def _mid(self, sd, p, dev, groups):
+        return ([ResnetBlock(sd, p + ".resnets.0", dev, groups, 1e-6, None), ResnetBlock(sd, p + ".resnets.1", dev, groups, 1e-6, None)],
+                VAEAttention(sd, p + ".attentions.0", dev, groups))
+
+
+class VAEDecoder(_VAEStage):
+    def __init__(self, sd: SD, cfg, dev):
+        g = cfg.norm_num_groups
+        self.cfg = cfg
+        self.post_quant = Conv(sd, "post_quant_conv", dev)
+        self.conv_in = Conv(sd, "decoder.conv_in", dev)
+        self.mid_res, self.mid_attn = self._mid(sd, "decoder.mid_block", dev, g)
+        self.blocks = []
+        for i in range(len(cfg.block_out_channels)):
+            res = [ResnetBlock(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, g, 1e-6, None) for j in range(cfg.layers_per_block + 1)]
+            up = Upsample(sd, f"decoder.up_blocks.{i}.upsamplers.0", dev) if f"decoder.up_blocks.{i}.upsamplers.0.conv.weight" in sd else None
+            self.blocks.append((res, up))
+        self.norm_out = Norm(sd, "decoder.conv_norm_out", dev)
+        self.conv_out = Conv(sd, "decoder.conv_out", dev)
+
+    def __call__(self, z: torch.Tensor) -> torch.Tensor:
+        """z bf16 NHWC [n,h,w,4] (latents / scaling_factor) -> fp32 NHWC [n,8h,8w,3]."""
+        x = self.conv_in(self.post_quant(z))
+        x = self.mid_res[1](self.mid_attn(self.mid_res[0](x, None)), None)
+        for res, up in self.blocks:
+            for r in res:
+                x = r(x, None)
+            if up is not None:
+                x = up(x)
+        n, h, w, c = x.shape
+        a = ops.groupnorm(pix3d(x), self.cfg.norm_num_groups, 1e-6, self.norm_out.g, self.norm_out.b, ACT_SILU).view(n, h, w, c)
+        return self.conv_out(a, out_fp32=True)
+
+
+class VAEEncoder(_VAEStage):
+    def __init__(self, sd: SD, cfg, dev):
+        g = cfg.norm_num_groups
+        self.cfg = cfg
+        self.conv_in = Conv(sd, "encoder.conv_in", dev)
+        self.blocks = []
+        for i in range(len(cfg.block_out_channels)):
+            res = [ResnetBlock(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, g, 1e-6, None) for j in range(cfg.layers_per_block)]
+            dn = Downsample(sd, f"encoder.down_blocks.{i}.downsamplers.0", dev, padding=0) if f"encoder.down_blocks.{i}.downsamplers.0.conv.weight" in sd else None
+            self.blocks.append((res, dn))
+        self.mid_res, self.mid_attn = self._mid(sd, "encoder.mid_block", dev, g)
+        self.norm_out = Norm(sd, "encoder.conv_norm_out", dev)
+        self.conv_out = Conv(sd, "encoder.conv_out", dev)
+        self.quant = Conv(sd, "quant_conv", dev)
+
+    def __call__(self, img: torch.Tensor) -> torch.Tensor:
+        """img bf16 NHWC [n,H,W,3] in [-1,1] -> moments fp32 NHWC [n,H/8,W/8,8] (mean 0:4, logvar 4:8)."""
+        x = self.conv_in(img)
+        for res, dn in self.blocks:
+            for r in res:
+                x = r(x, None)
+            if dn is not None:
+                x = dn(x)
+        x = self.mid_res[1](self.mid_attn(self.mid_res[0](x, None)), None)
+        n, h, w, c = x.shape
+        a = ops.groupnorm(pix3d(x), self.cfg.norm_num_groups, 1e-6, self.norm_out.g, self.norm_out.b, ACT_SILU).view(n, h, w, c)
+        return self.quant(self.conv_out(a), out_fp32=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text encoder (transformers CLIPTextModel: causal pre-LN transformer, quick_gelu for ViT-L/14)
+# ------------------------------------------------------------------------------------------------
+class CLIPTextEncoder:
+    def __init__(self, sd: SD, dev, heads: int, act: str = "quick_gelu", eps: float = 1e-5):
+        p = "text_model."
+        self.dev, self.heads, self.eps = dev, heads, eps
+        self.act = ACT_QUICKGELU if act == "quick_gelu" else ops.ACT_GELU
+        self.tok = _bf(sd[p + "embeddings.token_embedding.weight"], dev)
+        self.pos = _bf(sd[p + "embeddings.position_embedding.weight"], dev)
+        self.layers = []
+        i = 0
+        while f"{p}encoder.layers.{i}.layer_norm1.weight" in sd:
+            q = f"{p}encoder.layers.{i}."
+            wqkv = torch.cat([sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.k_proj.weight"], sd[q + "self_attn.v_proj.weight"]], 0)
+            bqkv = torch.cat([sd[q + "self_attn.q_proj.bias"], sd[q + "self_attn.k_proj.bias"], sd[q + "self_attn.v_proj.bias"]], 0)
+            self.layers.append({
+                "ln1": Norm(sd, q + "layer_norm1", dev), "ln2": Norm(sd, q + "layer_norm2", dev),
+                "qkv": Linear(sd, "", dev, weight=wqkv, bias=bqkv), "o": Linear(sd, q + "self_attn.out_proj", dev),
+                "fc1": Linear(sd, q + "mlp.fc1", dev), "fc2": Linear(sd, q + "mlp.fc2", dev)})
+            i += 1
+        self.ln_final = Norm(sd, p + "final_layer_norm", dev)
+
+    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids int64 [n, 77] (device) -> last_hidden_state bf16 [n, 77, width]."""
+        n, t = ids.shape
+        c = self.tok.shape[1]
+        # embedding gather is index plumbing (no arithmetic): torch indexing, then our add kernel
+        e = self.tok.index_select(0, ids.reshape(-1))
+        pos = self.pos[:t].repeat(n, 1)
+        h = ops.add(e, pos)
+        for L in self.layers:
+            y = ops.layernorm(h, self.eps, L["ln1"].g, L["ln1"].b)
+            qkv = L["qkv"](y).view(n, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads, causal=True)
+            L["o"](a.view(n * t, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, self.eps, L["ln2"].g, L["ln2"].b)
+            f = L["fc1"](y, act=self.act)
+            L["fc2"](f, out=h, residual=h, beta=1.0)
+        return ops.layernorm(h, self.eps, self.ln_final.g, self.ln_final.b).view(n, t, c)

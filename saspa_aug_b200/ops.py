@@ -336,6 +336,22 @@ def cfg_sched_step(eps_uncond, eps_cond, guidance: float, inputs, outputs, coef)
     _count()
 
 
+def vae_sample_add_noise(moments: torch.Tensor, noise_post, noise_diff, scaling: float, alpha: float, sigma: float):
+    """moments fp32 NHWC [n,h,w,2*lc] -> (latents, z0) fp32 NCHW [n,lc,h,w]."""
+    _need_cuda(moments)
+    n, h, w, c2 = moments.shape
+    lc = c2 // 2
+    assert moments.dtype == torch.float32 and moments.is_contiguous()
+    lat = torch.empty((n, lc, h, w), dtype=torch.float32, device=moments.device)
+    z0 = torch.empty_like(lat)
+    for t in (noise_post, noise_diff):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == lat.shape)
+    check(_lib.load().saspa_vae_sample_add_noise(_ptr(moments), _ptr(noise_post), _ptr(noise_diff), float(scaling), float(alpha), float(sigma), n, h, w, lc,
+                                                 _ptr(lat), _ptr(z0), _stream()), "saspa_vae_sample_add_noise")
+    _count()
+    return lat, z0
+
+
 def vae_quantize_u8(x: torch.Tensor) -> torch.Tensor:
     """x [n,h,w,c>=3] (bf16|fp32, channel stride 1) -> u8 [n,h,w,3]."""
     _need_cuda(x)

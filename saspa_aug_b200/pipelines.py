@@ -1,0 +1,289 @@
+"""Drop-in pipelines for the reference's generation call.
+
+``run_aug/run_aug.py`` builds a diffusers pipeline (init_pipeline, :128-230) and calls it through
+``pass_thorugh_pipe`` (:233-279) with exactly these keyword sets:
+  text2img ControlNet : prompt, num_inference_steps, generator, guidance_scale, negative_prompt,
+                        image=<canny PIL>, controlnet_conditioning_scale
+  img2img  ControlNet : ... , image=<source PIL>, control_image=<canny PIL>, strength, controlnet_conditioning_scale
+and reads ``.images[0]``.  ``SaspaControlNetPipeline`` accepts the same kwargs and returns the same shape of
+result; ``generate_batch`` is the batched entry the sharded driver and bench.py use (same arithmetic, B images
+per launch list).  All compute is sm_100a kernels (saspa_aug_b200.nn / ops); no torch math on the path.
+"""
+from __future__ import annotations
+
+import zlib
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import checkpoints as ck
+from . import nn as snn
+from . import ops
+from .schedulers import SchedulerBase, make_scheduler
+
+BF16 = torch.bfloat16
+
+
+class SyntheticTokenizer:
+    """Deterministic stand-in for CLIPTokenizer (no vocabulary files exist offline): lower-cases, splits on
+    non-alphanumerics, maps each word to 1 + crc32(word) % (vocab-3); BOS = vocab-2, EOS = pad = vocab-1,
+    truncation at ``model_max_length`` (77).  A real CLIPTokenizer can be passed to the pipeline instead."""
+
+    def __init__(self, vocab_size: int = 49408, model_max_length: int = 77):
+        self.vocab_size, self.model_max_length = vocab_size, model_max_length
+
+    def encode(self, text: str) -> List[int]:
+        import re
+
+        words = [w for w in re.split(r"[^0-9a-zA-Z]+", text.lower()) if w]
+        ids = [1 + zlib.crc32(w.encode()) % (self.vocab_size - 3) for w in words][: self.model_max_length - 2]
+        ids = [self.vocab_size - 2] + ids + [self.vocab_size - 1]
+        return ids + [self.vocab_size - 1] * (self.model_max_length - len(ids))
+
+    def __call__(self, texts: Union[str, Sequence[str]]) -> torch.Tensor:
+        if isinstance(texts, str):
+            texts = [texts]
+        return torch.tensor([self.encode(t) for t in texts], dtype=torch.int64)
+
+
+@dataclass
+class PipelineOutput:
+    images: list
+    nsfw_content_detected: Optional[list] = None
+    latents_per_step: Optional[list] = None
+
+
+class _SchedulerConfigView(dict):
+    """`pipe.scheduler.config` as touched by run_aug.py:219-221 (`X.from_config(pipe.scheduler.config)`)."""
+
+
+class SaspaControlNetPipeline:
+    """SD v1.5-architecture ControlNet pipeline (text2img and img2img/SDEdit) on B200 kernels."""
+
+    def __init__(self, unet: snn.UNet, controlnet: Optional[snn.ControlNet], vae_decoder: snn.VAEDecoder, vae_encoder: Optional[snn.VAEEncoder],
+                 text_encoder: snn.CLIPTextEncoder, tokenizer=None, sampler: str = "ddim", device="cuda", vae_cfg: Optional[ck.VAEConfig] = None):
+        self.unet, self.controlnet = unet, controlnet
+        self.vae_decoder, self.vae_encoder = vae_decoder, vae_encoder
+        self.text_encoder = text_encoder
+        self.tokenizer = tokenizer or SyntheticTokenizer()
+        self.device = torch.device(device)
+        self.vae_cfg = vae_cfg or ck.VAEConfig.sd15()
+        self.scheduler: SchedulerBase = make_scheduler(sampler)
+        self._neg_cache = {}
+        self._graphs = {}
+        self.use_cuda_graph = False
+        self.vae_micro_batch = 8
+
+    # ---- construction -----------------------------------------------------------------------
+    @classmethod
+    def from_state_dicts(cls, unet_sd, controlnet_sd, vae_sd, text_sd, *, unet_cfg=None, vae_cfg=None, text_cfg=None, sampler="ddim",
+                         device="cuda", tokenizer=None, img2img=True):
+        unet_cfg = unet_cfg or ck.UNetConfig.sd15()
+        vae_cfg = vae_cfg or ck.VAEConfig.sd15()
+        text_cfg = text_cfg or ck.CLIPTextConfig.sd15()
+        dev = torch.device(device)
+        unet = snn.UNet(unet_sd, unet_cfg, dev)
+        cn = snn.ControlNet(controlnet_sd, unet_cfg, dev) if controlnet_sd is not None else None
+        dec = snn.VAEDecoder(vae_sd, vae_cfg, dev)
+        enc = snn.VAEEncoder(vae_sd, vae_cfg, dev) if img2img else None
+        te = snn.CLIPTextEncoder(text_sd, dev, text_cfg.num_attention_heads, text_cfg.hidden_act, text_cfg.layer_norm_eps)
+        tok = tokenizer or SyntheticTokenizer(text_cfg.vocab_size, text_cfg.max_position_embeddings)
+        return cls(unet, cn, dec, enc, te, tok, sampler, device, vae_cfg)
+
+    @classmethod
+    def random_init(cls, config: str = "sd15", seed: int = 1234, **kw):
+        """Random-init weights of the named architecture ("sd15" | "tiny"); SURVEY.md 8d."""
+        ucfg = getattr(ck.UNetConfig, config)() if config != "tiny" else ck.UNetConfig.tiny()
+        vcfg = getattr(ck.VAEConfig, config)() if config != "tiny" else ck.VAEConfig.tiny()
+        tcfg = ck.CLIPTextConfig.sd15() if config != "tiny" else ck.CLIPTextConfig.tiny()
+        sds = random_state_dicts(config, seed)
+        return cls.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], unet_cfg=ucfg, vae_cfg=vcfg, text_cfg=tcfg, **kw)
+
+    # ---- surface touched by run_aug.py ---------------------------------------------------------
+    def to(self, *a, **k):  # `.to(DEVICE, torch.float16)` at run_aug.py:323; weights already live on the device in bf16
+        return self
+
+    def upcast_vae(self):  # run_aug.py:224 (sd_xl-turbo); the VAE path already accumulates in fp32
+        return None
+
+    def set_sampler(self, name: str, **kw):
+        self.scheduler = make_scheduler(name, **kw)
+
+    # ---- text ----------------------------------------------------------------------------------
+    def encode_prompt_ids(self, ids: torch.Tensor) -> torch.Tensor:
+        return self.text_encoder(ids.to(self.device))
+
+    def _neg_embeds(self, negative_prompt: Optional[str], n: int) -> torch.Tensor:
+        key = negative_prompt or ""
+        if key not in self._neg_cache:  # the negative prompt is a constant of the run (run_aug.py:47): encode once
+            self._neg_cache[key] = self.encode_prompt_ids(self.tokenizer([key]))
+        return self._neg_cache[key].expand(n, -1, -1)
+
+    # ---- image helpers -----------------------------------------------------------------------------
+    def _to_u8_batch(self, image) -> torch.Tensor:
+        """PIL | ndarray | list thereof | u8 tensor -> u8 [n,H,W,3] on the device."""
+        if isinstance(image, torch.Tensor):
+            t = image
+        elif isinstance(image, np.ndarray) and image.ndim == 4:
+            t = torch.from_numpy(np.ascontiguousarray(image.astype(np.uint8)))
+        else:
+            if not isinstance(image, (list, tuple)):
+                image = [image]
+            arrs = []
+            for im in image:
+                a = np.asarray(im.convert("RGB")) if hasattr(im, "convert") else np.asarray(im)
+                if a.ndim == 2:
+                    a = np.repeat(a[..., None], 3, axis=2)
+                arrs.append(a.astype(np.uint8))
+            t = torch.from_numpy(np.stack(arrs))
+        if t.dim() == 3:
+            t = t[None]
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # ---- core --------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate_batch(self, text_embeds: torch.Tensor, neg_embeds: Optional[torch.Tensor], control_u8: Optional[torch.Tensor] = None,
+                       source_u8: Optional[torch.Tensor] = None, *, noise: torch.Tensor, noise_posterior: Optional[torch.Tensor] = None,
+                       num_inference_steps: int = 50, guidance_scale: float = 7.5, strength: float = 1.0,
+                       controlnet_conditioning_scale: float = 1.0, control_bf16: Optional[torch.Tensor] = None,
+                       step_callback: Optional[Callable] = None, decode: bool = True):
+        """B images in one launch list.
+        text_embeds/neg_embeds bf16 [B,77,D]; control_u8/source_u8 u8 [B,H,W,3]; noise fp32 NCHW [B,4,H/8,W/8] (device).
+        Returns u8 [B,H,W,3] (device) -- or the final latents when decode=False."""
+        dev = self.device
+        B = text_embeds.shape[0]
+        do_cfg = guidance_scale > 1.0 and neg_embeds is not None
+        sched = self.scheduler
+        sched.set_timesteps(num_inference_steps)
+        img2img = source_u8 is not None
+        start = sched.img2img_start(num_inference_steps, strength) * sched.order if img2img else 0
+        lc = self.vae_cfg.latent_channels
+        sf = self.vae_cfg.scaling_factor
+        _, _, lh, lw = noise.shape
+
+        # step-invariant work, once per image: text K/V projections, ControlNet conditioning embedding
+        text = torch.cat([neg_embeds, text_embeds], 0).contiguous() if do_cfg else text_embeds.contiguous()
+        rows = text.shape[0]
+        kv_u = self.unet.text_kv(text)
+        cond_emb = None
+        kv_c = None
+        if self.controlnet is not None:
+            kv_c = self.controlnet.text_kv(text)
+            if control_bf16 is None:
+                H, W = control_u8.shape[1:3]
+                control_bf16 = ops.crop_normalize(control_u8, 0, 0, H, W, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), out_c=3)
+            ce = self.controlnet.cond_embedding(control_bf16)
+            cond_emb = torch.cat([ce, ce], 0) if do_cfg else ce  # same control image for both CFG rows (placement only)
+
+        # initial latents
+        if img2img:
+            H, W = source_u8.shape[1:3]
+            src = ops.crop_normalize(source_u8, 0, 0, H, W, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), out_c=3)
+            moments = torch.cat([self.vae_encoder(src[i : i + self.vae_micro_batch]) for i in range(0, B, self.vae_micro_batch)], 0)
+            a, s = sched.add_noise_coef(start)
+            latents, _ = ops.vae_sample_add_noise(moments, noise_posterior, noise, sf, a, s)
+        else:
+            latents = (noise * sched.init_noise_sigma).contiguous() if sched.init_noise_sigma != 1.0 else noise.clone()
+
+        bufs = {"x": latents}
+        for name in sched.history_buffers:
+            bufs[name] = torch.zeros_like(latents)
+        sched.begin(start)
+        x2 = torch.empty((rows, lh, lw, lc), dtype=BF16, device=dev)
+        tvec = torch.empty((rows,), dtype=torch.float32, device=dev)
+        per_step = []
+        for i in range(start, len(sched.timesteps)):
+            t = float(sched.timesteps[i])
+            tvec.fill_(t)
+            eps = self._eps(latents, x2, tvec, kv_u, kv_c, cond_emb, controlnet_conditioning_scale, B, do_cfg, lh, lw)
+            plan = sched.plan(i)
+            ops.cfg_sched_step(eps[:B] if do_cfg else None, eps[B:] if do_cfg else eps, guidance_scale,
+                               [None if nm is None else bufs[nm] for nm in plan.inputs], [bufs[nm] for nm in plan.outputs], plan.coef)
+            if step_callback is not None:
+                step_callback(i, t, latents)
+        if not decode:
+            return latents
+        return self.decode_latents(latents)
+
+    def _eps(self, latents, x2, tvec, kv_u, kv_c, cond_emb, cond_scale, B, do_cfg, lh, lw) -> torch.Tensor:
+        """One UNet(+ControlNet) evaluation -> eps fp32 NCHW [rows,4,h,w] (rows = 2B with CFG: uncond first)."""
+        rows = x2.shape[0]
+        ops.nchw_f32_to_nhwc_bf16(latents, out=x2[:B])
+        if do_cfg:
+            ops.nchw_f32_to_nhwc_bf16(latents, out=x2[B:])
+        temb_u = self.unet.time_embed(tvec)
+        st = self.unet.encode(x2, temb_u, kv_u, rows, lh, lw)
+        if self.controlnet is not None:
+            temb_c = self.controlnet.time_embed(tvec)
+            self.controlnet.inject(x2, temb_c, kv_c, cond_emb, cond_scale, st)
+        eps_nhwc = self.unet.decode(st, temb_u, kv_u)
+        return ops.nhwc_to_nchw_f32(eps_nhwc)
+
+    @torch.no_grad()
+    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """latents fp32 NCHW -> u8 [B,H,W,3] (vae.decode(latents / scaling_factor) + image-processor postprocess)."""
+        outs = []
+        for i in range(0, latents.shape[0], self.vae_micro_batch):
+            z = ops.nchw_f32_to_nhwc_bf16(latents[i : i + self.vae_micro_batch].contiguous(), scale=1.0 / self.vae_cfg.scaling_factor)
+            outs.append(ops.vae_quantize_u8(self.vae_decoder(z)))
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    # ---- reference-compatible call -------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, prompt: Union[str, List[str], None] = None, image=None, control_image=None, strength: float = 0.8,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt: Optional[str] = None,
+                 generator: Optional[torch.Generator] = None, controlnet_conditioning_scale: float = 1.0, output_type: str = "pil",
+                 height: Optional[int] = None, width: Optional[int] = None, prompt_ids: Optional[torch.Tensor] = None,
+                 negative_prompt_ids: Optional[torch.Tensor] = None, return_latents_per_step: bool = False, latents: Optional[torch.Tensor] = None,
+                 **unused) -> PipelineOutput:
+        # img2img pipelines take (image=source, control_image=canny); text2img takes (image=canny)  [run_aug.py:258-276]
+        if control_image is None:
+            control, source = image, None
+        else:
+            control, source = control_image, image
+        if prompt_ids is None:
+            prompt_ids = self.tokenizer([prompt] if isinstance(prompt, str) else list(prompt))
+        B = prompt_ids.shape[0]
+        text = self.encode_prompt_ids(prompt_ids)
+        neg = None
+        if guidance_scale > 1.0:
+            neg = self.encode_prompt_ids(negative_prompt_ids) if negative_prompt_ids is not None else self._neg_embeds(negative_prompt, B).contiguous()
+        control_u8 = self._to_u8_batch(control) if control is not None else None
+        source_u8 = self._to_u8_batch(source) if source is not None else None
+        ref = control_u8 if control_u8 is not None else source_u8
+        H, W = (ref.shape[1], ref.shape[2]) if ref is not None else (height or 512, width or 512)
+        shape = (B, self.vae_cfg.latent_channels, H // 8, W // 8)
+        # diffusers randn_tensor: CPU generator -> sample on CPU, then move.  img2img draws the VAE posterior noise first.
+        post = torch.randn(shape, generator=generator, dtype=torch.float32).to(self.device) if source_u8 is not None else None
+        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=torch.float32)
+        noise = noise.to(self.device)
+        per_step = [] if return_latents_per_step else None
+        cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
+        out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, num_inference_steps=num_inference_steps,
+                                  guidance_scale=guidance_scale, strength=strength, controlnet_conditioning_scale=controlnet_conditioning_scale,
+                                  step_callback=cb)
+        arr = out.cpu().numpy()
+        if output_type == "pil":
+            from PIL import Image
+
+            images = [Image.fromarray(a) for a in arr]
+        else:
+            images = [a for a in arr]
+        return PipelineOutput(images=images, nsfw_content_detected=None, latents_per_step=per_step)
+
+
+def random_state_dicts(config: str = "sd15", seed: int = 1234) -> dict:
+    if config == "tiny":
+        ucfg, vcfg, tcfg = ck.UNetConfig.tiny(), ck.VAEConfig.tiny(), ck.CLIPTextConfig.tiny()
+    elif config == "sd15":
+        ucfg, vcfg, tcfg = ck.UNetConfig.sd15(), ck.VAEConfig.sd15(), ck.CLIPTextConfig.sd15()
+    else:
+        raise ValueError(config)
+    return {
+        "unet": ck.random_state_dict(ck.unet_shapes(ucfg), seed),
+        "controlnet": ck.random_state_dict(ck.controlnet_shapes(ucfg), seed + 1),
+        "vae": ck.random_state_dict(ck.vae_shapes(vcfg), seed + 2),
+        "text": ck.random_state_dict(ck.clip_text_shapes(tcfg), seed + 3),
+    }

@@ -76,7 +76,7 @@ def test_gemm_geglu(cuda_device):
 @pytest.mark.parametrize("cfg", [  # n, h, w, cin, cout, ksize
     (2, 64, 64, 320, 320, 3), (4, 32, 32, 640, 640, 3), (4, 16, 16, 1280, 1280, 3), (6, 8, 8, 1280, 1280, 3),
     (2, 64, 88, 320, 320, 3), (1, 128, 128, 128, 128, 3), (3, 16, 16, 64, 96, 3), (2, 32, 32, 320, 640, 1), (1, 24, 40, 128, 256, 3),
-    (2, 8, 8, 2560, 1280, 3)])
+    (2, 8, 8, 2560, 1280, 3), (2, 64, 64, 16, 16, 3), (2, 32, 32, 32, 32, 3), (1, 64, 64, 96, 96, 3), (2, 16, 16, 8, 24, 3), (2, 64, 64, 320, 4, 3)])
 def test_conv_igemm(cuda_device, cfg):
     n, h, w, cin, cout, ks = cfg
     x = _rand((n, h, w, cin), 10)

@@ -1,0 +1,82 @@
+"""CPU: the product's coefficient-table schedulers (host logic feeding saspa_cfg_sched_step) reproduce the
+oracle restatement of diffusers' DDIM / UniPC / PNDM step() on random eps sequences (fp64-vs-fp32 scalar
+algebra => tolerance 2e-5 relative to max|x|)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.diffusers_restated import schedulers as osched
+from saspa_aug_b200 import schedulers as psched
+
+
+def _apply(plan, bufs, eps):
+    ins = [eps if nm is None else bufs[nm] for nm in plan.inputs]
+    outs = []
+    for row in plan.coef:
+        acc = torch.zeros_like(eps)
+        for c, t in zip(row, ins):
+            acc = acc + c * t
+        outs.append(acc)
+    for nm, o in zip(plan.outputs, outs):
+        bufs[nm] = o
+
+
+def _run(name, n, strength=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shape = (2, 4, 8, 8)
+    o = {"ddim": osched.DDIMScheduler, "unipc": osched.UniPCMultistepScheduler, "pndm": osched.PNDMScheduler}[name]()
+    p = psched.make_scheduler(name)
+    o.set_timesteps(n)
+    p.set_timesteps(n)
+    assert np.array_equal(o.timesteps.numpy(), p.timesteps)
+    start = 0
+    ts = o.timesteps
+    x = torch.randn(shape, generator=g)
+    if strength is not None:
+        start = p.img2img_start(n, strength)
+        ts = ts[start:]
+        if hasattr(o, "set_begin_index"):
+            o.set_begin_index(start)
+        z0, noise = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+        xo = o.add_noise(z0, noise, ts[0])
+        a, s = p.add_noise_coef(start)
+        assert torch.allclose(xo, a * z0 + s * noise, atol=1e-5)
+        x = xo
+    bufs = {"x": x.clone()}
+    for nm in p.history_buffers:
+        bufs[nm] = torch.zeros(shape)
+    p.begin(start)
+    xo = x.clone()
+    for k, t in enumerate(ts):
+        eps = torch.randn(shape, generator=g)
+        xo = o.step(eps, t, xo)
+        _apply(p.plan(start + k), bufs, eps)
+        err = (bufs["x"] - xo).abs().max().item() / max(xo.abs().max().item(), 1.0)
+        assert err < 2e-5, (name, n, strength, k, err)
+    return len(ts)
+
+
+@pytest.mark.parametrize("name", ["ddim", "unipc", "pndm"])
+@pytest.mark.parametrize("n", [2, 5, 20, 30])
+def test_full_schedule(name, n):
+    evals = _run(name, n)
+    assert evals == (n + 1 if name == "pndm" else n)
+
+
+@pytest.mark.parametrize("name", ["ddim", "unipc"])
+@pytest.mark.parametrize("n,strength", [(20, 0.5), (30, 0.85), (50, 0.15), (20, 1.0)])
+def test_img2img_schedule(name, n, strength):
+    evals = _run(name, n, strength)
+    assert evals == min(int(n * strength), n)
+
+
+def test_known_timesteps():
+    p = psched.make_scheduler("unipc")
+    p.set_timesteps(20)
+    assert p.timesteps[0] == 941 and p.timesteps[1] == 894 and p.timesteps[-1] == 48
+    d = psched.make_scheduler("ddim")
+    d.set_timesteps(30)
+    assert d.timesteps[0] == 958 and d.timesteps[-1] == 1
+    t = psched.make_scheduler("ddim", timestep_spacing="trailing")
+    t.set_timesteps(4)
+    assert t.timesteps.tolist() == [999, 749, 499, 249]
