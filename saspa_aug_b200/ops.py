@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_SILU, Epilogue, LinComb, SaspaError, check
 
 LAUNCHES = 0  # kernels launched via this module (host-side count)
+PROFILE = None  # set to a list to record (kind, flops, start_event, end_event) around every tcgen05 launch (bench.py roofline leg)
 
 BF16 = torch.bfloat16
 
@@ -37,6 +38,22 @@ def _need_cuda(*ts):
 def _count(n: int = 1):
     global LAUNCHES
     LAUNCHES += n
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(ev, kind: str, flops: float):
+    if ev is None:
+        return
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    PROFILE.append((kind, flops, ev, end))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -98,10 +115,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         assert residual.dtype == BF16 and residual.stride(1) == 1 and residual.shape == (M, n_out)
     ep = make_epilogue(bias, row_bias, rows_per_group, act, alpha, residual, residual.stride(0) if residual is not None else 0, beta,
                        out.dtype == torch.float32, act_after_residual)
+    ev = _prof_begin()
     check(
         _lib.load().saspa_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, ctypes.byref(ep), _stream()),
         "saspa_gemm_bf16",
     )
+    _prof_end(ev, "gemm", 2.0 * M * N * K)
     _count()
     return out
 
@@ -127,11 +146,13 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
         assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == w * residual.stride(2)
         ld_res = residual.stride(2)
     ep = make_epilogue(bias, row_bias, h * w, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual)
+    ev = _prof_begin()
     check(
         _lib.load().saspa_conv2d_igemm_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
                                             _ptr(weight), ksize, _ptr(out), out.stride(2), cout, ctypes.byref(ep), _stream()),
         "saspa_conv2d_igemm_bf16",
     )
+    _prof_end(ev, "conv", 2.0 * n * h * w * cout * ksize * ksize * (c0 + c1))
     _count()
     return out
 
@@ -266,11 +287,13 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     if out is None:
         out = torch.empty((b, tq, hd), dtype=BF16, device=q.device)
     assert out.stride(2) == 1 and out.stride(0) == tq * out.stride(1)
+    ev = _prof_begin()
     check(
         _lib.load().saspa_attention_bf16(_ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(out), out.stride(1), b, heads, tq,
                                          tkv, d, float(scale), 1 if causal else 0, _stream()),
         "saspa_attention_bf16",
     )
+    _prof_end(ev, "attention", 4.0 * b * heads * tq * tkv * d)
     _count()
     return out
 
