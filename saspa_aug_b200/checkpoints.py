@@ -313,3 +313,125 @@ def count_params(shapes: Shapes) -> int:
             n *= d
         tot += n
     return tot
+
+
+# ----------------------------------------------------------------------------------------------------
+# filter networks: WSDAN_CAL (fgvc/models/cal.py) and openai CLIP RN50 (all_utils/utils.py:253)
+# ----------------------------------------------------------------------------------------------------
+def _bn(p, c) -> Shapes:
+    yield p + ".weight", (c,)
+    yield p + ".bias", (c,)
+    yield p + ".running_mean", (c,)
+    yield p + ".running_var", (c,)
+
+
+RESNET_LAYERS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+
+
+def wsdan_shapes(num_classes: int, net: str = "resnet50", M: int = 32) -> Shapes:
+    """State-dict keys of fgvc.models.cal.WSDAN_CAL(num_classes, net=net): `features` is the nn.Sequential of
+    fgvc/models/resnet.py:168-178 (conv1, bn1, relu, maxpool, layer1..4 at indices 0,1,4,5,6,7; layer4 stride 1)."""
+    yield "features.0.weight", (64, 3, 7, 7)
+    yield from _bn("features.1", 64)
+    inplanes = 64
+    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), RESNET_LAYERS[net])):
+        stride = 1 if li in (0, 3) else 2
+        for b in range(blocks):
+            p = f"features.{4 + li}.{b}"
+            yield p + ".conv1.weight", (planes, inplanes, 1, 1)
+            yield from _bn(p + ".bn1", planes)
+            yield p + ".conv2.weight", (planes, planes, 3, 3)
+            yield from _bn(p + ".bn2", planes)
+            yield p + ".conv3.weight", (planes * 4, planes, 1, 1)
+            yield from _bn(p + ".bn3", planes * 4)
+            if b == 0 and (stride != 1 or inplanes != planes * 4):
+                yield p + ".downsample.0.weight", (planes * 4, inplanes, 1, 1)
+                yield from _bn(p + ".downsample.1", planes * 4)
+            inplanes = planes * 4
+    yield "attentions.conv.weight", (M, 2048, 1, 1)
+    yield from _bn("attentions.bn", M)
+    yield "fc.weight", (num_classes, M * 2048)
+
+
+def clip_rn50_shapes(embed_dim=1024, width=64, layers=(3, 4, 6, 3), t_width=512, t_layers=12, vocab=49408, ctx=77, res=224) -> Shapes:
+    yield "positional_embedding", (ctx, t_width)
+    yield "text_projection", (t_width, embed_dim)
+    yield "logit_scale", ()
+    v = "visual."
+    yield v + "conv1.weight", (width // 2, 3, 3, 3)
+    yield from _bn(v + "bn1", width // 2)
+    yield v + "conv2.weight", (width // 2, width // 2, 3, 3)
+    yield from _bn(v + "bn2", width // 2)
+    yield v + "conv3.weight", (width, width // 2, 3, 3)
+    yield from _bn(v + "bn3", width)
+    inplanes = width
+    for li, blocks in enumerate(layers):
+        planes = width * (2 ** li)
+        stride = 1 if li == 0 else 2
+        for b in range(blocks):
+            p = f"{v}layer{li + 1}.{b}"
+            s = stride if b == 0 else 1
+            yield p + ".conv1.weight", (planes, inplanes, 1, 1)
+            yield from _bn(p + ".bn1", planes)
+            yield p + ".conv2.weight", (planes, planes, 3, 3)
+            yield from _bn(p + ".bn2", planes)
+            yield p + ".conv3.weight", (planes * 4, planes, 1, 1)
+            yield from _bn(p + ".bn3", planes * 4)
+            if s > 1 or inplanes != planes * 4:
+                yield p + ".downsample.0.weight", (planes * 4, inplanes, 1, 1)
+                yield from _bn(p + ".downsample.1", planes * 4)
+            inplanes = planes * 4
+    ed = width * 32
+    a = v + "attnpool."
+    yield a + "positional_embedding", ((res // 32) ** 2 + 1, ed)
+    for nm in ("k_proj", "q_proj", "v_proj"):
+        yield from _lin(a + nm, ed, ed)
+    yield from _lin(a + "c_proj", ed, embed_dim)
+    for i in range(t_layers):
+        q = f"transformer.resblocks.{i}."
+        yield q + "attn.in_proj_weight", (3 * t_width, t_width)
+        yield q + "attn.in_proj_bias", (3 * t_width,)
+        yield from _lin(q + "attn.out_proj", t_width, t_width)
+        yield from _norm(q + "ln_1", t_width)
+        yield from _lin(q + "mlp.c_fc", t_width, 4 * t_width)
+        yield from _lin(q + "mlp.c_proj", 4 * t_width, t_width)
+        yield from _norm(q + "ln_2", t_width)
+    yield "token_embedding.weight", (vocab, t_width)
+    yield from _norm("ln_final", t_width)
+
+
+def random_filter_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tensor]:
+    """He-normal conv/linear weights (ReLU nets), BatchNorm affine ~ N(1,.1)/N(0,.1) with non-trivial running stats,
+    the last BN scale of each residual branch damped (x0.5) so depth does not blow the activations up."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in shapes:
+        if name == "logit_scale":
+            t = torch.tensor(math.log(1 / 0.07))
+        elif name.endswith("running_var"):
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif name.endswith("running_mean"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif "positional_embedding" in name or name == "token_embedding.weight":
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif name == "text_projection":
+            t = torch.randn(shape, generator=g) * shape[0] ** -0.5
+        elif len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            relu_net = name.startswith(("features.", "visual.", "attentions.")) and "attnpool" not in name
+            std = math.sqrt((2.0 if relu_net else 1.0) / fan_in)
+            if name.endswith(_RESIDUAL_OUT) and not relu_net:
+                std /= math.sqrt(2.0)
+            t = torch.randn(shape, generator=g) * std
+        elif (".bn" in name or "downsample.1" in name or "features.1" in name) and name.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            if ".bn3." in name:
+                t = t * 0.5
+        elif ("ln_" in name or "ln_final" in name) and name.endswith("weight"):
+            t = 1.0 + 0.05 * torch.randn(shape, generator=g)
+        else:
+            t = 0.05 * torch.randn(shape, generator=g)
+        sd[name] = t.float()
+    return sd

@@ -1,0 +1,215 @@
+"""Filter networks on the sm_100a kernels: the baseline classifier WSDAN_CAL (ResNet-50/101 trunk + bilinear
+attention pooling, reference fgvc/models/cal.py:131-213, resnet.py:61-178) and CLIP RN50 (openai-clip
+ModifiedResNet + AttentionPool2d + text transformer, loaded at all_utils/utils.py:253 and wrapped by
+TextEncoder / CLIP_selector at :113-166).  Eval-mode only: BatchNorm is folded into the preceding conv at load
+(w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)); ReLU and the residual add run in the GEMM epilogue.
+Batched: the reference runs both nets at batch 1 with autograd on (all_utils/utils.py:360-361, :171-172) and
+re-runs the CLIP text tower per image (:152-158); here images are batched and the text features cached."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import nn as snn
+from . import ops
+from .checkpoints import RESNET_LAYERS
+from .ops import ACT_NONE, ACT_QUICKGELU, ACT_RELU, BF16
+
+SD = Dict[str, torch.Tensor]
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)           # all_utils/dataset_utils.py:83-84
+CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)  # openai-clip _transform
+
+
+def _fold_bn(sd: SD, conv: str, bn: str, eps: float):
+    w = sd[conv + ".weight"].float()
+    g, b = sd[bn + ".weight"].float(), sd[bn + ".bias"].float()
+    m, v = sd[bn + ".running_mean"].float(), sd[bn + ".running_var"].float()
+    s = g / torch.sqrt(v + eps)
+    return w * s[:, None, None, None], b - m * s
+
+
+class ConvBN(snn.Conv):
+    def __init__(self, sd: SD, conv: str, bn: str, dev, stride=1, padding=None, eps=1e-5):
+        w, b = _fold_bn(sd, conv, bn, eps)
+        if w.shape[1] == 3:  # RGB stems read the 8-channel (zero-padded) normalised image: pad Cin 3 -> 8 with zero weights
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 5))
+        super().__init__(sd, conv, dev, stride=stride, padding=padding, weight=w, bias=b)
+
+
+class _Bottleneck:
+    """ResNet bottleneck.  torchvision-style (stride on the 3x3) for WSDAN; CLIP-style (avg-pool anti-aliasing
+    after the 3x3, avg-pool + 1x1 downsample) when ``clip`` is set."""
+
+    def __init__(self, sd: SD, p: str, dev, stride: int, clip: bool):
+        self.clip, self.stride = clip, stride
+        self.c1 = ConvBN(sd, p + ".conv1", p + ".bn1", dev)
+        self.c2 = ConvBN(sd, p + ".conv2", p + ".bn2", dev, stride=1 if clip else stride)
+        self.c3 = ConvBN(sd, p + ".conv3", p + ".bn3", dev)
+        self.down = None
+        if p + ".downsample.0.weight" in sd:
+            self.down = ConvBN(sd, p + ".downsample.0", p + ".downsample.1", dev, stride=1 if clip else stride, padding=0)
+
+    def __call__(self, x):
+        o = self.c1(x, act=ACT_RELU)
+        o = self.c2(o, act=ACT_RELU)
+        if self.clip and self.stride > 1:
+            o = ops.pool2d(o, self.stride, self.stride, 0, False)
+        idn = x
+        if self.down is not None:
+            xi = ops.pool2d(x, self.stride, self.stride, 0, False) if (self.clip and self.stride > 1) else x
+            idn = self.down(xi)
+        return self.c3(o, act=ACT_RELU, residual=idn, beta=1.0, act_after_residual=True)
+
+
+class WSDANClassifier:
+    """Eval forward of WSDAN_CAL -> logits p = fc(feature_matrix * 100) (the only output the filter reads,
+    all_utils/utils.py:361)."""
+
+    def __init__(self, sd: SD, num_classes: int, net: str = "resnet50", device="cuda"):
+        dev = torch.device(device)
+        sd = {k.replace("_orig_mod.", ""): v for k, v in sd.items()}  # torch.compile'd checkpoints (dataset_utils.py:101-102)
+        self.dev, self.num_classes = dev, num_classes
+        self.stem = ConvBN(sd, "features.0", "features.1", dev, stride=2, padding=3)
+        self.blocks: List[_Bottleneck] = []
+        for li, nb in enumerate(RESNET_LAYERS[net]):
+            stride = 1 if li in (0, 3) else 2  # layer4 stride 1 -> total stride 16 (resnet.py:118-119)
+            for b in range(nb):
+                self.blocks.append(_Bottleneck(sd, f"features.{4 + li}.{b}", dev, stride if b == 0 else 1, clip=False))
+        self.att = ConvBN(sd, "attentions.conv", "attentions.bn", dev, eps=1e-3)  # BasicConv2d (inception.py:374-384)
+        self.fc_w = sd["fc.weight"].detach().to(dev, torch.float32).contiguous()
+
+    def features(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.stem(x, act=ACT_RELU)
+        x = ops.pool2d(x, 3, 2, 1, True)
+        for b in self.blocks:
+            x = b(x)
+        return x
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x bf16 NHWC [n,224,224,8] (ImageNet-normalised, channels 3..7 zero) -> logits fp32 [n, classes]."""
+        f = self.features(x)
+        a = self.att(f, act=ACT_RELU)
+        n, h, w, c = f.shape
+        fm = ops.bap_head(f.view(n, h * w, c), a.view(n, h * w, a.shape[3]))
+        return ops.fc_f32(fm, self.fc_w, None)
+
+
+class CLIPRN50:
+    def __init__(self, sd: SD, device="cuda", heads: int = 32, text_heads: int = 8):
+        dev = torch.device(device)
+        self.dev, self.heads, self.text_heads = dev, heads, text_heads
+        v = "visual."
+        self.stem = [ConvBN(sd, v + "conv1", v + "bn1", dev, stride=2, padding=1), ConvBN(sd, v + "conv2", v + "bn2", dev), ConvBN(sd, v + "conv3", v + "bn3", dev)]
+        self.blocks: List[_Bottleneck] = []
+        li = 1
+        while f"{v}layer{li}.0.conv1.weight" in sd:
+            b = 0
+            while f"{v}layer{li}.{b}.conv1.weight" in sd:
+                self.blocks.append(_Bottleneck(sd, f"{v}layer{li}.{b}", dev, (1 if li == 1 else 2) if b == 0 else 1, clip=True))
+                b += 1
+            li += 1
+        a = v + "attnpool."
+        self.pos = snn._bf(sd[a + "positional_embedding"], dev)
+        self.q = snn.Linear(sd, a + "q_proj", dev)
+        self.kv = snn.Linear(sd, "", dev, weight=torch.cat([sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0),
+                             bias=torch.cat([sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0))
+        self.c = snn.Linear(sd, a + "c_proj", dev)
+        # text tower
+        self.tok = snn._bf(sd["token_embedding.weight"], dev)
+        self.tpos = snn._bf(sd["positional_embedding"], dev)
+        self.layers = []
+        i = 0
+        while f"transformer.resblocks.{i}.ln_1.weight" in sd:
+            q = f"transformer.resblocks.{i}."
+            self.layers.append({"ln1": snn.Norm(sd, q + "ln_1", dev), "ln2": snn.Norm(sd, q + "ln_2", dev),
+                                "qkv": snn.Linear(sd, "", dev, weight=sd[q + "attn.in_proj_weight"], bias=sd[q + "attn.in_proj_bias"]),
+                                "o": snn.Linear(sd, q + "attn.out_proj", dev), "fc1": snn.Linear(sd, q + "mlp.c_fc", dev),
+                                "fc2": snn.Linear(sd, q + "mlp.c_proj", dev)})
+            i += 1
+        self.ln_final = snn.Norm(sd, "ln_final", dev)
+        self.text_proj_t = snn._bf(sd["text_projection"].t().contiguous(), dev)  # [embed, width] K-major
+        self.logit_scale = float(sd["logit_scale"].exp())
+
+    def encode_image(self, x: torch.Tensor) -> torch.Tensor:
+        """x bf16 NHWC [n,224,224,8] (CLIP-normalised) -> fp32 [n, 1024]."""
+        for s in self.stem:
+            x = s(x, act=ACT_RELU)
+        x = ops.pool2d(x, 2, 2, 0, False)
+        for b in self.blocks:
+            x = b(x)
+        n, h, w, c = x.shape
+        t = h * w
+        mean = ops.pool2d(x, h, h, 0, False)  # [n,1,1,c] global mean token
+        tok = torch.empty((n, t + 1, c), dtype=BF16, device=x.device)
+        tok[:, 0].copy_(mean.view(n, c))  # token placement only
+        tok[:, 1:].copy_(x.view(n, t, c))
+        tok2 = ops.add(tok.view(n * (t + 1), c), self.pos.repeat(n, 1))
+        tok3 = tok2.view(n, t + 1, c)
+        q = self.q(tok3[:, 0])  # strided rows: first token of every image
+        kv = self.kv(tok2).view(n, t + 1, 2 * c)
+        a = ops.attention(q.view(n, 1, c), kv[..., :c], kv[..., c:], self.heads)
+        return self.c(a.view(n, c), out_fp32=True)
+
+    def encode_text(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids int64 [p, 77] -> fp32 [p, 1024] (features at the EOT token = argmax id, all_utils/utils.py:134)."""
+        p, t = ids.shape
+        c = self.tok.shape[1]
+        h = ops.add(self.tok.index_select(0, ids.reshape(-1)), self.tpos[:t].repeat(p, 1))
+        for L in self.layers:
+            y = ops.layernorm(h, 1e-5, L["ln1"].g, L["ln1"].b)
+            qkv = L["qkv"](y).view(p, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.text_heads, causal=True)
+            L["o"](a.view(p * t, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, 1e-5, L["ln2"].g, L["ln2"].b)
+            L["fc2"](L["fc1"](y, act=ACT_QUICKGELU), out=h, residual=h, beta=1.0)
+        x = ops.layernorm(h, 1e-5, self.ln_final.g, self.ln_final.b).view(p, t, c)
+        eot = x[torch.arange(p, device=x.device), ids.argmax(dim=-1)].contiguous()  # index plumbing
+        return ops.gemm(eot, self.text_proj_t, out_fp32=True)
+
+
+class AugmentationFilter:
+    """keep = (label in top-k(WSDAN logits)) AND (argmax CLIP(img, [basic prompt, 6 negatives]) == 0)
+    (all_utils/utils.py:357-365, :169-177, :401-404), on batches of u8 images resident on the device."""
+
+    def __init__(self, classifier: Optional[WSDANClassifier], clip: Optional[CLIPRN50], prompt_ids: Optional[torch.Tensor], conf_top_k: int = 10,
+                 micro_batch: int = 64):
+        self.classifier, self.clip, self.micro_batch = classifier, clip, micro_batch
+        self.conf_top_k = min(conf_top_k, classifier.num_classes) if classifier is not None else conf_top_k
+        self.text_features = clip.encode_text(prompt_ids.to(clip.dev)) if (clip is not None and prompt_ids is not None) else None
+
+    @torch.no_grad()
+    def __call__(self, images_u8: torch.Tensor, labels: torch.Tensor):
+        """images u8 [n,H,W,3] (device), labels int32 [n] -> dict(keep, in_topk, semantic, topk_margin, clip_logits)."""
+        n = images_u8.shape[0]
+        dev = images_u8.device
+        in_topk = torch.ones(n, dtype=torch.uint8, device=dev)
+        sem = torch.ones(n, dtype=torch.uint8, device=dev)
+        margin = torch.zeros(n, dtype=torch.float32, device=dev)
+        clip_logits = None
+        H, W = images_u8.shape[1:3]
+        for i0 in range(0, n, self.micro_batch):
+            i1 = min(i0 + self.micro_batch, n)
+            img = images_u8[i0:i1].contiguous()
+            if self.classifier is not None:
+                r = ops.resize_pil(img, 256, 256, "bilinear")                       # Resize((256,256)) on PIL
+                x = ops.crop_normalize(r, 16, 16, 224, 224, IMAGENET_MEAN, IMAGENET_STD, out_c=8)  # CenterCrop(224), ToTensor, Normalize
+                logits = self.classifier(x)
+                k, m = ops.topk_contains(logits, labels[i0:i1].contiguous(), self.conf_top_k)
+                in_topk[i0:i1] = k
+                margin[i0:i1] = m
+            if self.clip is not None:
+                # Resize(224): shorter side -> 224 keeping aspect (bicubic), then CenterCrop(224)
+                if H <= W:
+                    oh, ow = 224, int(224 * W / H)
+                else:
+                    oh, ow = int(224 * H / W), 224
+                r = ops.resize_pil(img, oh, ow, "bicubic")
+                cy, cx = int(round((oh - 224) / 2.0)), int(round((ow - 224) / 2.0))
+                x = ops.crop_normalize(r, cy, cx, 224, 224, CLIP_MEAN, CLIP_STD, out_c=8)
+                feats = self.clip.encode_image(x)
+                lg, arg = ops.clip_score_argmax(feats, self.text_features, self.clip.logit_scale)
+                sem[i0:i1] = (arg == 0).to(torch.uint8)
+                clip_logits = lg if clip_logits is None else torch.cat([clip_logits, lg], 0)
+        return {"keep": in_topk & sem, "in_topk": in_topk, "semantic": sem, "topk_margin": margin, "clip_logits": clip_logits}

@@ -1,0 +1,196 @@
+"""Post-generation filter + aug-JSON writer: host-side mirror of the reference's
+``all_utils.utils.create_json_of_image_name_to_augmented_images_paths`` (all_utils/utils.py:221-465) and
+``get_aug_json_path`` (:194-218).  Same names, argument meaning, file naming, JSON layout and error behaviour;
+the two enabled filters of run_aug.py (semantic_filtering + model_confidence_based_filtering, run_aug.py:551-556,
+:721-733) run batched on the B200 kernels (saspa_aug_b200.filter_nets) instead of batch-1 torch calls.
+
+JSON contract (consumed by fgvc/datasets/aug_wrapper_dataset.py:106-186): one object, key per source image in
+dataset order = ``Path(src).name``, value = list (possibly empty) of full path strings of kept augmentations in
+``os.listdir`` order, written with ``json.dump`` defaults.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+MAX_FILE_NAME_LENGTH = 40  # all_utils/utils.py:341; run_aug.py MAX_FILENAME_LENGTH
+SUBSTRINGS_TO_EXCLUDE = ["_source.", "_style.", "_target.", "_control.", "_original.", "_subject.", "subject_"]  # utils.py:246
+SEMANTIC_NEGATIVE_PROMPTS = ["a photo of an object", "a photo of a scene", "a photo of geometric shapes", "a photo", "an image", "a black photo"]  # utils.py:306
+
+
+def get_aug_json_path(augmented_image_folder_path, lpips_min=None, lpips_max=None, clip_filtering=False, clip_filtering_discount=1,
+                      semantic_filtering=False, model_confidence_based_filtering=False, conf_top_k: int = 10,
+                      filter_confidence_higher_than: int = None, alia_conf_filtering=False):
+    """all_utils/utils.py:194-218."""
+    name = ""
+    if lpips_min:
+        name += f"lpips_min_{lpips_min}-"
+    if lpips_max:
+        name += f"lpips_max_{lpips_max}-"
+    if clip_filtering:
+        name += f"clip_filtering_{clip_filtering}_discount_{clip_filtering_discount}-"
+    if semantic_filtering:
+        name += "semantic_filtering-"
+    if model_confidence_based_filtering:
+        name += f"model_confidence_based_filtering_top_{conf_top_k}_classes-"
+        if filter_confidence_higher_than:
+            name += f"filter_confidence_higher_than_{filter_confidence_higher_than}-"
+    if alia_conf_filtering:
+        name += "alia_conf_filtering-"
+    name += "aug.json"
+    return str(Path(augmented_image_folder_path).parent / name)
+
+
+def check_folder_of_images_with_pil(folder, max_delete=50, substrings_to_exclude=()):
+    """all_utils/utils.py:681-703: PIL-verify every image, delete the corrupt ones (at most ``max_delete``)."""
+    from PIL import Image
+
+    deleted = 0
+    for p in sorted(Path(folder).glob("*.*")):
+        if any(s in p.name for s in substrings_to_exclude):
+            continue
+        try:
+            with Image.open(p) as im:
+                im.verify()
+        except Exception:
+            if deleted >= max_delete:
+                raise RuntimeError(f"more than {max_delete} corrupt images in {folder}")
+            logging.info(f"deleting corrupt image {p}")
+            p.unlink()
+            deleted += 1
+    return deleted
+
+
+def match_augmentations(original_images_paths: Sequence[str], all_file_names: Sequence[str], folder: str) -> Dict[str, List[str]]:
+    """Matching rule of all_utils/utils.py:343-355: an augmentation belongs to a source iff stem[:40] is a SUBSTRING of its
+    file name (exclusion substrings already removed).  Keys keep dataset order, values keep listdir order."""
+    out: Dict[str, List[str]] = {}
+    for image_path in original_images_paths:
+        name = Path(image_path).name
+        stem = Path(name).stem[:MAX_FILE_NAME_LENGTH]
+        out[name] = [str(Path(folder) / f) for f in all_file_names if stem in f]
+    return out
+
+
+def get_dict_of_value_counts(d: Dict[str, List[str]]) -> Dict[int, int]:
+    """utils.py:468-482: histogram {n_kept: n_sources}."""
+    counts: Dict[int, int] = {}
+    for v in d.values():
+        counts[len(v)] = counts.get(len(v), 0) + 1
+    return dict(sorted(counts.items()))
+
+
+def _load_batches(paths: Sequence[str], batch: int):
+    """Decode PNGs on the host (PIL, as the reference does at utils.py:360,404) and group equal-sized images."""
+    from PIL import Image
+
+    by_shape: Dict[Tuple[int, int], List[Tuple[int, np.ndarray]]] = {}
+    for i, p in enumerate(paths):
+        a = np.asarray(Image.open(p).convert("RGB"))
+        by_shape.setdefault(a.shape[:2], []).append((i, a))
+    for items in by_shape.values():
+        for j in range(0, len(items), batch):
+            chunk = items[j : j + batch]
+            yield [c[0] for c in chunk], np.stack([c[1] for c in chunk])
+
+
+def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image_folder_path, lpips_min=None, lpips_max=None,
+                                                        resize: Tuple = (256, 256), clip_filtering=False, clip_filtering_discount=1,
+                                                        semantic_filtering=False, model_confidence_based_filtering=False, conf_top_k: int = 10,
+                                                        filter_confidence_higher_than: int = None, init_log=True, alia_conf_filtering=False, *,
+                                                        ds_utils=None, filter_models: Optional[Callable] = None, device="cuda", batch_size: int = 64,
+                                                        return_details: bool = False):
+    """Drop-in for all_utils/utils.py:221-465 (same positional signature).  Keyword-only extras:
+      ds_utils       dataset-utils object (default: saspa_aug_b200.datasets.DS_UTILS_DICT[dataset]())
+      filter_models  callable(ds_utils, device) -> (WSDANClassifier | None, CLIPRN50 | None, tokenizer) (default: ds_utils.load_filter_models)
+    """
+    import torch
+
+    from .filter_nets import AugmentationFilter
+
+    assert not (clip_filtering and model_confidence_based_filtering), "can't use both clip_filtering and model_confidence_based_filtering"
+    for flag, nm in ((lpips_min, "lpips_min"), (lpips_max, "lpips_max"), (clip_filtering, "clip_filtering"), (alia_conf_filtering, "alia_conf_filtering"),
+                     (filter_confidence_higher_than, "filter_confidence_higher_than")):
+        if flag:  # disabled in run_aug.py (LPIPS_*=None, CLIP_FILTERING_TYPE=None, ALIA_CONF_FILTERING=0); SURVEY.md 2.1 row 4b
+            raise NotImplementedError(f"{nm}: this filter is disabled on the reference's hot path and is not built (see DESIGN.md, out of scope)")
+    if not augmented_image_folder_path.endswith("/images"):
+        augmented_image_folder_path = str(Path(augmented_image_folder_path) / "images")
+    json_path = get_aug_json_path(augmented_image_folder_path, lpips_min, lpips_max, clip_filtering, clip_filtering_discount, semantic_filtering,
+                                  model_confidence_based_filtering, conf_top_k, filter_confidence_higher_than, alia_conf_filtering)
+    if init_log:
+        logging.info(f"log file: {json_path.replace('.json', '.log')}")
+    logging.info(f"json_path = {json_path}")
+    check_folder_of_images_with_pil(augmented_image_folder_path, max_delete=50, substrings_to_exclude=SUBSTRINGS_TO_EXCLUDE)
+    if ds_utils is None:
+        from .datasets import DS_UTILS_DICT
+
+        ds_utils = DS_UTILS_DICT[dataset](print_func=logging.info)
+    original_images_paths_list = ds_utils.original_images_paths
+    if len(list(Path(augmented_image_folder_path).glob("*.*"))) < 10:
+        logging.info(f"augmented_image_folder_path = {augmented_image_folder_path} doesn't exist or has less than 10 images")
+        augmented_image_folder_path = str(Path(augmented_image_folder_path) / "images")
+        if len(list(Path(augmented_image_folder_path).glob("*.*"))) < 10:
+            raise FileNotFoundError(f"augmented_image_folder_path = {augmented_image_folder_path} doesn't exist or has less than 10 images")
+
+    classifier = clip = tokenizer = None
+    if semantic_filtering or model_confidence_based_filtering:
+        loader = filter_models or ds_utils.load_filter_models
+        classifier, clip, tokenizer = loader(ds_utils, device)
+    prompt_ids = None
+    if semantic_filtering:
+        prompts = [ds_utils.get_basic_prompt()] + SEMANTIC_NEGATIVE_PROMPTS
+        logging.info(f"using semantic filtering with prompts = {prompts}")
+        prompt_ids = tokenizer(prompts)
+    if model_confidence_based_filtering:
+        image_path_to_class_id = ds_utils.get_image_path_to_class_id_dict()
+        conf_top_k = min(conf_top_k, ds_utils.num_classes)
+        logging.info(f"using model_confidence_based_filtering with conf_top_k = {conf_top_k}")
+    flt = AugmentationFilter(classifier if model_confidence_based_filtering else None, clip if semantic_filtering else None, prompt_ids, conf_top_k,
+                             micro_batch=batch_size)
+
+    all_file_names = [f for f in os.listdir(augmented_image_folder_path) if not any(s in f for s in SUBSTRINGS_TO_EXCLUDE)]
+    matched = match_augmentations(original_images_paths_list, all_file_names, augmented_image_folder_path)
+    # flatten (source, aug) pairs, run the nets batched, scatter the decisions back
+    pairs: List[Tuple[str, str, int]] = []
+    for image_path in original_images_paths_list:
+        name = Path(image_path).name
+        label = int(image_path_to_class_id[image_path]) if model_confidence_based_filtering else 0
+        for p in matched[name]:
+            pairs.append((name, p, label))
+    in_topk = np.ones(len(pairs), np.uint8)
+    sem = np.ones(len(pairs), np.uint8)
+    if (semantic_filtering or model_confidence_based_filtering) and pairs:
+        dev = torch.device(device)
+        for idx, imgs in _load_batches([p[1] for p in pairs], batch_size):
+            labels = torch.tensor([pairs[i][2] for i in idx], dtype=torch.int32, device=dev)
+            out = flt(torch.from_numpy(imgs).to(dev), labels)
+            in_topk[idx] = out["in_topk"].cpu().numpy()
+            sem[idx] = out["semantic"].cpu().numpy()
+    # the reference applies the confidence filter first, then the semantic filter on the survivors (utils.py:357-404)
+    result: Dict[str, List[str]] = {Path(p).name: [] for p in original_images_paths_list}
+    n_topk = n_sem = 0
+    for (name, path, _), a, b in zip(pairs, in_topk, sem):
+        if model_confidence_based_filtering and not a:
+            n_topk += 1
+            continue
+        if semantic_filtering and not b:
+            n_sem += 1
+            continue
+        result[name].append(path)
+    Path(json_path).parent.mkdir(parents=True, exist_ok=True)
+    with open(json_path, "w") as f:
+        json.dump(result, f)
+    logging.info(f"Finished creating json of image name to augmented images paths in: \n{json_path}")
+    if semantic_filtering:
+        logging.info(f"For filter = semantic_filtering, filtered {n_sem} images")
+    if model_confidence_based_filtering:
+        logging.info(f"For filter = not_in_top_{conf_top_k}, filtered {n_topk} images")
+    logging.info(f"dict_num_augmentations_per_image = {get_dict_of_value_counts(result)}")
+    if return_details:
+        return json_path, {"pairs": pairs, "in_topk": in_topk, "semantic": sem}
+    return json_path

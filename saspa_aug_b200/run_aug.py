@@ -1,0 +1,302 @@
+"""Sharded generation driver: host-side mirror of the reference's ``run_aug/run_aug.py`` for the ControlNet-canny path.
+
+Kept from the reference (names / defaults / behaviour): the module-level constants as ``AugConfig`` fields
+(run_aug.py:513-577), ``init_pipeline`` (:128-230), ``pass_thorugh_pipe`` (:233-279), the output-folder and file naming
+(:668-692, :377, :429, :442), prompt post-processing (:342-346, :380-394), skip-if-exists resume (:430-432), the error
+policy (RuntimeError logged, loop ends; :493-500) and the final filter + JSON call (:721-733).
+
+B200-first differences: one process per GPU; sources are partitioned ``index % world == rank`` with NO collective in the
+loop; Canny runs once per source on the GPU (the reference recomputes it per prompt on the CPU, :436-437); prompts of a
+micro-batch are generated together; PNG encoding runs in a thread pool; the only collective is one gather of the
+per-image filter records before rank 0 writes the JSON.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import random
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+NEGATIVE_PROMPT = ("over-exposure, under-exposure, saturated, duplicate, out of frame, lowres, cropped, worst quality, low quality, jpeg artifacts, morbid, "
+                   "mutilated, out of frame, ugly, bad anatomy, bad proportions, deformed, blurry, duplicate")  # the run constant of run_aug.py:47
+MAX_FILENAME_LENGTH = 40
+MAX_PROMPT_LENGTH = 150
+
+
+@dataclass
+class AugConfig:
+    """The reference's module-level constants (run_aug.py:513-556) with their shipped defaults."""
+    DATASET: str = "synthetic"
+    BASE_MODEL: str = "sd_v1.5"
+    CONTROLNET: Optional[str] = "canny"
+    SDEDIT: int = 0
+    NUM_PER_IMAGE: int = 2
+    SEED: int = 1
+    RESOLUTION: int = 512
+    GUIDANCE_SCALE: float = 7.5
+    NUM_INFERENCE_STEPS: int = 30
+    SDEDIT_STRENGTH: float = 0.85
+    LOW_THRESHOLD_CANNY: int = 120
+    HIGH_THRESHOLD_CANNY: int = 200
+    CONTROLNET_CONDITIONING_SCALE: float = 0.75
+    PROMPT_TYPE: str = "gpt-meta_class"
+    PROMPT_WITH_SUB_CLASS: bool = False
+    USE_ARTISTIC_PROMPTS: bool = False
+    ARTISTIC_PROMPTS_PROB: float = 0.5
+    SEMANTIC_FILTERING: int = 1
+    MODEL_CONFIDENCE_BASED_FILTERING: int = 1
+    CONF_TOP_K: int = 10
+    SAMPLER: str = "ddim"
+    RNG_MODE: str = "per_item"  # "per_item" (partition independent) | "reference_order" (replays the global generator)
+    MICRO_BATCH: int = 16
+
+    def apply_dataset_rules(self):
+        """run_aug.py:560-577."""
+        if self.DATASET == "cars":
+            self.NUM_INFERENCE_STEPS = 50
+        if self.BASE_MODEL == "sd_xl-turbo":
+            self.GUIDANCE_SCALE, self.NUM_INFERENCE_STEPS = 0.0, 2
+        if self.SDEDIT:
+            assert self.NUM_INFERENCE_STEPS * self.SDEDIT_STRENGTH >= 1, "NUM_INFERENCE_STEPS * SDEDIT_STRENGTH must be >= 1"
+        return self
+
+
+ARTISTIC_PROMPTS = ["a painting", "a sketch", "a watercolor", "an oil painting", "a pencil drawing"]  # stand-in list (prompts_engineering assets are data)
+
+
+def output_folder(ds_root: str, cfg: AugConfig) -> str:
+    """run_aug.py:668-692."""
+    base = f"{cfg.BASE_MODEL}-SDEdit_strength_{cfg.SDEDIT_STRENGTH}" if cfg.SDEDIT else cfg.BASE_MODEL
+    kind = "controlnet" if cfg.CONTROLNET else "regular"
+    prompt_str = cfg.PROMPT_TYPE
+    if cfg.PROMPT_WITH_SUB_CLASS:
+        prompt_str += "_prompt_w_sub_class"
+    if cfg.USE_ARTISTIC_PROMPTS:
+        prompt_str += f"_artistic_prompts_p_{cfg.ARTISTIC_PROMPTS_PROB}"
+    return str(Path(ds_root) / "aug_data" / kind / base / str(cfg.CONTROLNET) / f"{prompt_str}_seed_{cfg.SEED}" / "images")
+
+
+def aug_file_name(image_stem: str, prompt: str, i: int) -> str:
+    """run_aug.py:429."""
+    return f"{image_stem[:MAX_FILENAME_LENGTH]}_prompt_{prompt.replace('/', '-')}_{i}.png"
+
+
+def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
+    """all_utils/utils.py:58-79 (host-side pre-processing; identity for sources already at HxW % 64 == 0, min side = res)."""
+    import cv2
+
+    MAX_RES_SIZE = 1200000
+    H, W, _ = input_image.shape
+    H, W = float(H), float(W)
+    k = float(smaller_side_res) / min(H, W)
+    H *= k
+    W *= k
+    if H * W > MAX_RES_SIZE:
+        k = np.sqrt(MAX_RES_SIZE / (H * W))
+        H *= k
+        W *= k
+    H = int(np.round(H / 64.0)) * 64
+    W = int(np.round(W / 64.0)) * 64
+    if (H, W) == input_image.shape[:2]:
+        return input_image
+    return cv2.resize(input_image, (W, H), interpolation=cv2.INTER_LANCZOS4 if k > 1 else cv2.INTER_AREA)
+
+
+def HWC3(x: np.ndarray) -> np.ndarray:
+    """all_utils/utils.py:39-55."""
+    assert x.dtype == np.uint8
+    if x.ndim == 2:
+        x = x[:, :, None]
+    H, W, C = x.shape
+    assert C in (1, 3, 4)
+    if C == 3:
+        return x
+    if C == 1:
+        return np.concatenate([x, x, x], axis=2)
+    color = x[:, :, 0:3].astype(np.float32)
+    alpha = x[:, :, 3:4].astype(np.float32) / 255.0
+    return (color * alpha + 255.0 * (1.0 - alpha)).clip(0, 255).astype(np.uint8)
+
+
+def generate_canny(cond_image_input, low_threshold, high_threshold, image_resolution):
+    """Drop-in for all_utils/utils.py:102-109: PIL | ndarray -> PIL RGB edge map (0/255), computed by saspa_canny_u8."""
+    import torch
+    from PIL import Image
+
+    from . import ops
+
+    img = resize_image(HWC3(np.array(cond_image_input).astype(np.uint8)), image_resolution)
+    t = torch.from_numpy(np.ascontiguousarray(img)[None]).cuda()
+    edges, _ = ops.canny(t, int(low_threshold), int(high_threshold), out_channels=3)
+    return Image.fromarray(edges[0].cpu().numpy())
+
+
+def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="ddim", state_dicts=None, device="cuda"):
+    """run_aug.py:128-230 for the ControlNet-canny SD v1.5 architecture.  ``use_compile`` is accepted and ignored (the
+    launch list is replayed by CUDA graphs, not traced).  Weights: ``state_dicts`` (diffusers-keyed) or deterministic
+    random init -- no checkpoints exist offline."""
+    from .pipelines import SaspaControlNetPipeline, random_state_dicts
+
+    assert sampler in ["ddim", "unipcmultistep"]
+    if base_model not in ("sd_v1.5", "blip_diffusion", "tiny"):
+        raise NotImplementedError(f"base_model {base_model!r}: only the SD v1.5-architecture ControlNet path is built in round 1 (see DESIGN.md)")
+    assert controlnet in ("canny",), "only the canny ControlNet is on the hot path"
+    cfg = "tiny" if base_model == "tiny" else "sd15"
+    sds = state_dicts or random_state_dicts(cfg, 1234)
+    from . import checkpoints as ck
+
+    kw = {}
+    if cfg == "tiny":
+        kw = dict(unet_cfg=ck.UNetConfig.tiny(), vae_cfg=ck.VAEConfig.tiny(), text_cfg=ck.CLIPTextConfig.tiny())
+    smp = "pndm" if base_model == "blip_diffusion" else ("unipc" if sampler == "unipcmultistep" else "ddim")
+    return SaspaControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sampler=smp, device=device, img2img=bool(SDEdit), **kw)
+
+
+def pass_thorugh_pipe(base_model, pipe, prompt, orig_img, SDEdit, SDEdit_strength, num_inference_steps, generator, guidance_scale, control_cond_scale,
+                      negative_prompt=NEGATIVE_PROMPT, control_image=None, blip_src_category=None, blip_target_category=None):
+    """run_aug.py:233-279 (same kwargs assembly, same return)."""
+    pipe_args = {"prompt": str(prompt), "num_inference_steps": num_inference_steps, "generator": generator, "guidance_scale": guidance_scale,
+                 "negative_prompt": negative_prompt}
+    if control_image is not None:
+        if SDEdit:
+            pipe_args["control_image"] = control_image
+            pipe_args["controlnet_conditioning_scale"] = control_cond_scale
+        else:
+            pipe_args["image"] = control_image
+            pipe_args["controlnet_conditioning_scale"] = control_cond_scale
+    if SDEdit:
+        pipe_args["image"] = orig_img
+        pipe_args["strength"] = SDEdit_strength
+    return pipe(**pipe_args).images[0]
+
+
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """rank r of W takes source indices {i : i % W == r}; both augmentations of a source stay on one rank."""
+    return [i for i in range(n) if i % world == rank]
+
+
+def item_seed(seed: int, index: int, i: int) -> int:
+    """Per-item generator seed, independent of the partitioning (RNG_MODE = per_item)."""
+    return (seed * 1_000_003 + index * 131 + i) % (2 ** 31 - 1)
+
+
+def sample_prompts(prompts: Sequence[str], n_sources: int, cfg: AugConfig) -> List[List[str]]:
+    """Rank-independent pre-pass replaying the reference's sequential global draws (run_aug.py:382, :391-394):
+    np.random.seed(SEED) then one np.random.choice(prompts, NUM_PER_IMAGE) per source in dataset order."""
+    rs = np.random.RandomState(cfg.SEED)
+    prompts = [p.strip()[:MAX_PROMPT_LENGTH] for p in prompts]
+    prompts = [p[:-1] if p and p[-1] == "." else p for p in prompts]
+    out = []
+    for _ in range(n_sources):
+        chosen = list(rs.choice(prompts, cfg.NUM_PER_IMAGE))
+        for i in range(len(chosen)):
+            if cfg.USE_ARTISTIC_PROMPTS and i % 2 == 0 and cfg.ARTISTIC_PROMPTS_PROB == 0.5:
+                chosen[i] = f"{chosen[i]}, {rs.choice(ARTISTIC_PROMPTS)}"
+        out.append([str(c) for c in chosen])
+    return out
+
+
+def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: str, rank: int = 0, world: int = 1, io_threads: int = 8):
+    """The generation loop (run_aug.py:357-471) for this rank's shard.  Returns the list of (source index, i, path)."""
+    import torch
+    from PIL import Image
+
+    from . import ops
+
+    Path(out_dir).mkdir(parents=True, exist_ok=True)
+    paths = ds_utils.original_images_paths
+    sampled = sample_prompts(prompts, len(paths), cfg)
+    mine = shard_indices(len(paths), rank, world)
+    pool = ThreadPoolExecutor(max_workers=io_threads)
+    written = []
+    work = []  # (index, i, prompt, output_path)
+    sources = {}
+    num_errors = 0
+    try:
+        for index in mine:
+            stem = Path(paths[index]).stem
+            img = resize_image(np.array(Image.open(paths[index]).convert("RGB")), cfg.RESOLUTION)
+            src_out = os.path.join(out_dir, f"{stem[:MAX_FILENAME_LENGTH]}_source.png")
+            if not os.path.exists(src_out):
+                pool.submit(Image.fromarray(img).save, src_out)
+            for i, prompt in enumerate(sampled[index]):
+                out_path = Path(out_dir) / aug_file_name(stem, prompt, i)
+                if out_path.exists():  # resume (run_aug.py:430-432)
+                    logging.info(f"Skipping {out_path} as it already exists")
+                    written.append((index, i, str(out_path)))
+                    continue
+                sources[index] = img
+                work.append((index, i, prompt, str(out_path)))
+        dev = pipe.device
+        neg = pipe._neg_embeds(NEGATIVE_PROMPT, 1)
+        for b0 in range(0, len(work), cfg.MICRO_BATCH):
+            chunk = work[b0 : b0 + cfg.MICRO_BATCH]
+            uniq = sorted({w[0] for w in chunk})
+            shapes = {sources[u].shape for u in uniq}
+            if len(shapes) != 1:  # mixed resolutions: fall back to per-source batches
+                raise RuntimeError("mixed source resolutions in one micro-batch; set MICRO_BATCH = NUM_PER_IMAGE for non-uniform datasets")
+            src_t = torch.from_numpy(np.stack([sources[u] for u in uniq])).to(dev)
+            edges, ctrl = ops.canny(src_t, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, out_channels=3, want_ctrl=True)
+            sel = torch.tensor([uniq.index(w[0]) for w in chunk], device=dev)
+            for u_i, u in enumerate(uniq):
+                if u < 10:  # first 10 control images are saved (run_aug.py:441-442)
+                    cp = os.path.join(out_dir, f"{Path(paths[u]).stem[:MAX_FILENAME_LENGTH]}_control.png")
+                    if not os.path.exists(cp):
+                        pool.submit(Image.fromarray(edges[u_i].cpu().numpy()).save, cp)
+            ids = pipe.tokenizer([w[2] for w in chunk])
+            text = pipe.encode_prompt_ids(ids)
+            H, W = src_t.shape[1:3]
+            shape = (1, pipe.vae_cfg.latent_channels, H // 8, W // 8)
+            noise, post = [], []
+            for (index, i, _, _) in chunk:
+                g = torch.Generator().manual_seed(item_seed(cfg.SEED, index, i))
+                if cfg.SDEDIT:
+                    post.append(torch.randn(shape, generator=g))
+                noise.append(torch.randn(shape, generator=g))
+            noise = torch.cat(noise).to(dev)
+            post = torch.cat(post).to(dev) if cfg.SDEDIT else None
+            try:
+                imgs = pipe.generate_batch(text, neg.expand(len(chunk), -1, -1).contiguous(), None, src_t.index_select(0, sel) if cfg.SDEDIT else None,
+                                           noise=noise, noise_posterior=post, num_inference_steps=cfg.NUM_INFERENCE_STEPS, guidance_scale=cfg.GUIDANCE_SCALE,
+                                           strength=cfg.SDEDIT_STRENGTH, controlnet_conditioning_scale=cfg.CONTROLNET_CONDITIONING_SCALE,
+                                           control_bf16=ctrl.index_select(0, sel))
+            except RuntimeError as e:  # the reference logs OOM-style errors and leaves the loop (run_aug.py:493-500)
+                logging.exception(e)
+                num_errors += 1
+                break
+            arr = imgs.cpu().numpy()
+            for (index, i, _, out_path), a in zip(chunk, arr):
+                pool.submit(Image.fromarray(a).save, out_path)
+                written.append((index, i, out_path))
+    finally:
+        pool.shutdown(wait=True)
+    logging.info(f"Done Generating ({len(written)} files on rank {rank}, {num_errors} errors)")
+    return written
+
+
+def gather_records(records: np.ndarray, rank: int, world: int):
+    """The ONE collective of the path: fixed-size per-image filter records -> rank 0 (torch.distributed all_gather over
+    NCCL/NVLink on GPUs, gloo in CPU tests).  records: int32 [n_local, k]; ranks may hold different n_local."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return records
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    m = int(max(s.item() for s in sizes))
+    k = records.shape[1]
+    buf = torch.full((m, k), -1, dtype=torch.int32, device=dev)
+    if records.shape[0]:
+        buf[: records.shape[0]] = torch.from_numpy(records).to(dev)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return np.concatenate([o[: int(s.item())].cpu().numpy() for o, s in zip(out, sizes)], 0)

@@ -76,3 +76,69 @@ def test_clip_score_argmax(cuda_device):
     ref = 100.0 * F.normalize(img, dim=-1) @ F.normalize(txt, dim=-1).t()
     assert (logits - ref).abs().max().item() < 1e-3
     assert torch.equal(arg.long(), ref.argmax(-1))
+
+
+def _filter_fixture():
+    import json
+
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200.filter_nets import CLIPRN50, AugmentationFilter, WSDANClassifier
+    from saspa_aug_b200.synthetic import synthetic_token_ids
+
+    meta = json.load(open(os.path.join(G, "filter_golden.json")))
+    gold = np.load(os.path.join(G, "filter_golden.npz"))
+    wsd = ck.random_filter_state_dict(ck.wsdan_shapes(meta["classes"], "resnet50"), meta["wsdan_seed"])
+    csd = ck.random_filter_state_dict(ck.clip_rn50_shapes(), meta["clip_seed"])
+    ids = torch.cat([synthetic_token_ids(s) for s in meta["prompt_id_seeds"]])
+    flt = AugmentationFilter(WSDANClassifier(wsd, meta["classes"], "resnet50"), CLIPRN50(csd), ids, conf_top_k=10)
+    return meta, gold, flt, wsd, csd, ids
+
+
+def test_filter_nets_match_reference_golden(cuda_device):
+    """WSDAN_CAL logits and CLIP_selector logits of the REFERENCE code (tests/golden/make_filter_golden.py) on the
+    same seeds; bf16 trunk vs the reference's fp32: tolerance 5e-2 on logits with std ~0.4 / CLIP logits O(1)."""
+    meta, gold, flt, *_ = _filter_fixture()
+    imgs = torch.from_numpy(np.stack([synthetic_source(s) for s in meta["image_seeds"]])).cuda()
+    r = ops.resize_pil(imgs, 256, 256, "bilinear")
+    x = ops.crop_normalize(r, 16, 16, 224, 224, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), out_c=8)
+    logits = flt.classifier(x).cpu().numpy()
+    err = np.abs(logits - gold["wsdan_logits"]).max()
+    print("wsdan logits max err", err, "std", gold["wsdan_logits"].std())
+    assert err < 5e-2, err
+    out = flt(imgs, torch.zeros(len(meta["image_seeds"]), dtype=torch.int32, device="cuda"))
+    cerr = np.abs(out["clip_logits"].cpu().numpy() - gold["clip_logits"]).max()
+    print("clip logits max err", cerr)
+    assert cerr < 5e-2, cerr
+    assert (out["semantic"].cpu().numpy() == gold["semantic_keep"]).all()
+
+
+def test_filter_decisions_identical_to_oracle(cuda_device):
+    """Keep/drop decisions on 48 synthetic images vs the fp32 oracle nets (WSDAN restatement pinned to the reference;
+    CLIP restatement).  Decisions must be identical; margins are printed so a near-tie flip is diagnosable."""
+    from oracle import clip_rn50, wsdan
+    from tests.test_filter_oracle_cpu import preprocess_baseline, preprocess_clip
+    import torch.nn.functional as F
+
+    meta, gold, flt, wsd, csd, ids = _filter_fixture()
+    n = 48
+    src = np.stack([synthetic_source(700 + i, kind=("blobs", "noise", "smooth")[i % 3]) for i in range(n)])
+    labels = torch.arange(n, dtype=torch.int32) % meta["classes"]
+    om = wsdan.WSDANOracle(meta["classes"], "resnet50").eval()
+    om.load_state_dict(wsd, strict=False)
+    oc = clip_rn50.CLIP().eval()
+    oc.load_state_dict(csd)
+    with torch.no_grad():
+        lo = torch.cat([om(torch.stack([preprocess_baseline(s) for s in src[i:i + 8]])) for i in range(0, n, 8)])
+        fi = torch.cat([oc.encode_image(torch.stack([preprocess_clip(s) for s in src[i:i + 8]])) for i in range(0, n, 8)])
+        ft = oc.encode_text(ids)
+        cl = oc.logit_scale.exp() * F.normalize(fi, dim=-1) @ F.normalize(ft, dim=-1).t()
+    keep_topk = wsdan.in_topk(lo, labels.tolist(), 10)
+    keep_sem = (cl.argmax(-1) == 0).to(torch.uint8)
+    out = flt(torch.from_numpy(src).cuda(), labels.cuda())
+    srt = lo.sort(dim=-1, descending=True)[0]
+    gap = (srt[:, 9] - srt[:, 10]).min().item()
+    top2 = cl.topk(2, dim=-1)[0]
+    print(f"min 10th-11th logit gap {gap:.4g}; min CLIP top1-top2 gap {(top2[:, 0] - top2[:, 1]).min().item():.4g}; kept {int(keep_topk.sum())}/{n} topk, {int(keep_sem.sum())}/{n} semantic")
+    assert torch.equal(out["in_topk"].cpu(), keep_topk)
+    assert torch.equal(out["semantic"].cpu(), keep_sem)
+    assert torch.equal(out["keep"].cpu(), keep_topk & keep_sem)

@@ -1,0 +1,82 @@
+"""CPU: the filter-side oracles (WSDAN_CAL restatement, CLIP RN50 restatement driven through the reference's own
+CLIP_selector arithmetic) against the committed golden outputs of the reference code
+(tests/golden/make_filter_golden.py), and live against /root/reference when present."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import clib, clip_rn50, ref_import, wsdan
+from saspa_aug_b200 import checkpoints as ck
+from saspa_aug_b200.synthetic import synthetic_source, synthetic_token_ids
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+META = json.load(open(os.path.join(G, "filter_golden.json")))
+GOLD = np.load(os.path.join(G, "filter_golden.npz"))
+
+
+def preprocess_baseline(img_u8: np.ndarray) -> torch.Tensor:
+    """all_utils/dataset_utils.py:78-85 via the pinned PIL-resize oracle: Resize(256,256) -> CenterCrop(224) -> /255 -> Normalize."""
+    r = clib.pil_resize(img_u8, 256, 256, "bilinear")[16:240, 16:240]
+    x = torch.from_numpy(r.astype(np.float32) / 255.0).permute(2, 0, 1)
+    m, s = torch.tensor([0.485, 0.456, 0.406])[:, None, None], torch.tensor([0.229, 0.224, 0.225])[:, None, None]
+    return (x - m) / s
+
+
+def preprocess_clip(img_u8: np.ndarray) -> torch.Tensor:
+    h, w = img_u8.shape[:2]
+    oh, ow = (224, int(224 * w / h)) if h <= w else (int(224 * h / w), 224)
+    r = clib.pil_resize(img_u8, oh, ow, "bicubic")
+    cy, cx = int(round((oh - 224) / 2.0)), int(round((ow - 224) / 2.0))
+    x = torch.from_numpy(r[cy:cy + 224, cx:cx + 224].astype(np.float32) / 255.0).permute(2, 0, 1)
+    m = torch.tensor([0.48145466, 0.4578275, 0.40821073])[:, None, None]
+    s = torch.tensor([0.26862954, 0.26130258, 0.27577711])[:, None, None]
+    return (x - m) / s
+
+
+def test_wsdan_oracle_matches_reference_golden_logits():
+    sd = ck.random_filter_state_dict(ck.wsdan_shapes(META["classes"], "resnet50"), META["wsdan_seed"])
+    m = wsdan.WSDANOracle(META["classes"], "resnet50").eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing)
+    x = torch.stack([preprocess_baseline(synthetic_source(s)) for s in META["image_seeds"][:3]])
+    assert np.allclose(x[0, :, ::32, ::32].numpy(), GOLD["wsdan_input_sample"], atol=1e-6)  # the transform itself
+    with torch.no_grad():
+        logits = m(x)
+    assert np.allclose(logits.numpy(), GOLD["wsdan_logits"][:3], atol=2e-4), np.abs(logits.numpy() - GOLD["wsdan_logits"][:3]).max()
+
+
+def test_clip_oracle_matches_reference_selector_golden():
+    sd = ck.random_filter_state_dict(ck.clip_rn50_shapes(), META["clip_seed"])
+    c = clip_rn50.CLIP().eval()
+    c.load_state_dict(sd)
+    ids = torch.cat([synthetic_token_ids(s) for s in META["prompt_id_seeds"]])
+    with torch.no_grad():
+        x = torch.stack([preprocess_clip(synthetic_source(s)) for s in META["image_seeds"][:2]])
+        fi, ft = c.encode_image(x), c.encode_text(ids)
+        logits = c.logit_scale.exp() * F.normalize(fi, dim=-1) @ F.normalize(ft, dim=-1).t()
+    assert np.allclose(logits.numpy(), GOLD["clip_logits"][:2], atol=2e-4)
+    assert ((logits.argmax(-1) == 0).numpy().astype(np.uint8) == GOLD["semantic_keep"][:2]).all()
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_wsdan_oracle_against_reference_live_resnet101():
+    cal = ref_import.import_reference_cal()
+    sd = ck.random_filter_state_dict(ck.wsdan_shapes(17, "resnet101"), 5)
+    ref = cal.WSDAN_CAL(17, net="resnet101", print_func=lambda *a: None).eval()
+    ref.load_state_dict(sd)
+    mine = wsdan.WSDANOracle(17, "resnet101").eval()
+    mine.load_state_dict(sd, strict=False)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        assert torch.allclose(ref(x)[0], mine(x), atol=1e-4)
+
+
+def test_topk_rule():
+    # exact ties are implementation-defined in torch.topk (and measure-zero for fp32 logits); use distinct values
+    logits = torch.tensor([[0.1, 0.9, 0.5, 0.4], [1.0, 0.7, 0.8, 0.9]])
+    assert wsdan.in_topk(logits, [2, 1], 2).tolist() == [1, 0]
+    assert wsdan.in_topk(logits, [3, 3], 2).tolist() == [0, 1]

@@ -1,0 +1,102 @@
+"""CPU: host-side mirror of the reference interface -- JSON naming / layout, file naming, matching rule,
+sharding, and the world-size-2 gather (gloo)."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from saspa_aug_b200 import filtering, run_aug
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_json_names_match_reference_golden():
+    names = json.load(open(os.path.join(G, "filter_golden.json")))["json_names"]  # produced by the reference's get_aug_json_path
+    f = filtering.get_aug_json_path
+    assert f("/x/y/images", semantic_filtering=1, model_confidence_based_filtering=1) == names["sem+conf"]
+    assert f("/x/y/images") == names["none"]
+    assert f("/x/y/images", model_confidence_based_filtering=True, conf_top_k=5) == names["conf_top5"]
+    assert f("/x/y/images", lpips_min=0.1, lpips_max=0.7, clip_filtering="per_class", clip_filtering_discount=2, semantic_filtering=True,
+             alia_conf_filtering=True) == names["all"]
+    assert names["sem+conf"] == "/x/y/semantic_filtering-model_confidence_based_filtering_top_10_classes-aug.json"
+
+
+def test_matching_rule_and_exclusions():
+    srcs = ["/d/images/0001234.jpg", "/d/images/000123.jpg", "/d/images/" + "a" * 50 + ".png"]
+    files = ["0001234_prompt_a photo_0.png", "0001234_source.png", "0001234_control.png", "000123_prompt_x_1.png", "a" * 40 + "_prompt_p_0.png",
+             "subject_0.png"]
+    files = [f for f in files if not any(s in f for s in filtering.SUBSTRINGS_TO_EXCLUDE)]
+    m = filtering.match_augmentations(srcs, files, "/out/images")
+    assert list(m) == ["0001234.jpg", "000123.jpg", "a" * 50 + ".png"]
+    assert m["0001234.jpg"] == ["/out/images/0001234_prompt_a photo_0.png"]
+    # substring semantics of the reference: "000123" also matches the "0001234_..." file
+    assert m["000123.jpg"] == ["/out/images/0001234_prompt_a photo_0.png", "/out/images/000123_prompt_x_1.png"]
+    assert m["a" * 50 + ".png"] == ["/out/images/" + "a" * 40 + "_prompt_p_0.png"]
+    assert filtering.get_dict_of_value_counts(m) == {1: 2, 2: 1}
+
+
+def test_file_and_folder_naming():
+    cfg = run_aug.AugConfig(USE_ARTISTIC_PROMPTS=True, PROMPT_WITH_SUB_CLASS=True)
+    assert run_aug.output_folder("/data/planes", cfg) == \
+        "/data/planes/aug_data/controlnet/sd_v1.5/canny/gpt-meta_class_prompt_w_sub_class_artistic_prompts_p_0.5_seed_1/images"
+    cfg2 = run_aug.AugConfig(SDEDIT=1, SDEDIT_STRENGTH=0.5, CONTROLNET=None)
+    assert "/aug_data/regular/sd_v1.5-SDEdit_strength_0.5/None/" in run_aug.output_folder("/d", cfg2)
+    assert run_aug.aug_file_name("x" * 60, "a/b photo", 1) == "x" * 40 + "_prompt_a-b photo_1.png"
+    assert run_aug.AugConfig(BASE_MODEL="sd_xl-turbo").apply_dataset_rules().NUM_INFERENCE_STEPS == 2
+    with pytest.raises(AssertionError):
+        run_aug.AugConfig(SDEDIT=1, SDEDIT_STRENGTH=0.01).apply_dataset_rules()
+
+
+def test_resize_image_and_hwc3_match_reference_semantics():
+    img = np.zeros((375, 500, 3), np.uint8)
+    assert run_aug.resize_image(img, 512).shape == (512, 704, 3)
+    sq = np.random.default_rng(0).integers(0, 255, (512, 512, 3), dtype=np.uint8)
+    assert run_aug.resize_image(sq, 512) is sq
+    g = np.full((4, 4), 7, np.uint8)
+    assert run_aug.HWC3(g).shape == (4, 4, 3)
+    rgba = np.zeros((2, 2, 4), np.uint8)
+    assert (run_aug.HWC3(rgba) == 255).all()  # transparent over white
+
+
+def test_prompt_sampling_is_partition_independent():
+    cfg = run_aug.AugConfig(USE_ARTISTIC_PROMPTS=True)
+    prompts = [f"an airplane number {i}." for i in range(50)]
+    a = run_aug.sample_prompts(prompts, 12, cfg)
+    b = run_aug.sample_prompts(prompts, 12, cfg)
+    assert a == b and len(a) == 12 and all(len(x) == 2 for x in a)
+    assert all(not p.endswith(".") for x in a for p in x) and all("," in x[0] and "," not in x[1] for x in a)
+    parts = [run_aug.shard_indices(12, r, 4) for r in range(4)]
+    assert sorted(i for p in parts for i in p) == list(range(12)) and parts[1] == [1, 5, 9]
+    assert run_aug.item_seed(1, 5, 0) != run_aug.item_seed(1, 5, 1)
+
+
+_WORKER = r'''
+import os, sys, numpy as np, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from saspa_aug_b200 import run_aug
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+mine = run_aug.shard_indices(11, rank, world)
+rec = np.array([[i, i % 2, (i * 7) % 3] for i in mine], dtype=np.int32).reshape(-1, 3)
+allrec = run_aug.gather_records(rec, rank, world)
+if rank == 0:
+    allrec = allrec[np.argsort(allrec[:, 0])]
+    assert allrec.shape == (11, 3) and (allrec[:, 0] == np.arange(11)).all() and (allrec[:, 2] == (np.arange(11) * 7) % 3).all()
+    print("GATHER_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gather_gloo():
+    with tempfile.TemporaryDirectory() as d:
+        w = os.path.join(d, "worker.py")
+        open(w, "w").write(_WORKER)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29611", w, ROOT], capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
