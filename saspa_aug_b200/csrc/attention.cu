@@ -288,7 +288,18 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
+int g_attention_impl = 0;  // 0 = auto (tcgen05 when the shape has an instantiation), 1 = mma.sync flash kernel, 2 = tcgen05 only
+
 }  // namespace
+
+int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq,
+                       int tkv, int d, float scale, int causal, cudaStream_t stream);
+
+extern "C" int saspa_attention_impl(int impl) {
+  const int prev = g_attention_impl;
+  if (impl >= 0 && impl <= 2) g_attention_impl = impl;
+  return prev;
+}
 
 extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch,
                                     int heads, int tq, int tkv, int d, float scale, int causal, cudaStream_t stream) {
@@ -301,6 +312,11 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
                       (reinterpret_cast<uintptr_t>(o) & 3) == 0,
                   "saspa_attention_bf16: q/k/v must be 16-byte aligned");
   SASPA_CHECK_ARG((long long)batch * heads <= 65535, "saspa_attention_bf16: batch*heads must be <= 65535");
+  if (g_attention_impl != 1) {
+    const int rc = saspa_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
+    if (rc != SASPA_ERR_UNSUPPORTED) return rc;
+    SASPA_CHECK_ARG(g_attention_impl != 2, "saspa_attention_bf16: no tcgen05 instantiation for head_dim %d", d);
+  }
   if (d <= 48) return launch_flash<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
   if (d <= 64) return launch_flash<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
   if (d <= 80) return launch_flash<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);

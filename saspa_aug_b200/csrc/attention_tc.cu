@@ -1,0 +1,412 @@
+// tcgen05 / TMEM flash attention for sm_100a: O = softmax(Q K^T * scale) V per (batch, head).
+//
+// Serves the UNet / ControlNet transformer blocks of the denoising loop (self-attention over 4096 / 1024 /
+// 256 / 64 image tokens with head_dim 40 / 80 / 160, cross-attention over 77 text tokens) and the CLIP
+// towers (head_dim 64, causal).  Replaces F.scaled_dot_product_attention under diffusers'
+// AttnProcessor2_0 (reference call site: pipe(**pipe_args), run_aug/run_aug.py:278).
+//
+// One CTA owns 256 queries of one (batch, head) as two 128-row tiles and sweeps the keys in tiles of
+// BKV (128 for head_dim <= 64, else 64).  Ten warps:
+//   warp 0     TMA producer: Q once, then K_j / V_j into a STAGES-deep ring of 128B-swizzled smem tiles
+//              (64-column panels straight out of the fused [b, t, 3c] QKV buffer -- nothing is repacked in HBM).
+//   warp 1     owns the 512 TMEM columns; one lane issues every tcgen05.mma:
+//                S_i  = Q_i K_j^T          (SS: both operands K-major in smem)           -> TMEM
+//                O_i += P_i V_j            (TS: P_i read from TMEM, V_j MN-major in smem) -> TMEM
+//              issue order per key tile j:  QK(0,j+1) QK(1,j+1) PV(0,j) PV(1,j), so the next S is ready
+//              before the softmax warps finish the current one.
+//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1: one thread per query row (no shuffles):
+//              tcgen05.ld the S row, release S, running max with lazy rescale (O is only rescaled in TMEM
+//              when the max grows by more than 2^8), p = ex2(s*c - m), bf16 P packed two per column back
+//              into TMEM with tcgen05.st; finally O / l -> global.
+// Padding is free: head_dim 40 runs as K = 48 (the Q pad chunk is zeroed in smem; K's pad columns then
+// multiply zeros) and PV as N = 48 (the extra accumulator columns are never stored).
+#include "tc_ptx.cuh"
+#include "../../include/saspa_b200.h"
+
+namespace {
+using namespace tcx;
+
+constexpr int ATC_THREADS = 320;
+constexpr int QROWS = 128;
+
+template <int D>
+struct ACfg {
+  static constexpr int KS = (D + 15) / 16;    // k-steps of Q K^T
+  static constexpr int NPAN = (D + 63) / 64;  // 64-column (128 B) panels of the head dim
+  static constexpr int ON = KS * 16;          // N of the P V MMA = O columns in TMEM
+  static constexpr int BKV = D <= 64 ? 128 : 64;
+  static constexpr int STAGES = D <= 128 ? 3 : 2;
+  static constexpr int QPAN_BYTES = QROWS * 128;
+  static constexpr int KPAN_BYTES = BKV * 128;
+  static constexpr int Q_BYTES = 2 * NPAN * QPAN_BYTES;
+  static constexpr int KV_STAGE_BYTES = NPAN * KPAN_BYTES;
+  static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int P_OFF = 2 * BKV;  // TMEM columns: S_i at i*BKV, P_i at P_OFF + i*BKV/2, O_i at O_OFF + i*ON
+  static constexpr int O_OFF = 3 * BKV;
+  static_assert(O_OFF + 2 * ON <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "smem budget");
+};
+
+struct AttnParams {
+  __nv_bfloat16* o;
+  int ldo;
+  int heads, tq, tkv;
+  float scale_log2;
+  int causal;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+    attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const AttnParams p) {
+  using C = ACfg<D>;
+  constexpr int BKV = C::BKV, STAGES = C::STAGES, ON = C::ON, KS = C::KS, NPAN = C::NPAN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + C::Q_BYTES;
+  uint8_t* sV = sK + STAGES * C::KV_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * C::KV_STAGE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* q_ready = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = k_full + STAGES;
+  uint64_t* v_full = k_empty + STAGES;
+  uint64_t* v_empty = v_full + STAGES;
+  uint64_t* s_full = v_empty + STAGES;  // [2]
+  uint64_t* s_free = s_full + 2;
+  uint64_t* p_full = s_free + 2;
+  uint64_t* o_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.x * (2 * QROWS);
+  int n_tiles = (p.tkv + BKV - 1) / BKV;
+  if (p.causal) n_tiles = min(n_tiles, (min(q0 + 2 * QROWS, p.tq) + BKV - 1) / BKV);
+  constexpr bool PAD_Q = (D % 16) != 0;  // head_dim % 16 == 8: zero the pad chunk of Q in smem
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 256);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_done[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int col0 = h * D;
+      mbar_expect_tx(q_full, C::Q_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int pn = 0; pn < NPAN; ++pn) tma_load_3d(&tmQ, sQ + (i * NPAN + pn) * C::QPAN_BYTES, q_full, col0 + 64 * pn, q0 + i * QROWS, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t par = ((j / STAGES) & 1) ^ 1;
+        mbar_wait(&k_empty[s], par);
+        mbar_expect_tx(&k_full[s], C::KV_STAGE_BYTES);
+        for (int pn = 0; pn < NPAN; ++pn)
+          tma_load_3d(&tmK, sK + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES, &k_full[s], col0 + 64 * pn, j * BKV, b);
+        mbar_wait(&v_empty[s], par);
+        mbar_expect_tx(&v_full[s], C::KV_STAGE_BYTES);
+        for (int pn = 0; pn < NPAN; ++pn)
+          tma_load_3d(&tmV, sV + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES, &v_full[s], col0 + 64 * pn, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(QROWS, BKV, 0);
+      constexpr uint32_t idesc_pv = make_idesc(QROWS, ON, 1);
+      auto issue_qk = [&](int i, int s) {
+        const uint32_t d_tmem = tmem_base + i * BKV;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int pn = ks >> 2, kk = ks & 3;
+          const uint64_t a = make_smem_desc(smem_u32(sQ + (i * NPAN + pn) * C::QPAN_BYTES) + kk * 32);
+          const uint64_t bd = make_smem_desc(smem_u32(sK + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES) + kk * 32);
+          tc_mma_bf16(d_tmem, a, bd, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[i]);
+      };
+      auto issue_pv = [&](int i, int s, bool acc) {
+        const uint32_t d_tmem = tmem_base + C::O_OFF + i * ON;
+        const uint32_t a_tmem = tmem_base + C::P_OFF + i * (BKV / 2);
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint64_t bd = make_smem_desc_mn(smem_u32(sV + s * C::KV_STAGE_BYTES) + ks * 2048, C::KPAN_BYTES);
+          tc_mma_bf16_ts(d_tmem, a_tmem + ks * 8, bd, idesc_pv, (acc || ks != 0) ? 1u : 0u);
+        }
+        tc_commit(&o_done[i]);
+      };
+      mbar_wait(PAD_Q ? q_ready : q_full, 0);
+      tc_fence_after();
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % STAGES;
+        if (j + 1 < n_tiles) {
+          const int s1 = (j + 1) % STAGES;
+          mbar_wait(&k_full[s1], ((j + 1) / STAGES) & 1);
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(&s_free[i], j & 1);  // softmax(i, j) holds its S row in registers
+            tc_fence_after();
+            issue_qk(i, s1);
+          }
+          tc_commit(&k_empty[s1]);
+        }
+        mbar_wait(&v_full[s], (j / STAGES) & 1);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], j & 1);
+          tc_fence_after();
+          issue_pv(i, s, j > 0);
+        }
+        tc_commit(&v_empty[s]);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..9) =====================
+    const int i = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int qi = q0 + i * QROWS + row;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_s = lane_base + i * BKV;
+    const uint32_t t_p = lane_base + C::P_OFF + i * (BKV / 2);
+    const uint32_t t_o = lane_base + C::O_OFF + i * ON;
+
+    if (PAD_Q) {
+      mbar_wait(q_full, 0);
+      constexpr int ch = D / 8, pn = ch / 8, lc = ch % 8;
+      uint8_t* dst = sQ + (i * NPAN + pn) * C::QPAN_BYTES + row * 128 + ((lc ^ (row & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+      mbar_arrive(q_ready);
+    }
+
+    float m_used = -INFINITY;  // exponent reference (log2 domain); lags the true running max by at most 8
+    float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      uint32_t su[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) tc_ld32p(t_s + c, &su[c]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[i]);
+
+      const int kv0 = j * BKV;
+      if (kv0 + BKV > p.tkv) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (kv0 + c >= p.tkv) su[c] = 0xff800000u;
+      }
+      if (p.causal && kv0 + BKV - 1 > qi) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (kv0 + c > qi) su[c] = 0xff800000u;
+      }
+      float mx[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx[c] = __uint_as_float(su[c]);
+#pragma unroll
+      for (int c = 8; c < BKV; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(su[c]));
+      const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * p.scale_log2;
+
+      bool p_free = (j == 0);
+      if (j == 0) {
+        m_used = (m_tile == -INFINITY) ? 0.0f : m_tile;
+      } else {
+        const bool need = m_tile > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: rescale this tile's O accumulator in TMEM (after P V of the previous key tile has landed)
+          mbar_wait(&o_done[i], (j - 1) & 1);
+          tc_fence_after();
+          p_free = true;
+          const float f = need ? ex2_approx(m_used - m_tile) : 1.0f;
+          if (need) {
+            m_used = m_tile;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) lsum[a] *= f;
+          }
+#pragma unroll 1
+          for (int c = 0; c < ON; c += 16) {
+            uint32_t o[16];
+            tc_ld16(t_o + c, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tc_st16(t_o + c, o);
+          }
+          tc_wait_st();
+        }
+      }
+
+      const float neg_m = -m_used;
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m));
+        lsum[(c >> 1) & 3] += p0 + p1;
+        pk[c >> 1] = pack_bf16(p0, p1);
+      }
+      if (!p_free) {  // P V of the previous key tile must have consumed P_i
+        mbar_wait(&o_done[i], (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < BKV / 2; c += 32) tc_st32(t_p + c, &pk[c]);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    }
+
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(&o_done[i], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+    const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+    __nv_bfloat16* og = p.o + ((long long)b * p.tq + qi) * p.ldo + (long long)h * D;
+    const bool valid = qi < p.tq;
+#pragma unroll 1
+    for (int c = 0; c < ON; c += 16) {
+      uint32_t o[16];
+      tc_ld16(t_o + c, o);
+      tc_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < D) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(og + c + g * 8) = u;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [batch, rows, cols] with row stride ld (elements) and dense batch stride rows*ld; box = [1, box_rows, 64], 128B swizzle.
+int encode_rows3d(CUtensorMap* tm, const void* base, int cols, int rows, int batch, long long ld, int box_rows) {
+  PFN_tmapEncodeTiled enc = encode_fn();
+  if (!enc) {
+    saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return SASPA_ERR_DRIVER;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * rows};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    saspa_set_error("cuTensorMapEncodeTiled(attention cols=%d rows=%d batch=%d ld=%lld box_rows=%d) failed: %d", cols, rows, batch, ld, box_rows, (int)r);
+    return SASPA_ERR_DRIVER;
+  }
+  return SASPA_OK;
+}
+
+template <int D>
+int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+              float scale, int causal, cudaStream_t stream) {
+  using C = ACfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    SASPA_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = encode_rows3d(&tmQ, q, heads * D, tq, batch, ldq, QROWS))) return rc;
+  if ((rc = encode_rows3d(&tmK, k, heads * D, tkv, batch, ldk, C::BKV))) return rc;
+  if ((rc = encode_rows3d(&tmV, v, heads * D, tkv, batch, ldv, C::BKV))) return rc;
+  AttnParams p;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.heads = heads;
+  p.tq = tq;
+  p.tkv = tkv;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  dim3 grid(ceil_div(tq, 2 * QROWS), batch * heads);
+  attn_tc_kernel<D><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+
+}  // namespace
+
+// Returns SASPA_ERR_UNSUPPORTED (without setting an error) when the shape has no tcgen05 instantiation; the
+// caller (saspa_attention_bf16) then uses the mma.sync kernel.
+int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq,
+                       int tkv, int d, float scale, int causal, cudaStream_t stream) {
+  if ((ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0 || scale <= 0.0f) return SASPA_ERR_UNSUPPORTED;
+  switch (d) {
+    case 40: return launch_tc<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+    case 64: return launch_tc<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+    case 80: return launch_tc<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+    case 128: return launch_tc<128>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+    case 160: return launch_tc<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+    default: return SASPA_ERR_UNSUPPORTED;
+  }
+}

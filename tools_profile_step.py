@@ -1,0 +1,52 @@
+"""One micro-batch generation bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off`.
+Usage (GPU box):
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file gpurun_out/launches.csv python tools_profile_step.py [--mb 16] [--steps 2] [--decode]
+Not the bench.py contract: numbers printed under ncu are never bench values; this only produces launch lists."""
+import argparse
+
+import numpy as np
+import torch
+
+from saspa_aug_b200 import ops
+from saspa_aug_b200.pipelines import SaspaControlNetPipeline
+from saspa_aug_b200.synthetic import synthetic_source, synthetic_token_ids
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mb", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--decode", action="store_true")
+    ap.add_argument("--graph", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    pipe = SaspaControlNetPipeline.random_init("sd15", seed=1234, sampler="unipc", device=dev, img2img=False)
+    if a.graph:
+        pipe.use_cuda_graph = True
+    src = torch.from_numpy(np.stack([synthetic_source(s) for s in range(max(1, a.mb // 2))])).to(dev)
+    ids = torch.cat([synthetic_token_ids(i) for i in range(a.mb)]).to(dev)
+    neg = pipe.encode_prompt_ids(synthetic_token_ids(999_999).to(dev)).expand(a.mb, -1, -1).contiguous()
+    noise = torch.randn((a.mb, 4, 64, 64), generator=torch.Generator().manual_seed(1)).to(dev)
+    _, ctrl = ops.canny(src, 120, 200, want_ctrl=True)
+    c = ctrl.index_select(0, torch.arange(a.mb, device=dev) // 2)
+    text = pipe.encode_prompt_ids(ids)
+
+    def run(steps, decode):
+        return pipe.generate_batch(text, neg, None, None, noise=noise, num_inference_steps=steps, guidance_scale=7.5,
+                                   controlnet_conditioning_scale=0.75, control_bf16=c, decode=decode)
+
+    run(1, a.decode)  # warm-up (module load, smem attribute calls)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()
+    s.record()
+    run(a.steps, a.decode)
+    e.record()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print(f"profiled region: {a.steps} steps mb={a.mb} decode={a.decode}: {s.elapsed_time(e):.2f} ms")
+
+
+if __name__ == "__main__":
+    main()
