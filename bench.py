@@ -265,7 +265,7 @@ def roofline_leg(pipe, dev_in, args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
-    for kind, flops, a, b in prof:
+    for kind, flops, a, b, _shape in prof:
         d = agg.setdefault(kind, [0.0, 0.0, 0])
         d[0] += flops
         d[1] += a.elapsed_time(b)

@@ -129,10 +129,13 @@ int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, int c, int kh
 /* ------------------------------------------------------------------------------------------
  * Normalisation / elementwise (HBM-bound, vectorised, warp-shuffle reductions).
  * ------------------------------------------------------------------------------------------ */
-/* GroupNorm over NHWC: x [n, hw, c] (pixel stride ldx), groups | c; y = act((x-mean)*rstd*gamma+beta).
- * act: SASPA_ACT_NONE or SASPA_ACT_SILU.  stats_ws: 16*n*groups bytes (double sum / sum-of-squares), 8-byte aligned. */
+/* GroupNorm over NHWC: x [n, hw, c] (pixel stride ldx), groups | c, groups <= 64; y = act((x-mean)*rstd*gamma+beta).
+ * act: SASPA_ACT_NONE or SASPA_ACT_SILU.  One launch; results are deterministic and independent of which other
+ * images share the batch (fixed-order reductions, no float atomics).  stats_ws: saspa_groupnorm_workspace_bytes(n, hw,
+ * groups) bytes, 256-byte aligned, contents irrelevant on entry. */
+size_t saspa_groupnorm_workspace_bytes(int n, int hw, int groups);
 int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma,
-                              const float* beta, int act, void* y, int ldy, void* stats_ws, cudaStream_t stream);
+                              const float* beta, int act, void* y, int ldy, void* stats_ws, size_t ws_bytes, cudaStream_t stream);
 /* LayerNorm over the last dim: x [rows, c] (row stride ldx) -> y bf16 [rows, c] (row stride ldy). */
 int saspa_layernorm_bf16(const void* x, int ldx, int rows, int c, float eps, const float* gamma, const float* beta, void* y,
                          int ldy, cudaStream_t stream);

@@ -72,7 +72,8 @@ SIGNATURES = {
         c_int,
         [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     ),
-    "saspa_groupnorm_nhwc_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P, c_int, _P, _P]),
+    "saspa_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "saspa_groupnorm_nhwc_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P, c_int, _P, c_size_t, _P]),
     "saspa_layernorm_bf16": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int, _P]),
     "saspa_act_bf16": (c_int, [_P, _P, c_size_t, c_int, _P]),
     "saspa_add_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P]),

@@ -80,102 +80,165 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm (NHWC).  Pass 1: per-(image, channel) partial sums -> per-(image, group) double atomics.
-// Pass 2: per-channel scale/shift staged in smem, applied with 16-byte vectors, optional SiLU.
+// GroupNorm (NHWC), one launch, x read from HBM once, deterministic (batch-composition invariant).
+// Each image is split over `ctas_per_img` (<= 32, a function of hw only) CTAs.  Phase 1: per-CTA (sum, sum of squares) per
+// group over its pixel range -> workspace (fixed-order reductions only, no float atomics).  A per-image
+// arrive/spin counter orders phase 1 before phase 2 across the image's CTAs.  Phase 2: every CTA folds the
+// partials in the same order (double), stages per-channel scale/shift in smem and normalises its own pixel
+// range again (the re-read is served by L2), optional SiLU, 16-byte vectors.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int c, int groups,
-                                                       int pix_per_block, double* __restrict__ stats) {
-  extern __shared__ float s_acc[];  // [2][c]
-  const int img = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(p0 + pix_per_block, hw);
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) s_acc[i] = 0.0f;
-  __syncthreads();
+constexpr int GN_THREADS = 512;
+
+__global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int c, int groups, float eps,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                              __nv_bfloat16* __restrict__ y, int ldy, int ctas_per_img, int pix_per_cta,
+                                                              float2* __restrict__ partials, unsigned int* __restrict__ counters) {
+  extern __shared__ float gn_smem[];  // phase 1: [pix_par][c] sums + [pix_par][c] squares; phase 2: scale[c], shift[c]
+  __shared__ float s_stat[2 * 64];    // per-group mean, rstd (groups <= 64)
+  const int img = blockIdx.x / ctas_per_img, part = blockIdx.x % ctas_per_img;
+  const int p0 = part * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, hw);
   const int cv = c / 8;  // 16-byte vectors per pixel
-  // thread -> fixed channel vector(s), strided over pixels: vpt vectors per thread, tpp threads per pixel
-  const int vpt = (cv + blockDim.x - 1) / blockDim.x;  // 1 or 2 (c <= 4096)
-  const int tpp = (cv + vpt - 1) / vpt;
-  const int pix_par = blockDim.x / tpp;  // >= 1
-  const int my_l = threadIdx.x % tpp;
-  const int my_p = threadIdx.x / tpp;
+  const int tpp = cv;    // threads per pixel (cv <= GN_THREADS)
+  const int pix_par = GN_THREADS / tpp;
+  const int my_v = threadIdx.x % tpp, my_p = threadIdx.x / tpp;
+  const __nv_bfloat16* xi = x + (size_t)img * hw * ldx;
+  float* s_sum = gn_smem;
+  float* s_sq = gn_smem + (size_t)pix_par * c;
+
+  // ---- phase 1: partial statistics of my pixel range ----
   if (my_p < pix_par) {
+    float s[8], ss[8];
 #pragma unroll
-    for (int jv = 0; jv < 2; ++jv) {
-      const int v = my_l + jv * tpp;
-      if (jv < vpt && v < cv) {
-        float s[8], ss[8];
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0f;
+    const __nv_bfloat16* base = xi + my_v * 8;
+    int p = p0 + my_p;
+    for (; p + pix_par < p1; p += 2 * pix_par) {  // two loads in flight
+      uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
+      uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + pix_par) * ldx));
+      float f[8], g[8];
+      unpack8(u0, f);
+      unpack8(u1, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0f;
-        const __nv_bfloat16* base = x + ((size_t)img * hw) * ldx + v * 8;
-        for (int p = p0 + my_p; p < p1; p += pix_par) {
-          uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
-          float f[8];
-          unpack8(u, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s[j] += f[j];
-            ss[j] += f[j] * f[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&s_acc[v * 8 + j], s[j]);
-          atomicAdd(&s_acc[c + v * 8 + j], ss[j]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j] + g[j];
+        ss[j] += f[j] * f[j] + g[j] * g[j];
       }
+    }
+    for (; p < p1; p += pix_par) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_sum[my_p * c + my_v * 8 + j] = s[j];
+      s_sq[my_p * c + my_v * 8 + j] = ss[j];
     }
   }
   __syncthreads();
-  const int cg = c / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int j = 0; j < cg; ++j) {
-      a += (double)s_acc[g * cg + j];
-      b += (double)s_acc[c + g * cg + j];
+  {
+    // one warp per group, lanes stride over the (pixel lane, channel) partials, shuffle tree: fixed order
+    const int cg = c / groups;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < groups; g += GN_THREADS / 32) {
+      float a = 0.0f, b = 0.0f;
+      for (int i = lane; i < pix_par * cg; i += 32) {
+        const int pp = i / cg, ch = g * cg + (i - pp * cg);
+        a += s_sum[pp * c + ch];
+        b += s_sq[pp * c + ch];
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) partials[((size_t)img * ctas_per_img + part) * groups + g] = make_float2(a, b);
     }
-    atomicAdd(&stats[((size_t)img * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[((size_t)img * groups + g) * 2 + 1], b);
+  }
+  // ---- all CTAs of this image have published their partials ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&counters[img], 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + img) : "memory");
+      if (seen < (unsigned int)ctas_per_img) __nanosleep(32);
+    } while (seen < (unsigned int)ctas_per_img);
+  }
+  __syncthreads();
+
+  // ---- phase 2: fold partials (same order in every CTA), per-channel scale / shift, apply ----
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < ctas_per_img; ++q) {
+      float2 v = __ldcg(&partials[((size_t)img * ctas_per_img + q) * groups + g]);
+      a += (double)v.x;
+      b += (double)v.y;
+    }
+    const double cnt = (double)hw * (c / groups);
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_stat[g] = (float)mean;
+    s_stat[64 + g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  float* s_scale = gn_smem;
+  float* s_shift = gn_smem + c;
+  for (int ch = threadIdx.x; ch < c; ch += GN_THREADS) {
+    const int g = ch / (c / groups);
+    const float ga = gamma ? gamma[ch] : 1.0f, be = beta ? beta[ch] : 0.0f;
+    const float sc = s_stat[64 + g] * ga;
+    s_scale[ch] = sc;
+    s_shift[ch] = be - s_stat[g] * sc;
+  }
+  __syncthreads();
+  if (my_p < pix_par) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = s_scale[my_v * 8 + j];
+      sh[j] = s_shift[my_v * 8 + j];
+    }
+    const __nv_bfloat16* base = xi + my_v * 8;
+    __nv_bfloat16* yb = y + (size_t)img * hw * ldy + my_v * 8;
+    for (int p = p0 + my_p; p < p1; p += pix_par) {
+      uint4 u = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(f[j], sc[j], sh[j]);
+        f[j] = (act == SASPA_ACT_SILU) ? silu_f(t) : t;
+      }
+      *reinterpret_cast<uint4*>(yb + (size_t)p * ldy) = pack8(f);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int c, int groups, float eps,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                                       __nv_bfloat16* __restrict__ y, int ldy, int pix_per_block,
-                                                       const double* __restrict__ stats) {
-  extern __shared__ float s_ab[];  // scale[c], shift[c]
-  const int img = blockIdx.y;
-  const int cg = c / groups;
-  const double cnt = (double)hw * cg;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    int g = ch / cg;
-    double sum = stats[((size_t)img * groups + g) * 2 + 0], sq = stats[((size_t)img * groups + g) * 2 + 1];
-    double mean = sum / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float ga = gamma ? gamma[ch] : 1.0f, be = beta ? beta[ch] : 0.0f;
-    s_ab[ch] = rstd * ga;
-    s_ab[c + ch] = be - (float)mean * rstd * ga;
-  }
-  __syncthreads();
-  const int cv = c / 8;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(p0 + pix_per_block, hw);
-  const long long total = (long long)(p1 - p0) * cv;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    int v = (int)(i % cv);
-    int p = p0 + (int)(i / cv);
-    size_t pix = (size_t)img * hw + p;
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + v * 8));
-    float f[8];
-    unpack8(u, f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = f[j] * s_ab[v * 8 + j] + s_ab[c + v * 8 + j];
-      f[j] = (act == SASPA_ACT_SILU) ? silu_f(t) : t;
-    }
-    *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = pack8(f);
-  }
+// workspace layout: [n] u32 arrive counters (padded to 256 B) | [n][ctas_per_img][groups] float2 partials
+struct GnPlan {
+  int ctas_per_img, pix_per_cta;
+  size_t counters_bytes, total_bytes;
+};
+GnPlan gn_plan(int n, int hw, int groups) {
+  GnPlan p;
+  // The split of an image over CTAs depends on hw only -- never on n -- so an image's statistics are reduced in the
+  // same order whatever else shares the batch (bit-exact batch invariance).  Only the CTAs of ONE image wait for each
+  // other (<= 32 of them), so in-order block dispatch always makes progress.
+  int per = hw / 256;
+  if (per < 1) per = 1;
+  if (per > 32) per = 32;
+  p.pix_per_cta = ceil_div(hw, per);
+  p.ctas_per_img = ceil_div(hw, p.pix_per_cta);
+  p.counters_bytes = ((size_t)n * 4 + 255) / 256 * 256;
+  p.total_bytes = p.counters_bytes + (size_t)n * p.ctas_per_img * groups * sizeof(float2);
+  return p;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -231,6 +294,76 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
       }
     }
   }
+}
+
+// LayerNorm for the transformer widths of the denoising path (c = 8 * LPR * VPL): LPR lanes per row, 32 / LPR rows
+// per warp, VPL 16-byte vectors per lane (row stays in registers), shuffle reductions over LPR lanes, two-pass variance.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_sub_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, float eps,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, int ldy) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  constexpr int C = 8 * LPR * VPL;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  float ga[VPL][8], be[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = (l + i * LPR) * 8 + j;
+      ga[i][j] = gamma ? __ldg(gamma + ch) : 1.0f;
+      be[i][j] = beta ? __ldg(beta + ch) : 0.0f;
+    }
+  }
+  for (long long r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
+    const long long row = r0 + sub;
+    const bool ok = row < rows;
+    const __nv_bfloat16* xr = x + (size_t)(ok ? row : 0) * ldx;
+    float f[VPL][8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + (l + i * LPR) * 8));
+      unpack8(u, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / (float)C);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        sq += d * d;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / (float)C) + eps);
+    if (ok) {
+      __nv_bfloat16* yr = y + (size_t)row * ldy;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * ga[i][j] + be[i][j];
+        *reinterpret_cast<uint4*>(yr + (l + i * LPR) * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+template <int LPR, int VPL>
+void launch_ln_sub(const void* x, int ldx, int rows, float eps, const float* gamma, const float* beta, void* y, int ldy, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  const int grid = grid_for(ceil_div_ll(rows, RPW), 8, 8);
+  layernorm_sub_kernel<LPR, VPL><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, eps, gamma, beta,
+                                                           static_cast<__nv_bfloat16*>(y), ldy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,27 +578,36 @@ extern "C" int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, in
   return SASPA_OK;
 }
 
+extern "C" size_t saspa_groupnorm_workspace_bytes(int n, int hw, int groups) {
+  if (n <= 0 || hw <= 0 || groups <= 0) return 256;
+  return gn_plan(n, hw, groups).total_bytes;
+}
+
 extern "C" int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma,
-                                         const float* beta, int act, void* y, int ldy, void* stats_ws, cudaStream_t stream) {
-  SASPA_CHECK_ARG(n >= 0 && hw >= 0 && c > 0 && groups > 0 && c % groups == 0, "saspa_groupnorm_nhwc_bf16: bad shape (c=%d groups=%d)", c, groups);
-  SASPA_CHECK_ARG(c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && c <= 4096, "saspa_groupnorm_nhwc_bf16: c, ldx, ldy must be multiples of 8 and c <= 4096, got c=%d", c);
+                                         const float* beta, int act, void* y, int ldy, void* stats_ws, size_t ws_bytes, cudaStream_t stream) {
+  SASPA_CHECK_ARG(n >= 0 && hw >= 0 && c > 0 && groups > 0 && groups <= 64 && c % groups == 0, "saspa_groupnorm_nhwc_bf16: bad shape (c=%d groups=%d)", c, groups);
+  SASPA_CHECK_ARG(c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && c <= 8 * GN_THREADS, "saspa_groupnorm_nhwc_bf16: c, ldx, ldy must be multiples of 8 and c <= %d, got c=%d", 8 * GN_THREADS, c);
   SASPA_CHECK_ARG(act == SASPA_ACT_NONE || act == SASPA_ACT_SILU, "saspa_groupnorm_nhwc_bf16: act must be NONE or SILU");
   if (n == 0 || hw == 0) return SASPA_OK;
   SASPA_CHECK_ARG(x && y && stats_ws, "saspa_groupnorm_nhwc_bf16: null pointer");
-  SASPA_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_ws) & 7) == 0, "saspa_groupnorm_nhwc_bf16: stats_ws must be 8-byte aligned");
-  double* stats = reinterpret_cast<double*>(stats_ws);
-  SASPA_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)n * groups, stream));
-  // ~4 CTAs per SM over the whole batch
-  int blocks_x = ceil_div(saspa_num_sms() * 4, n);
-  int pix_per_block = ceil_div(hw, blocks_x);
-  if (pix_per_block < 32) pix_per_block = 32;
-  blocks_x = ceil_div(hw, pix_per_block);
-  dim3 grid(blocks_x, n);
-  size_t smem = sizeof(float) * 2 * c;
-  gn_stats_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, pix_per_block, stats);
-  SASPA_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, eps, gamma, beta, act,
-                                               static_cast<__nv_bfloat16*>(y), ldy, pix_per_block, stats);
+  SASPA_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_ws) & 255) == 0, "saspa_groupnorm_nhwc_bf16: stats_ws must be 256-byte aligned");
+  const GnPlan p = gn_plan(n, hw, groups);
+  if (ws_bytes < p.total_bytes) {
+    saspa_set_error("saspa_groupnorm_nhwc_bf16: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
+    return SASPA_ERR_WORKSPACE;
+  }
+  unsigned int* counters = reinterpret_cast<unsigned int*>(stats_ws);
+  float2* partials = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats_ws) + p.counters_bytes);
+  SASPA_CUDA(cudaMemsetAsync(counters, 0, (size_t)n * 4, stream));
+  const int pix_par = GN_THREADS / (c / 8);
+  const size_t smem = sizeof(float) * 2 * (size_t)(pix_par > 1 ? pix_par : 1) * c;
+  static size_t smem_configured = 0;
+  if (smem > 48 * 1024 && smem > smem_configured) {
+    SASPA_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_configured = smem;
+  }
+  gn_fused_kernel<<<n * p.ctas_per_img, GN_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, eps, gamma, beta, act,
+                                                                    static_cast<__nv_bfloat16*>(y), ldy, p.ctas_per_img, p.pix_per_cta, partials, counters);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }
@@ -476,6 +618,15 @@ extern "C" int saspa_layernorm_bf16(const void* x, int ldx, int rows, int c, flo
   SASPA_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "saspa_layernorm_bf16: row strides must be multiples of 8");
   if (rows == 0) return SASPA_OK;
   SASPA_CHECK_ARG(x && y, "saspa_layernorm_bf16: null pointer");
+  switch (c) {  // widths of the SD v1.5 / SDXL transformer blocks and the CLIP towers
+    case 320: launch_ln_sub<8, 5>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    case 640: launch_ln_sub<16, 5>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    case 1280: launch_ln_sub<32, 5>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    case 512: launch_ln_sub<32, 2>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    case 768: launch_ln_sub<32, 3>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    case 1024: launch_ln_sub<32, 4>(x, ldx, rows, eps, gamma, beta, y, ldy, stream); SASPA_LAUNCH_CHECK(); return SASPA_OK;
+    default: break;
+  }
   const int grid = grid_for(rows, 8, 8);
   layernorm_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, c, eps, gamma, beta, static_cast<__nv_bfloat16*>(y), ldy);
   SASPA_LAUNCH_CHECK();

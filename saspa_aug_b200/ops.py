@@ -48,12 +48,12 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(ev, kind: str, flops: float):
+def _prof_end(ev, kind: str, flops: float, shape=None):
     if ev is None:
         return
     end = torch.cuda.Event(enable_timing=True)
     end.record()
-    PROFILE.append((kind, flops, ev, end))
+    PROFILE.append((kind, flops, ev, end, shape))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -120,7 +120,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         _lib.load().saspa_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, ctypes.byref(ep), _stream()),
         "saspa_gemm_bf16",
     )
-    _prof_end(ev, "gemm", 2.0 * M * N * K)
+    _prof_end(ev, "gemm", 2.0 * M * N * K, (M, N, K, int(act), residual is not None))
     _count()
     return out
 
@@ -152,7 +152,7 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
                                             _ptr(weight), ksize, _ptr(out), out.stride(2), cout, ctypes.byref(ep), _stream()),
         "saspa_conv2d_igemm_bf16",
     )
-    _prof_end(ev, "conv", 2.0 * n * h * w * cout * ksize * ksize * (c0 + c1))
+    _prof_end(ev, "conv", 2.0 * n * h * w * cout * ksize * ksize * (c0 + c1), (n, h, w, c0 + c1, cout, ksize))
     _count()
     return out
 
@@ -181,13 +181,15 @@ def groupnorm(x: torch.Tensor, groups: int, eps: float, gamma, beta, act=ACT_NON
     if out is None:
         out = torch.empty((n, hw, c), dtype=BF16, device=x.device)
     assert out.stride(2) == 1 and out.stride(0) == hw * out.stride(1)
-    ws = torch.empty(2 * n * groups, dtype=torch.float64, device=x.device)
+    lib = _lib.load()
+    ws_bytes = lib.saspa_groupnorm_workspace_bytes(n, hw, groups)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     check(
-        _lib.load().saspa_groupnorm_nhwc_bf16(_ptr(x), x.stride(1), n, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta), int(act), _ptr(out),
-                                              out.stride(1), _ptr(ws), _stream()),
+        lib.saspa_groupnorm_nhwc_bf16(_ptr(x), x.stride(1), n, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta), int(act), _ptr(out),
+                                      out.stride(1), _ptr(ws), ws_bytes, _stream()),
         "saspa_groupnorm_nhwc_bf16",
     )
-    _count(3)
+    _count(1)
     return out
 
 
@@ -293,7 +295,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
                                          tkv, d, float(scale), 1 if causal else 0, _stream()),
         "saspa_attention_bf16",
     )
-    _prof_end(ev, "attention", 4.0 * b * heads * tq * tkv * d)
+    _prof_end(ev, "attention", 4.0 * b * heads * tq * tkv * d, (b, heads, tq, tkv, d))
     _count()
     return out
 

@@ -38,6 +38,21 @@ def test_groupnorm(cuda_device, cfg, act):
     _close(got, ref.permute(0, 2, 1), 2e-2)
 
 
+def test_groupnorm_is_batch_invariant_and_repeatable(cuda_device):
+    """Fixed-order reductions: an image's result must not depend on which images share the launch (the sharded driver
+    regroups micro-batches) nor change between runs."""
+    x = _rand((7, 1024, 640), 9, 2.0, 0.3)
+    gamma, beta = torch.randn(640, device="cuda"), torch.randn(640, device="cuda")
+    full = ops.groupnorm(x, 32, 1e-5, gamma, beta, ops.ACT_SILU)
+    again = ops.groupnorm(x, 32, 1e-5, gamma, beta, ops.ACT_SILU)
+    assert torch.equal(full, again)
+    for i in (0, 3, 6):
+        one = ops.groupnorm(x[i : i + 1], 32, 1e-5, gamma, beta, ops.ACT_SILU)
+        assert torch.equal(one, full[i : i + 1])
+    pair = ops.groupnorm(x[2:4], 32, 1e-5, gamma, beta, ops.ACT_SILU)
+    assert torch.equal(pair, full[2:4])
+
+
 def test_groupnorm_strided_into_concat_buffer(cuda_device):
     n, hw, c = 2, 256, 640
     buf = _rand((n, hw, 1920), 2)

@@ -39,6 +39,9 @@ def rnd(*shape):
 def main():
     rows = []
     B = 32  # CFG rows (16 images)
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if only == "hbm":
+        return hbm(B)
     print("== GEMM (tcgen05) ==")
     for M, N, K in [(8192, 8192, 8192), (B * 4096, 320, 320), (B * 4096, 2560, 320), (B * 4096, 320, 1280), (B * 1024, 640, 640), (B * 1024, 5120, 640),
                     (B * 256, 1280, 1280), (B * 256, 10240, 1280), (B * 256, 1280, 5120), (B * 64, 1280, 1280), (B * 4096, 320, 2880)]:
@@ -63,19 +66,25 @@ def main():
         ms = timeit(lambda: ops.attention(q, k, v, heads, out=out))
         tf = 4.0 * b * heads * tq * tkv * d / ms / 1e9
         print(f"attn b{b} h{heads} {tq}x{tkv} d{d}: {ms:.3f} ms {tf:.0f} TF/s")
+    hbm(B)
+
+
+def hbm(B):
     print("== HBM-bound ==")
-    for n, hw, c in [(B, 4096, 320), (B, 1024, 640), (B, 256, 1280), (B, 4096, 640)]:
+    for n, hw, c in [(B, 4096, 320), (B, 1024, 640), (B, 256, 1280), (B, 4096, 640), (B, 4096, 960), (B, 1024, 1920), (B, 64, 2560), (8, 262144, 128), (8, 65536, 256)]:
         x = rnd(n, hw, c)
         out = torch.empty_like(x)
         g, bt = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
         ms = timeit(lambda: ops.groupnorm(x, 32, 1e-5, g, bt, ops.ACT_SILU, out=out))
-        gb = 3.0 * x.numel() * 2 / ms / 1e6  # read twice + write once
-        print(f"groupnorm+silu {n}x{hw}x{c}: {ms:.3f} ms {gb:.0f} GB/s ({gb / PEAKS['hbm_gbs']:.2f})")
-    x = rnd(B * 4096, 320)
-    out = torch.empty_like(x)
-    g, bt = torch.ones(320, device="cuda"), torch.zeros(320, device="cuda")
-    ms = timeit(lambda: ops.layernorm(x, 1e-5, g, bt, out=out))
-    print(f"layernorm {B*4096}x320: {ms:.3f} ms {2.0 * x.numel() * 2 / ms / 1e6:.0f} GB/s")
+        gb = 2.0 * x.numel() * 2 / ms / 1e6  # algorithmic: read once + write once
+        print(f"groupnorm+silu {n}x{hw}x{c}: {ms:.3f} ms {gb:.0f} GB/s algorithmic ({gb / PEAKS['hbm_gbs']:.2f})")
+    for rows_, c in [(B * 4096, 320), (B * 1024, 640), (B * 256, 1280), (B * 77, 768)]:
+        x = rnd(rows_, c)
+        out = torch.empty_like(x)
+        g, bt = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        ms = timeit(lambda: ops.layernorm(x, 1e-5, g, bt, out=out))
+        gb = 2.0 * x.numel() * 2 / ms / 1e6
+        print(f"layernorm {rows_}x{c}: {ms:.3f} ms {gb:.0f} GB/s ({gb / PEAKS['hbm_gbs']:.2f})")
     imgs = torch.randint(0, 256, (256, 512, 512, 3), dtype=torch.uint8, device="cuda")
     import numpy as np
     from saspa_aug_b200.synthetic import synthetic_source

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--decode", action="store_true")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="CUDA-event time every tcgen05 launch and print a per-shape table (no ncu)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     pipe = SaspaControlNetPipeline.random_init("sd15", seed=1234, sampler="unipc", device=dev, img2img=False)
@@ -38,6 +39,22 @@ def main():
 
     run(1, a.decode)  # warm-up (module load, smem attribute calls)
     torch.cuda.synchronize()
+    if a.shapes:
+        ops.PROFILE = []
+        run(a.steps, a.decode)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, flops, s, e, shape in prof:
+            d = agg.setdefault((kind, shape), [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += s.elapsed_time(e)
+            d[2] += flops
+        tot = sum(v[1] for v in agg.values())
+        print(f"event-timed tcgen05/attention launches: {sum(v[0] for v in agg.values())}, {tot:.2f} ms over {a.steps} steps")
+        for (kind, shape), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{v[1]:8.3f} ms {100 * v[1] / tot:5.1f}% {v[0]:4d}x {1e3 * v[1] / v[0]:8.1f} us {v[2] / v[1] / 1e9:7.0f} TF/s  {kind} {shape}")
+        return
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()
     s.record()
