@@ -7,7 +7,7 @@
 // AutoencoderKL forward (reference: pipe(**pipe_args), run_aug/run_aug.py:278) and the filter nets
 // (all_utils/utils.py:361 WSDAN_CAL, :152-164 CLIP).
 //
-// Structure per CTA (192 threads, 1 CTA / SM, grid = min(tiles, #SM)):
+// Structure per CTA (320 threads, 1 CTA / SM, grid = min(tiles, #SM)):
 //   warp 0   : TMA producer  - cp.async.bulk.tensor (2-D for GEMM, 4-D NHWC boxes for conv: the 3x3 taps are
 //              nine shifted boxes and TMA's out-of-bounds zero fill IS the conv padding) into a
 //              STAGES-deep ring of 128B-swizzled smem tiles, signalled by mbarrier complete_tx.
@@ -15,8 +15,15 @@
 //              (128 x BN x 16 per instruction, fp32 accumulate in TMEM), tcgen05.commit frees smem
 //              stages and publishes the accumulator.  Two accumulator buffers (columns 0 / 256) let the
 //              epilogue of tile i overlap the main loop of tile i+1.
-//   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 (one output row per thread), fused bias / per-image
-//              row bias (time embedding) / activation / GEGLU / alpha / residual, 16-byte stores.
+//   warps 2-9: epilogue, two groups of four warps (one warp per TMEM lane quadrant); group g owns the
+//              32-column output panels k = g, g+2, ...:  tcgen05.ld 32x32b.x32 (one output row per thread),
+//              fused bias / per-image row bias (time embedding) / activation / GEGLU / alpha / residual.
+//              bf16 outputs leave through shared memory: each thread writes its 64-byte row slice into a
+//              64B-swizzled [128 x 32] staging panel and one thread issues a TMA store (coalesced, clipped at
+//              the tensor edge by the hardware); the residual arrives the same way (TMA load into the staging
+//              panel, prefetched two panels ahead, across tile boundaries).  Most of this model's GEMMs
+//              have K <= 1280 and M >= 32768, i.e. they are bound by how fast the epilogue drains TMEM.
+//              fp32 / unaligned outputs take the direct (row-per-thread, 16-byte) global path.
 #include "tc_ptx.cuh"
 #include "../../include/saspa_b200.h"
 
@@ -24,10 +31,14 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // column offset between the two accumulator buffers
+constexpr int PANEL = 32;        // output columns per staging panel (64 B of bf16 per row)
+constexpr int PANEL_BYTES = BM * PANEL * 2;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
   int M, N, K;
@@ -51,8 +62,9 @@ struct GemmParams {
   int out_fp32;
   void* D;
   int ldd;
-  int n_out;   // valid output columns (N, or N/2 for GEGLU)
-  int vec_ok;  // 16-byte vector path allowed for residual loads / stores
+  int n_out;      // valid output columns (N, or N/2 for GEGLU)
+  int vec_ok;     // 16-byte vector path allowed for residual loads / stores (direct path)
+  int tma_store;  // bf16 output (and residual) move through smem staging panels + TMA
 };
 
 using namespace tcx;
@@ -61,8 +73,15 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // staging panels per epilogue group: 4 (residual prefetch distance 2) unless the operand ring needs the room
+  static constexpr int NBUF = BN > 160 ? 2 : 4;
+  static constexpr int PD = NBUF / 2;
+  static constexpr int STAGING_BYTES = 2 * NBUF * PANEL_BYTES;
+  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static_assert(STAGES >= 3, "operand ring too shallow");
+  static_assert(BN % PANEL == 0, "BN must be a multiple of the staging panel width");
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -75,23 +94,45 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                   const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
+  constexpr int NBUF = C::NBUF;
+  constexpr int PD = C::PD;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_BYTES);
+  uint8_t* sStage = sB + STAGES * C::B_BYTES;  // 1024-aligned: every size above is a multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + C::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rfull = bars + 2 * STAGES + 4;  // [2 groups][NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -102,14 +143,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
     if (p.mode == 1 && p.c1 > 0) tma_prefetch_desc(&tmA1);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmD);
+      if (p.residual) tma_prefetch_desc(&tmR);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_WARPS);
     }
+    for (int i = 0; i < 2 * NBUF; ++i) mbar_init(&rfull[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -197,16 +243,75 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int grp = (warp - 2) >> 2;  // epilogue group: owns panels k = grp, grp + 2, ...
+    const int q = warp & 3;           // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;      // accumulator row of this thread
+    const bool leader = (warp == 2 + 4 * grp) && lane == 0;
     const bool geglu = (p.act == SASPA_ACT_GEGLU);
-    constexpr int OUT_BN = BN;  // columns of output per tile (BN/2 when GEGLU)
+    const int out_bn = geglu ? BN / 2 : BN;
+    const int NP = out_bn / PANEL;
+    uint8_t* stg = sStage + grp * NBUF * PANEL_BYTES;
+    uint64_t* rf = rfull + grp * NBUF;
+    const uint32_t row_off = (uint32_t)r * 64u;
+    const uint32_t row_swz = (uint32_t)(r >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
+    const bool use_tma = p.tma_store != 0;
+    const bool tma_res = use_tma && p.residual != nullptr;
+
+    // (tile, k) sequence of this group's valid panels
+    auto panel_valid = [&](int tile, int k) { return (tile % p.num_n_tiles) * out_bn + k * PANEL < p.n_out; };
+    auto panel_next = [&](int& tile, int& k) {
+      for (;;) {
+        k += 2;
+        if (k >= NP) {
+          tile += gridDim.x;
+          k = grp;
+          if (tile >= total_tiles) return;
+        }
+        if (k < NP && panel_valid(tile, k)) return;
+      }
+    };
+    auto panel_coords = [&](int tile, int k, int& col, int& c1, int& c2, int& c3) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      col = n_blk * out_bn + k * PANEL;
+      if (p.mode == 0) {
+        c1 = m_blk * BM;
+        c2 = c3 = 0;
+      } else {
+        int tx = m_blk % p.tiles_x, rr = m_blk / p.tiles_x;
+        int ty = rr % p.tiles_y, tn = rr / p.tiles_y;
+        c1 = tx * p.bw;
+        c2 = ty * p.bh;
+        c3 = tn * p.bn;
+      }
+    };
+    auto issue_res_load = [&](int tile, int k, int buf) {
+      int col, c1, c2, c3;
+      panel_coords(tile, k, col, c1, c2, c3);
+      mbar_expect_tx(&rf[buf], PANEL_BYTES);
+      if (p.mode == 0)
+        tma_load_2d(&tmR, stg + buf * PANEL_BYTES, &rf[buf], col, c1);
+      else
+        tma_load_4d(&tmR, stg + buf * PANEL_BYTES, &rf[buf], col, c1, c2, c3);
+    };
+
+    // residual prefetch state (leader only)
+    int pf_tile = blockIdx.x, pf_k = grp - 2, pf_n = 0;
+    if (tma_res && leader) {
+      panel_next(pf_tile, pf_k);
+      for (int i = 0; i < PD && pf_tile < total_tiles; ++i) {
+        issue_res_load(pf_tile, pf_k, pf_n % NBUF);
+        ++pf_n;
+        panel_next(pf_tile, pf_k);
+      }
+    }
+
+    int n_seq = 0;  // panels processed by this group so far
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-      const int r = q * 32 + lane;
       long long pix;
       bool row_ok;
       int group;
@@ -227,18 +332,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
-      const int out_bn = geglu ? OUT_BN / 2 : OUT_BN;
       const int col_base_in = n_blk * BN;       // column in the (interleaved) weight / bias space
       const int col_base_out = n_blk * out_bn;  // column in the output
 #pragma unroll 1
-      for (int c0 = 0; c0 < out_bn; c0 += 32) {
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+      for (int k = grp; k < NP; k += 2) {
+        const int c0 = k * PANEL;
+        if (col_base_out + c0 >= p.n_out) break;  // group-uniform
+        __syncwarp();  // tcgen05.ld is .sync.aligned
         uint32_t v[32];
         tc_ld32(t_row + c0, v);
-        uint32_t g[32];
-        if (geglu) tc_ld32(t_row + c0 + OUT_BN / 2, g);
+        uint32_t gt[32];
+        if (geglu) tc_ld32(t_row + c0 + BN / 2, gt);
         tc_wait_ld();
-        if (col_base_out + c0 >= p.n_out) continue;  // warp-uniform
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -257,11 +362,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         if (geglu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float gate = __uint_as_float(g[j]);
-            int n = col_base_in + OUT_BN / 2 + c0 + j;
-            if (p.bias && n < p.N) gate += __ldg(p.bias + n);
-            f[j] = f[j] * gelu_erf_f(gate);
+          for (int j = 0; j < 32; j += 4) {
+            int n = col_base_in + BN / 2 + c0 + j;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));  // N % 256 == 0 for GEGLU
+            f[j] *= gelu_erf_f(__uint_as_float(gt[j]) + b.x);
+            f[j + 1] *= gelu_erf_f(__uint_as_float(gt[j + 1]) + b.y);
+            f[j + 2] *= gelu_erf_f(__uint_as_float(gt[j + 2]) + b.z);
+            f[j + 3] *= gelu_erf_f(__uint_as_float(gt[j + 3]) + b.w);
           }
         } else {
           if (p.row_bias && row_ok) {
@@ -288,59 +396,117 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
         }
         const int n0 = col_base_out + c0;
-        if (row_ok) {
-        if (p.residual) {
-          const __nv_bfloat16* rp = p.residual + (size_t)pix * p.ld_res + n0;
-          if (p.vec_ok && n0 + 31 < p.n_out) {
+
+        if (use_tma) {
+          // ---------- staged path: residual in / bf16 out through a swizzled smem panel + TMA ----------
+          const int buf = n_seq % NBUF;
+          uint8_t* pbuf = stg + buf * PANEL_BYTES + row_off;
+          if (tma_res) {
+            if (leader && pf_tile < total_tiles) {
+              // panel n_seq + PD reuses the buffer of store n_seq + PD - NBUF, which must have drained
+              bulk_wait_read<NBUF - PD - 1>();
+              issue_res_load(pf_tile, pf_k, pf_n % NBUF);
+              ++pf_n;
+              panel_next(pf_tile, pf_k);
+            }
+            mbar_wait(&rf[buf], (uint32_t)(n_seq / NBUF) & 1u);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+            for (int c = 0; c < 4; ++c) {
+              const uint4 u = *reinterpret_cast<const uint4*>(pbuf + ((c ^ row_swz) << 4));
+              const int j = c * 8;
               f[j + 0] += p.beta * bf16_lo(u.x); f[j + 1] += p.beta * bf16_hi(u.x);
               f[j + 2] += p.beta * bf16_lo(u.y); f[j + 3] += p.beta * bf16_hi(u.y);
               f[j + 4] += p.beta * bf16_lo(u.z); f[j + 5] += p.beta * bf16_hi(u.z);
               f[j + 6] += p.beta * bf16_lo(u.w); f[j + 7] += p.beta * bf16_hi(u.w);
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.n_out) f[j] += p.beta * __bfloat162float(rp[j]);
           }
-        }
-        if (p.act_post) {
+          if (p.act_post) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        }
-        if (p.out_fp32) {
-          float* op = reinterpret_cast<float*>(p.D) + (size_t)pix * p.ldd + n0;
-          if (p.vec_ok && n0 + 31 < p.n_out) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.n_out) op[j] = f[j];
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
           }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)pix * p.ldd + n0;
-          if (p.vec_ok && n0 + 31 < p.n_out) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]);
-              u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]);
-              u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(op + j) = u;
+          for (int c = 0; c < 4; ++c) {
+            const int j = c * 8;
+            uint4 u;
+            u.x = pack_bf16(f[j], f[j + 1]);
+            u.y = pack_bf16(f[j + 2], f[j + 3]);
+            u.z = pack_bf16(f[j + 4], f[j + 5]);
+            u.w = pack_bf16(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(pbuf + ((c ^ row_swz) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          // after this barrier every thread knows stores <= n_seq - NBUF + 1 have drained their panel
+          if (leader && !tma_res) bulk_wait_read<(NBUF >= 2 ? NBUF - 2 : 0)>();
+          __syncwarp();
+          group_bar(1 + grp);
+          if (leader) {
+            int col, c1, c2, c3;
+            panel_coords(tile, k, col, c1, c2, c3);
+            if (p.mode == 0)
+              tma_store_2d(&tmD, stg + buf * PANEL_BYTES, col, c1);
+            else
+              tma_store_4d(&tmD, stg + buf * PANEL_BYTES, col, c1, c2, c3);
+            bulk_commit();
+          }
+          ++n_seq;
+          continue;
+        }
+
+        // ---------- direct path (fp32 / unaligned outputs) ----------
+        if (row_ok) {
+          if (p.residual) {
+            const __nv_bfloat16* rp = p.residual + (size_t)pix * p.ld_res + n0;
+            if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                f[j + 0] += p.beta * bf16_lo(u.x); f[j + 1] += p.beta * bf16_hi(u.x);
+                f[j + 2] += p.beta * bf16_lo(u.y); f[j + 3] += p.beta * bf16_hi(u.y);
+                f[j + 4] += p.beta * bf16_lo(u.z); f[j + 5] += p.beta * bf16_hi(u.z);
+                f[j + 6] += p.beta * bf16_lo(u.w); f[j + 7] += p.beta * bf16_hi(u.w);
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.n_out) f[j] += p.beta * __bfloat162float(rp[j]);
+            }
+          }
+          if (p.act_post) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          }
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.D) + (size_t)pix * p.ldd + n0;
+            if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.n_out) op[j] = f[j];
             }
           } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.n_out) op[j] = __float2bfloat16(f[j]);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)pix * p.ldd + n0;
+            if (p.vec_ok && n0 + 31 < p.n_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16(f[j], f[j + 1]);
+                u.y = pack_bf16(f[j + 2], f[j + 3]);
+                u.z = pack_bf16(f[j + 4], f[j + 5]);
+                u.w = pack_bf16(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(op + j) = u;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.n_out) op[j] = __float2bfloat16(f[j]);
+            }
           }
-        }
         }  // row_ok
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (use_tma && leader) bulk_wait_read<0>();  // staging panels must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -371,7 +537,8 @@ PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 // rank-2 bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols = BK,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   if (!enc) {
     saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -379,10 +546,10 @@ int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     saspa_set_error("cuTensorMapEncodeTiled(2d rows=%lld cols=%lld ld=%lld box_rows=%d) failed: %d", rows, cols, ld, box_rows, (int)r);
@@ -392,7 +559,8 @@ int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
 }
 
 // rank-4 NHWC bf16 activation [n, h, w, c] with pixel stride ld (elements); box = [bn, bh, bw, 64].
-int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, long long ld, int bn, int bh, int bw) {
+int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, long long ld, int bn, int bh, int bw, int box_c = BK,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   if (!enc) {
     saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -400,10 +568,10 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, l
   }
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     saspa_set_error("cuTensorMapEncodeTiled(nhwc n=%d h=%d w=%d c=%d ld=%lld box=%d,%d,%d) failed: %d", n, h, w, c, ld, bn, bh, bw, (int)r);
@@ -413,7 +581,8 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, l
 }
 
 template <int BN>
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r, const GemmParams& p,
+           cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     SASPA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
@@ -421,7 +590,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
   }
   int total = p.num_m_tiles * p.num_n_tiles;
   int grid = total < saspa_num_sms() ? total : saspa_num_sms();
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a0, a1, b, p);
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a0, a1, b, d, r, p);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }
@@ -449,13 +618,14 @@ int pick_bn(int N, int act) {
   return best;
 }
 
-int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p, cudaStream_t stream) {
+int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r,
+             const GemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 32: return launch<32>(a0, a1, b, p, stream);
-    case 64: return launch<64>(a0, a1, b, p, stream);
-    case 128: return launch<128>(a0, a1, b, p, stream);
-    case 160: return launch<160>(a0, a1, b, p, stream);
-    case 256: return launch<256>(a0, a1, b, p, stream);
+    case 32: return launch<32>(a0, a1, b, d, r, p, stream);
+    case 64: return launch<64>(a0, a1, b, d, r, p, stream);
+    case 128: return launch<128>(a0, a1, b, d, r, p, stream);
+    case 160: return launch<160>(a0, a1, b, d, r, p, stream);
+    case 256: return launch<256>(a0, a1, b, d, r, p, stream);
   }
   saspa_set_error("internal: no kernel for BN=%d", bn);
   return SASPA_ERR_UNSUPPORTED;
@@ -487,6 +657,11 @@ int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int l
   if (ep->bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0);
   if (ep->row_bias) vec = vec && ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0) && (N % 4 == 0) && (p.ld_row_bias % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
+  // staged TMA epilogue: bf16 output whose rows (and the residual's) are 16-byte aligned / strided
+  p.tma_store = (!ep->out_fp32 && ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && (ldd % 8 == 0) &&
+                 (!ep->residual || (((reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0) && (ep->ld_res % 8 == 0))))
+                    ? 1
+                    : 0;
   // the float4 bias loads assume 16-byte aligned bias pointers; fall back is per-element only when n+3 >= N
   SASPA_CHECK_ARG(!ep->bias || (reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "epilogue: bias must be 16-byte aligned");
   SASPA_CHECK_ARG(!ep->row_bias || ((reinterpret_cast<uintptr_t>(ep->row_bias) & 15) == 0 && N % 4 == 0 && p.ld_row_bias % 4 == 0),
@@ -517,7 +692,12 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   CUtensorMap tmA, tmB;
   if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
   if ((rc = encode_2d(&tmB, B, N, K, ldb, bn))) return rc;
-  return dispatch(bn, tmA, tmA, tmB, p, stream);
+  CUtensorMap tmD = tmA, tmR = tmA;
+  if (p.tma_store) {
+    if ((rc = encode_2d(&tmD, D, M, p.n_out, ldd, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (p.residual && (rc = encode_2d(&tmR, p.residual, M, p.n_out, p.ld_res, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
+  return dispatch(bn, tmA, tmA, tmB, tmD, tmR, p, stream);
 }
 
 extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int h, int w,
@@ -586,5 +766,11 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
     tmA1 = tmA0;
   }
   if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile))) return rc;
-  return dispatch(bn_tile, tmA0, tmA1, tmB, p, stream);
+  CUtensorMap tmD = tmA0, tmR = tmA0;
+  if (p.tma_store) {
+    if ((rc = encode_nhwc(&tmD, out, n, h, w, p.n_out, ldo, p.bn, p.bh, p.bw, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (p.residual && (rc = encode_nhwc(&tmR, p.residual, n, h, w, p.n_out, p.ld_res, p.bn, p.bh, p.bw, PANEL, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+  }
+  return dispatch(bn_tile, tmA0, tmA1, tmB, tmD, tmR, p, stream);
 }

@@ -51,6 +51,29 @@ def main():
         tf = 2.0 * M * N * K / ms / 1e9
         ref_ms = timeit(lambda: torch.matmul(a, b.t()))
         print(f"gemm {M}x{N}x{K}: {ms:.3f} ms {tf:.0f} TF/s ({tf / PEAKS['bf16_tflops']:.2f} of measured peak) | cuBLAS {2.0*M*N*K/ref_ms/1e9:.0f} TF/s")
+    print("== GEMM epilogue variants (GEGLU / in-place residual / wide QKV) ==")
+    for M, N, K, kind in [(B * 4096, 2560, 320, "geglu"), (B * 1024, 5120, 640, "geglu"), (B * 256, 10240, 1280, "geglu"), (B * 4096, 320, 320, "res"),
+                          (B * 1024, 640, 640, "res"), (B * 256, 1280, 1280, "res"), (B * 4096, 320, 1280, "res"), (B * 4096, 960, 320, "plain"),
+                          (B * 1024, 1920, 640, "plain")]:
+        a, b = rnd(M, K), rnd(N, K) * 0.05
+        bias = torch.zeros(N, device="cuda")
+        if kind == "geglu":
+            out = torch.empty(M, N // 2, dtype=torch.bfloat16, device="cuda")
+            fn = lambda: ops.gemm(a, b, out=out, bias=bias, act=ops.ACT_GEGLU)
+            byt = 2.0 * (M * K + M * N // 2)
+        elif kind == "res":
+            out = rnd(M, N)
+            fn = lambda: ops.gemm(a, b, out=out, bias=bias, residual=out, beta=1.0)
+            byt = 2.0 * (M * K + 2 * M * N)
+        else:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+            fn = lambda: ops.gemm(a, b, out=out)
+            byt = 2.0 * (M * K + M * N)
+        ms = timeit(fn)
+        tf = 2.0 * M * N * K / ms / 1e9
+        print(f"gemm[{kind}] {M}x{N}x{K}: {ms:.3f} ms {tf:.0f} TF/s ({tf / PEAKS['bf16_tflops']:.2f} of peak), {byt / ms / 1e6:.0f} GB/s algorithmic")
+    if only == "gemm":
+        return
     print("== conv3x3 implicit GEMM ==")
     for n, h, w, cin, cout in [(B, 64, 64, 320, 320), (B, 32, 32, 640, 640), (B, 16, 16, 1280, 1280), (B, 8, 8, 1280, 1280), (B, 64, 64, 640, 320),
                                (B, 16, 16, 2560, 1280), (4, 512, 512, 128, 128), (4, 256, 256, 256, 256), (8, 128, 128, 512, 512), (16, 64, 64, 512, 512)]:
