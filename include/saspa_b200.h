@@ -120,6 +120,11 @@ int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, in
                             const void* weight, int ksize, void* out, int ldo, int cout, const saspa_epilogue* ep_host,
                             cudaStream_t stream);
 
+/* Selects the 3x3 implicit-GEMM main loop: 0 = auto (halo tile when the map holds an 8 x 16 pixel tile, else one TMA
+ * box per tap), 1 = per-tap boxes only, 2 = halo only (error when not eligible).  Returns the previous setting; a
+ * negative argument only queries.  Process-wide; meant for tests and A/B timing. */
+int saspa_conv_impl(int impl);
+
 /* General im2col for the few strided / odd-channel convolutions (conv_in Cin=4, ControlNet cond embedding,
  * stride-2 downsamplers, ResNet stems): x bf16 NHWC [n,h,w,c] (pixel stride ldx) ->
  * cols bf16 [n*oh*ow, kpad], kpad >= kh*kw*c, zero padded; (kh,kw,c) ordering. */

@@ -39,11 +39,17 @@ constexpr int ACC_STRIDE = 256;  // column offset between the two accumulator bu
 constexpr int PANEL = 32;        // output columns per staging panel (64 B of bf16 per row)
 constexpr int PANEL_BYTES = BM * PANEL * 2;
 constexpr int SMEM_LIMIT = 227 * 1024;
+// halo mode: one TMA box of (HALO_BH + 2) x (HALO_BW + 2) pixels x 64 channels feeds all nine 3x3 taps
+constexpr int HALO_BW = 8, HALO_BH = 16;
+constexpr int HALO_ROWS = (HALO_BW + 2) * (HALO_BH + 2);
+constexpr int HALO_TX_BYTES = HALO_ROWS * 128;
+constexpr int HALO_STAGE_BYTES = (HALO_TX_BYTES + 1023) / 1024 * 1024;
+constexpr int HALO_STAGES = 2;
 
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles;
-  int mode;  // 0 = GEMM, 1 = implicit conv
+  int mode;  // 0 = GEMM, 1 = implicit conv (one TMA box per tap), 2 = implicit 3x3 conv from a halo tile
   // conv geometry
   int n_img, H, W, c0, c1, ksize;
   int bw, bh, bn;
@@ -78,9 +84,12 @@ struct Cfg {
   static constexpr int PD = NBUF / 2;
   static constexpr int STAGING_BYTES = 2 * NBUF * PANEL_BYTES;
   static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
-  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
-  static_assert(STAGES >= 3, "operand ring too shallow");
+  static constexpr int RING_BYTES = RING_BUDGET / 1024 * 1024;
+  static constexpr int STAGES = (RING_BYTES / STAGE_BYTES) > 8 ? 8 : (RING_BYTES / STAGE_BYTES);
+  // halo mode (3x3 conv): 2 halo stages of the activation + a ring of weight k-blocks
+  static constexpr int HB_STAGES = ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES) > 8 ? 8 : ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES);
+  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512;
+  static_assert(STAGES >= 3 && HB_STAGES >= 4, "operand ring too shallow");
   static_assert(BN % PANEL == 0, "BN must be a multiple of the staging panel width");
 };
 
@@ -125,31 +134,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* sStage = sB + STAGES * C::B_BYTES;  // 1024-aligned: every size above is a multiple of 1024
+  uint8_t* sHalo = smem;                                    // mode 2: HALO_STAGES halo tiles ...
+  uint8_t* sBh = smem + HALO_STAGES * HALO_STAGE_BYTES;     // ... then HB_STAGES weight k-blocks
+  uint8_t* sStage = smem + C::RING_BYTES;                   // 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + C::STAGING_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint64_t* rfull = bars + 2 * STAGES + 4;  // [2 groups][NBUF]
+  uint64_t* full = bars;         // [8]
+  uint64_t* empty = bars + 8;    // [8]
+  uint64_t* afull = bars + 16;   // [HALO_STAGES]
+  uint64_t* aempty = bars + 18;  // [HALO_STAGES]
+  uint64_t* tfull = bars + 20;
+  uint64_t* tempty = bars + 22;
+  uint64_t* rfull = bars + 24;  // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int cchunks = (p.mode == 1) ? (p.c0 + p.c1 + BK - 1) / BK : 0;
-  const int num_kb = (p.mode == 1) ? p.ksize * p.ksize * cchunks : (p.K + BK - 1) / BK;
+  const int cchunks = (p.mode != 0) ? (p.c0 + p.c1 + BK - 1) / BK : 0;
+  const int num_kb = (p.mode != 0) ? p.ksize * p.ksize * cchunks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
-    if (p.mode == 1 && p.c1 > 0) tma_prefetch_desc(&tmA1);
+    if (p.mode != 0 && p.c1 > 0) tma_prefetch_desc(&tmA1);
     if (p.tma_store) {
       tma_prefetch_desc(&tmD);
       if (p.residual) tma_prefetch_desc(&tmR);
     }
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < HALO_STAGES; ++a) {
+      mbar_init(&afull[a], 1);
+      mbar_init(&aempty[a], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -169,7 +186,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && p.mode == 2) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int ctot = p.c0 + p.c1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        const int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
+        const int ty = r % p.tiles_y, tn = r / p.tiles_y;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const int c = cc * BK;
+          mbar_wait(&aempty[sa], pa ^ 1);
+          mbar_expect_tx(&afull[sa], HALO_TX_BYTES);
+          if (c < p.c0)
+            tma_load_4d(&tmA0, sHalo + sa * HALO_STAGE_BYTES, &afull[sa], c, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+          else
+            tma_load_4d(&tmA1, sHalo + sa * HALO_STAGE_BYTES, &afull[sa], c - p.c0, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+          if (++sa == HALO_STAGES) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty[sb], pb ^ 1);
+            mbar_expect_tx(&full[sb], C::B_BYTES);
+            tma_load_2d(&tmB, sBh + sb * C::B_BYTES, &full[sb], tap * ctot + c, n_blk * BN);
+            if (++sb == C::HB_STAGES) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -212,7 +260,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && p.mode == 2) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          mbar_wait(&afull[sa], pa);
+          tc_fence_after();
+          const uint32_t halo = smem_u32(sHalo + sa * HALO_STAGE_BYTES);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full[sb], pb);
+            tc_fence_after();
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            // output pixel (ly, lx) reads halo pixel (ly + ky, lx + kx): a row shift inside the halo tile.  Each
+            // 8-row core-matrix group is one image row of the tile (8 px x 128 B contiguous); groups are one halo
+            // row ((HALO_BW + 2) x 128 B) apart.  The 128B swizzle is a function of the absolute smem address, so
+            // row-shifted start addresses read back exactly what TMA wrote.
+            const uint64_t a_desc = make_smem_desc_sbo(halo + (ky * (HALO_BW + 2) + kx) * 128, (HALO_BW + 2) * 128);
+            const uint64_t b_desc = make_smem_desc(smem_u32(sBh + sb * C::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+            tc_commit(&empty[sb]);
+            if (++sb == C::HB_STAGES) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          tc_commit(&aempty[sa]);
+          if (++sa == HALO_STAGES) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        tc_commit(&tfull[acc]);
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -631,6 +721,8 @@ int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
   return SASPA_ERR_UNSUPPORTED;
 }
 
+int g_conv_impl = 0;  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
+
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
   static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0};
   if (!ep) ep = &kDefault;
@@ -740,7 +832,19 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
       best_bi = bi;
     }
   }
-  p.mode = 1;
+  // 3x3 on maps of at least one 8 x 16 tile: halo mode (the activation is fetched once per 64-channel chunk
+  // instead of once per tap; operand traffic out of L2 is what bounds this kernel)
+  const bool halo = ksize == 3 && h >= HALO_BH && w >= HALO_BW && g_conv_impl != 1;
+  if (g_conv_impl == 2 && !halo) {
+    saspa_set_error("saspa_conv2d_igemm_bf16: halo mode forced but the shape is not eligible (ksize=%d h=%d w=%d)", ksize, h, w);
+    return SASPA_ERR_UNSUPPORTED;
+  }
+  if (halo) {
+    best_bw = HALO_BW;
+    best_bh = HALO_BH;
+    best_bi = 1;
+  }
+  p.mode = halo ? 2 : 1;
   p.n_img = n;
   p.H = h;
   p.W = w;
@@ -759,9 +863,10 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   p.K = ksize * ksize * (c0 + c1);
   p.M = n * h * w;
   CUtensorMap tmA0, tmA1, tmB;
-  if ((rc = encode_nhwc(&tmA0, x0, n, h, w, c0, ldx0, p.bn, p.bh, p.bw))) return rc;
+  const int abh = halo ? p.bh + 2 : p.bh, abw = halo ? p.bw + 2 : p.bw;  // activation box (with the 1-px halo in mode 2)
+  if ((rc = encode_nhwc(&tmA0, x0, n, h, w, c0, ldx0, p.bn, abh, abw))) return rc;
   if (c1 > 0) {
-    if ((rc = encode_nhwc(&tmA1, x1, n, h, w, c1, ldx1, p.bn, p.bh, p.bw))) return rc;
+    if ((rc = encode_nhwc(&tmA1, x1, n, h, w, c1, ldx1, p.bn, abh, abw))) return rc;
   } else {
     tmA1 = tmA0;
   }
@@ -773,4 +878,10 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
       return rc;
   }
   return dispatch(bn_tile, tmA0, tmA1, tmB, tmD, tmR, p, stream);
+}
+
+extern "C" int saspa_conv_impl(int impl) {
+  const int prev = g_conv_impl;
+  if (impl >= 0 && impl <= 2) g_conv_impl = impl;
+  return prev;
 }

@@ -96,6 +96,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
+// Same, with an explicit stride between 8-row groups (rows of a group stay 128 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // bf16 x bf16 -> fp32; A K-major (smem or TMEM), B K-major or MN-major; M = bm, N = bn.
 __host__ __device__ constexpr uint32_t make_idesc(int bm, int bn, int b_mn_major = 0) {
   return (1u << 4) /*D fp32*/ | (1u << 7) /*A bf16*/ | (1u << 10) /*B bf16*/ | ((uint32_t)b_mn_major << 16) | ((uint32_t)(bn >> 3) << 17) |

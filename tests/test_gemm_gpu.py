@@ -73,11 +73,22 @@ def test_gemm_geglu(cuda_device):
     _check(got, ref)
 
 
+@pytest.fixture(params=[0, 1], ids=["conv-auto-halo", "conv-per-tap"])
+def conv_impl(request):
+    """Runs a conv test once per 3x3 main loop (saspa_conv_impl: 0 = auto / halo tile where eligible, 1 = one TMA box per tap)."""
+    from saspa_aug_b200 import _lib
+
+    prev = _lib.load().saspa_conv_impl(request.param)
+    yield request.param
+    _lib.load().saspa_conv_impl(prev)
+
+
 @pytest.mark.parametrize("cfg", [  # n, h, w, cin, cout, ksize
+    (1, 17, 9, 64, 64, 3), (3, 40, 24, 72, 40, 3),
     (2, 64, 64, 320, 320, 3), (4, 32, 32, 640, 640, 3), (4, 16, 16, 1280, 1280, 3), (6, 8, 8, 1280, 1280, 3),
     (2, 64, 88, 320, 320, 3), (1, 128, 128, 128, 128, 3), (3, 16, 16, 64, 96, 3), (2, 32, 32, 320, 640, 1), (1, 24, 40, 128, 256, 3),
     (2, 8, 8, 2560, 1280, 3), (2, 64, 64, 16, 16, 3), (2, 32, 32, 32, 32, 3), (1, 64, 64, 96, 96, 3), (2, 16, 16, 8, 24, 3), (2, 64, 64, 320, 4, 3)])
-def test_conv_igemm(cuda_device, cfg):
+def test_conv_igemm(cuda_device, conv_impl, cfg):
     n, h, w, cin, cout, ks = cfg
     x = _rand((n, h, w, cin), 10)
     wt = _rand((cout, cin, ks, ks), 11, 1.0 / math.sqrt(cin * ks * ks))
@@ -88,7 +99,7 @@ def test_conv_igemm(cuda_device, cfg):
     _check(got, ref)
 
 
-def test_conv_igemm_two_sources_rowbias_residual(cuda_device):
+def test_conv_igemm_two_sources_rowbias_residual(cuda_device, conv_impl):
     n, h, w, c0, c1, cout = 2, 32, 32, 640, 320, 640
     x0, x1 = _rand((n, h, w, c0), 12), _rand((n, h, w, c1), 13)
     wt = _rand((cout, c0 + c1, 3, 3), 14, 1.0 / math.sqrt(9 * (c0 + c1)))
@@ -102,7 +113,7 @@ def test_conv_igemm_two_sources_rowbias_residual(cuda_device):
     _check(got, ref)
 
 
-def test_conv_igemm_channel_slice_views(cuda_device):
+def test_conv_igemm_channel_slice_views(cuda_device, conv_impl):
     """Inputs / outputs living inside wider concat buffers (pixel stride > channels)."""
     n, h, w = 2, 16, 16
     buf = _rand((n, h, w, 1280 + 640), 16)

@@ -42,6 +42,14 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     if only == "hbm":
         return hbm(B)
+    if only != "conv":
+        gemm_section(B, only)
+    if only == "gemm":
+        return
+    conv_section(B, only)
+
+
+def gemm_section(B, only):
     print("== GEMM (tcgen05) ==")
     for M, N, K in [(8192, 8192, 8192), (B * 4096, 320, 320), (B * 4096, 2560, 320), (B * 4096, 320, 1280), (B * 1024, 640, 640), (B * 1024, 5120, 640),
                     (B * 256, 1280, 1280), (B * 256, 10240, 1280), (B * 256, 1280, 5120), (B * 64, 1280, 1280), (B * 4096, 320, 2880)]:
@@ -72,16 +80,25 @@ def main():
         ms = timeit(fn)
         tf = 2.0 * M * N * K / ms / 1e9
         print(f"gemm[{kind}] {M}x{N}x{K}: {ms:.3f} ms {tf:.0f} TF/s ({tf / PEAKS['bf16_tflops']:.2f} of peak), {byt / ms / 1e6:.0f} GB/s algorithmic")
-    if only == "gemm":
-        return
+
+
+def conv_section(B, only):
     print("== conv3x3 implicit GEMM ==")
     for n, h, w, cin, cout in [(B, 64, 64, 320, 320), (B, 32, 32, 640, 640), (B, 16, 16, 1280, 1280), (B, 8, 8, 1280, 1280), (B, 64, 64, 640, 320),
                                (B, 16, 16, 2560, 1280), (4, 512, 512, 128, 128), (4, 256, 256, 256, 256), (8, 128, 128, 512, 512), (16, 64, 64, 512, 512)]:
         x, wk = rnd(n, h, w, cin), rnd(cout, 9 * cin)
         out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
-        ms = timeit(lambda: ops.conv2d_igemm(x, wk, 3, out=out))
-        tf = 2.0 * n * h * w * cout * 9 * cin / ms / 1e9
-        print(f"conv {n}x{h}x{w} {cin}->{cout}: {ms:.3f} ms {tf:.0f} TF/s ({tf / PEAKS['bf16_tflops']:.2f})")
+        from saspa_aug_b200 import _lib
+        res = []
+        for impl in (1, 0):
+            _lib.load().saspa_conv_impl(impl)
+            ms = timeit(lambda: ops.conv2d_igemm(x, wk, 3, out=out))
+            res.append((ms, 2.0 * n * h * w * cout * 9 * cin / ms / 1e9))
+        _lib.load().saspa_conv_impl(0)
+        print(f"conv {n}x{h}x{w} {cin}->{cout}: per-tap {res[0][0]:.3f} ms {res[0][1]:.0f} TF/s | auto(halo) {res[1][0]:.3f} ms {res[1][1]:.0f} TF/s "
+              f"({res[1][1] / PEAKS['bf16_tflops']:.2f} of peak)")
+    if only == "conv":
+        return
     print("== attention (mma.sync flash) ==")
     for b, heads, tq, tkv, d in [(B, 8, 4096, 4096, 40), (B, 8, 1024, 1024, 80), (B, 8, 256, 256, 160), (B, 8, 4096, 77, 40), (B, 8, 1024, 77, 80)]:
         q, k, v = rnd(b, tq, heads * d), rnd(b, tkv, heads * d), rnd(b, tkv, heads * d)
