@@ -687,8 +687,11 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 
 // Tile width along N.  SD channel counts are multiples of 320 -> 160 tiles them exactly; the VAE /
 // ResNets are powers of two; GEGLU needs value|gate halves in one tile (256 = 128 + 128).
+int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
+
 int pick_bn(int N, int act) {
   if (act == SASPA_ACT_GEGLU) return 256;
+  if (g_force_bn) return g_force_bn;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   if (N % 160 == 0 && N % 256 != 0) return 160;
@@ -883,5 +886,12 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
 extern "C" int saspa_conv_impl(int impl) {
   const int prev = g_conv_impl;
   if (impl >= 0 && impl <= 2) g_conv_impl = impl;
+  return prev;
+}
+
+// Tuning hook: force the N tile width of the non-GEGLU kernels (0 restores the heuristic).  Not part of the product API.
+extern "C" int saspa_gemm_force_bn(int bn) {
+  const int prev = g_force_bn;
+  if (bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256) g_force_bn = bn;
   return prev;
 }
