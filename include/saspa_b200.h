@@ -125,6 +125,11 @@ int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, in
  * negative argument only queries.  Process-wide; meant for tests and A/B timing. */
 int saspa_conv_impl(int impl);
 
+/* CTAs per output tile of the tcgen05 GEMM / conv kernel: 0 = auto (two-CTA 256-row tiles, tcgen05.mma.cta_group::2,
+ * whenever the problem has two or more 128-row tiles), 1 = single-CTA tiles only, 2 = two-CTA tiles only.  Returns the
+ * previous setting; a negative argument only queries.  Process-wide; meant for tests and A/B timing. */
+int saspa_gemm_force_ctas(int ctas);
+
 /* General im2col for the few strided / odd-channel convolutions (conv_in Cin=4, ControlNet cond embedding,
  * stride-2 downsamplers, ResNet stems): x bf16 NHWC [n,h,w,c] (pixel stride ldx) ->
  * cols bf16 [n*oh*ow, kpad], kpad >= kh*kw*c, zero padded; (kh,kw,c) ordering. */
@@ -141,6 +146,9 @@ int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, int c, int kh
 size_t saspa_groupnorm_workspace_bytes(int n, int hw, int groups);
 int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma,
                               const float* beta, int act, void* y, int ldy, void* stats_ws, size_t ws_bytes, cudaStream_t stream);
+/* 0 = auto (register-resident single-read kernel where an image slice fits one wave, else the two-pass kernel),
+ * 1 = two-pass kernel only.  Returns the previous setting; negative only queries.  For tests and A/B timing. */
+int saspa_groupnorm_impl(int impl);
 /* LayerNorm over the last dim: x [rows, c] (row stride ldx) -> y bf16 [rows, c] (row stride ldy). */
 int saspa_layernorm_bf16(const void* x, int ldx, int rows, int c, float eps, const float* gamma, const float* beta, void* y,
                          int ldy, cudaStream_t stream);

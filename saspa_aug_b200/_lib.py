@@ -87,6 +87,8 @@ SIGNATURES = {
     ),
     "saspa_attention_impl": (c_int, [c_int]),
     "saspa_conv_impl": (c_int, [c_int]),
+    "saspa_groupnorm_impl": (c_int, [c_int]),
+    "saspa_gemm_force_ctas": (c_int, [c_int]),
     "saspa_softmax_rows_bf16": (c_int, [_P, c_int, _P, c_int, ctypes.c_longlong, c_int, c_float, _P]),
     "saspa_transpose_bf16": (c_int, [_P, c_int, ctypes.c_longlong, _P, c_int, ctypes.c_longlong, c_int, c_int, c_int, _P]),
     "saspa_timestep_sinusoid_bf16": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),

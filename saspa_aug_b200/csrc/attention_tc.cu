@@ -18,6 +18,11 @@
 //              tcgen05.ld the S row, release S, running max with lazy rescale (O is only rescaled in TMEM
 //              when the max grows by more than 2^8), p = ex2(s*c - m), bf16 P packed two per column back
 //              into TMEM with tcgen05.st; finally O / l -> global.
+//              A quarter of the exponentials are evaluated on the FMA pipe (Cody-Waite split + cubic, rel. error 7.5e-5,
+//              far below the bf16 rounding of P): the d = 40 layers are bound by the 16/clk/SM MUFU unit, not by the
+//              tensor pipe.
+//   warp 10    (head_dim % 16 == 8 only) patches a column of ones into the zero-cost pad of each landed V tile, so
+//              the P V MMA also accumulates the softmax denominator sum_j P_ij in O[:, D] -- no per-element adds.
 // Padding is free: head_dim 40 runs as K = 48 (the Q pad chunk is zeroed in smem; K's pad columns then
 // multiply zeros) and PV as N = 48 (the extra accumulator columns are never stored).
 #include "tc_ptx.cuh"
@@ -26,7 +31,7 @@
 namespace {
 using namespace tcx;
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_THREADS = 352;
 constexpr int QROWS = 128;
 
 template <int D>
@@ -43,6 +48,8 @@ struct ACfg {
   static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int P_OFF = 2 * BKV;  // TMEM columns: S_i at i*BKV, P_i at P_OFF + i*BKV/2, O_i at O_OFF + i*ON
   static constexpr int O_OFF = 3 * BKV;
+  static constexpr bool ONES = (D % 16) != 0;  // a free pad column exists: row sums come out of the P V MMA
+  static constexpr int POLY_EVERY = 4;         // every POLY_EVERY-th exponential runs on the FMA pipe (0 = none)
   static_assert(O_OFF + 2 * ON <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "smem budget");
 };
@@ -53,6 +60,7 @@ struct AttnParams {
   int heads, tq, tkv;
   float scale_log2;
   int causal;
+  int debug;  // timing experiments only (tools_attn_bench.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
 };
 
 template <int D>
@@ -74,7 +82,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   uint64_t* k_empty = k_full + STAGES;
   uint64_t* v_full = k_empty + STAGES;
   uint64_t* v_empty = v_full + STAGES;
-  uint64_t* s_full = v_empty + STAGES;  // [2]
+  uint64_t* v_ready = v_empty + STAGES;  // V tile patched with the ones column (ONES only)
+  uint64_t* s_full = v_ready + STAGES;   // [2]
   uint64_t* s_free = s_full + 2;
   uint64_t* p_full = s_free + 2;
   uint64_t* o_done = p_full + 2;
@@ -98,6 +107,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
+      mbar_init(&v_ready[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -145,22 +155,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         const uint32_t d_tmem = tmem_base + i * BKV;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
+          if (p.debug & 4) break;
           const int pn = ks >> 2, kk = ks & 3;
           const uint64_t a = make_smem_desc(smem_u32(sQ + (i * NPAN + pn) * C::QPAN_BYTES) + kk * 32);
           const uint64_t bd = make_smem_desc(smem_u32(sK + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES) + kk * 32);
           tc_mma_bf16(d_tmem, a, bd, idesc_qk, ks != 0 ? 1u : 0u);
         }
         tc_commit(&s_full[i]);
-      };
-      auto issue_pv = [&](int i, int s, bool acc) {
-        const uint32_t d_tmem = tmem_base + C::O_OFF + i * ON;
-        const uint32_t a_tmem = tmem_base + C::P_OFF + i * (BKV / 2);
-#pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          const uint64_t bd = make_smem_desc_mn(smem_u32(sV + s * C::KV_STAGE_BYTES) + ks * 2048, C::KPAN_BYTES);
-          tc_mma_bf16_ts(d_tmem, a_tmem + ks * 8, bd, idesc_pv, (acc || ks != 0) ? 1u : 0u);
-        }
-        tc_commit(&o_done[i]);
       };
       mbar_wait(PAD_Q ? q_ready : q_full, 0);
       tc_fence_after();
@@ -181,13 +182,41 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
           }
           tc_commit(&k_empty[s1]);
         }
-        mbar_wait(&v_full[s], (j / STAGES) & 1);
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], j & 1);
-          tc_fence_after();
-          issue_pv(i, s, j > 0);
+        mbar_wait(C::ONES ? &v_ready[s] : &v_full[s], (j / STAGES) & 1);
+        tc_fence_after();
+        // the two query tiles accumulate into independent TMEM regions: interleaving their k-steps hides part of the
+        // per-instruction latency of these small (128 x 48 x 16) MMAs (measured -6% on the d = 40 layers)
+        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          if (p.debug & 2) break;
+          const uint64_t bd = make_smem_desc_mn(smem_u32(sV + s * C::KV_STAGE_BYTES) + ks * 2048, C::KPAN_BYTES);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tc_mma_bf16_ts(tmem_base + C::O_OFF + i * ON, tmem_base + C::P_OFF + i * (BKV / 2) + ks * 8, bd, idesc_pv, (j > 0 || ks != 0) ? 1u : 0u);
         }
+        tc_commit(&o_done[0]);
+        tc_commit(&o_done[1]);
         tc_commit(&v_empty[s]);
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== V patcher: ones into pad column D of every landed V tile =====================
+    if (C::ONES) {
+      constexpr int ch = D / 8, pn = ch / 8, lc = ch % 8;  // 16-byte chunk holding column D
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&v_full[s], (j / STAGES) & 1);
+        uint8_t* tile = sV + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES;
+        for (int row = lane; row < BKV; row += 32) {
+          // the whole chunk [D, D + 8) is pad: ones in column D, zeros after it (keeps the unused accumulator columns finite)
+          *reinterpret_cast<uint4*>(tile + row * 128 + ((lc ^ (row & 7)) << 4)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_ready[s]);
       }
     }
   } else {
@@ -211,7 +240,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     }
 
     float m_used = -INFINITY;  // exponent reference (log2 domain); lags the true running max by at most 8
-    float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // unused when the P V MMA accumulates the row sum (C::ONES)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
@@ -254,8 +283,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
           const float f = need ? ex2_approx(m_used - m_tile) : 1.0f;
           if (need) {
             m_used = m_tile;
+            if constexpr (!C::ONES) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) lsum[a] *= f;
+              for (int a = 0; a < 4; ++a) lsum[a] *= f;
+            }
           }
 #pragma unroll 1
           for (int c = 0; c < ON; c += 16) {
@@ -272,12 +303,21 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 
       const float neg_m = -m_used;
       uint32_t pk[BKV / 2];
+      if (p.debug & 1) {  // timing experiment: no exponentials at all
 #pragma unroll
-      for (int c = 0; c < BKV; c += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m));
-        lsum[(c >> 1) & 3] += p0 + p1;
-        pk[c >> 1] = pack_bf16(p0, p1);
+        for (int c = 0; c < BKV; c += 2)
+          pk[c >> 1] = pack_bf16(fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m), fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m));
+      } else {
+#pragma unroll
+        for (int c = 0; c < BKV; c += 2) {
+          const float x0 = fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m);
+          const float x1 = fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m);
+          constexpr int PE = C::POLY_EVERY;
+          const float p0 = (PE > 0 && (c % (PE > 0 ? PE : 1)) == PE - 1) ? ex2_poly(x0) : ex2_approx(x0);
+          const float p1 = (PE > 0 && ((c + 1) % (PE > 0 ? PE : 1)) == PE - 1) ? ex2_poly(x1) : ex2_approx(x1);
+          if constexpr (!C::ONES) lsum[(c >> 1) & 3] += p0 + p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
       }
       if (!p_free) {  // P V of the previous key tile must have consumed P_i
         mbar_wait(&o_done[i], (j - 1) & 1);
@@ -294,7 +334,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     // ---- epilogue: O / l -> global ----
     mbar_wait(&o_done[i], (n_tiles - 1) & 1);
     tc_fence_after();
-    const float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+    float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+    if constexpr (C::ONES) {
+      uint32_t lu;
+      tc_ld1(t_o + D, lu);  // column D of O = sum_j P_ij (ones column of V)
+      tc_wait_ld();
+      l = __uint_as_float(lu);
+    }
     const float inv = l > 0.0f ? 1.0f / l : 0.0f;
     __nv_bfloat16* og = p.o + ((long long)b * p.tq + qi) * p.ldo + (long long)h * D;
     const bool valid = qi < p.tq;
@@ -366,6 +412,8 @@ int encode_rows3d(CUtensorMap* tm, const void* base, int cols, int rows, int bat
   return SASPA_OK;
 }
 
+int g_attn_debug = 0;
+
 template <int D>
 int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
               float scale, int causal, cudaStream_t stream) {
@@ -388,6 +436,7 @@ int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int
   p.tkv = tkv;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  p.debug = g_attn_debug;
   dim3 grid(ceil_div(tq, 2 * QROWS), batch * heads);
   attn_tc_kernel<D><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
   SASPA_LAUNCH_CHECK();
@@ -409,4 +458,11 @@ int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const voi
     case 160: return launch_tc<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
     default: return SASPA_ERR_UNSUPPORTED;
   }
+}
+
+// Timing-experiment hook (see AttnParams::debug); results are WRONG while it is non-zero.  Not part of the product API.
+extern "C" int saspa_attention_debug(int flags) {
+  const int prev = g_attn_debug;
+  g_attn_debug = flags;
+  return prev;
 }

@@ -113,16 +113,20 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const __nv_bfloat1
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0f;
     const __nv_bfloat16* base = xi + my_v * 8;
     int p = p0 + my_p;
-    for (; p + pix_par < p1; p += 2 * pix_par) {  // two loads in flight
-      uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
-      uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + pix_par) * ldx));
-      float f[8], g[8];
-      unpack8(u0, f);
-      unpack8(u1, g);
+    for (; p + 3 * pix_par < p1; p += 4 * pix_par) {  // four loads in flight
+      uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j] + g[j];
-        ss[j] += f[j] * f[j] + g[j] * g[j];
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + k * pix_par) * ldx));
+#pragma unroll
+      for (int k = 0; k < 4; k += 2) {
+        float f[8], g[8];
+        unpack8(u[k], f);
+        unpack8(u[k + 1], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j] + g[j];
+          ss[j] += f[j] * f[j] + g[j] * g[j];
+        }
       }
     }
     for (; p < p1; p += pix_par) {
@@ -207,7 +211,24 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const __nv_bfloat1
     }
     const __nv_bfloat16* base = xi + my_v * 8;
     __nv_bfloat16* yb = y + (size_t)img * hw * ldy + my_v * 8;
-    for (int p = p0 + my_p; p < p1; p += pix_par) {
+    int p = p0 + my_p;
+    for (; p + 3 * pix_par < p1; p += 4 * pix_par) {  // four loads in flight
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)(p + k * pix_par) * ldx));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(f[j], sc[j], sh[j]);
+          f[j] = (act == SASPA_ACT_SILU) ? silu_f(t) : t;
+        }
+        *reinterpret_cast<uint4*>(yb + (size_t)(p + k * pix_par) * ldy) = pack8(f);
+      }
+    }
+    for (; p < p1; p += pix_par) {
       uint4 u = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
       float f[8];
       unpack8(u, f);
@@ -219,6 +240,185 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const __nv_bfloat1
       *reinterpret_cast<uint4*>(yb + (size_t)p * ldy) = pack8(f);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm, register-resident variant (every UNet / ControlNet level: hw <= ~8K pixels per image).
+// A CTA owns (image, channel slice, pixel part): a slice is a whole number of groups (and of 16-byte vectors), a part
+// is pix_par x GN_VPT pixels.  Every thread issues all of its <= GN_VPT 16-byte loads up front (memory-level
+// parallelism 16) and keeps them in registers: x is read from HBM exactly once, nothing is re-read.  Statistics:
+// per-thread per-channel sums -> shared memory -> one warp per group (fixed order) -> if the image slice spans several
+// parts, partials go through the workspace and the parts of ONE (image, slice) wait for each other on an arrive
+// counter (they are adjacent in dispatch order, so all of them are resident) -> every CTA folds the partials in the
+// same order (double).  Deterministic and independent of what else shares the batch.  Then scale / shift (+SiLU) is
+// applied to the registers and written out.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_VPT = 16;
+
+__global__ void __launch_bounds__(GN_THREADS, 1)
+    gn_reg_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int c, int groups, float eps, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int act, __nv_bfloat16* __restrict__ y, int ldy, int c_slice, int slices, int parts,
+                  int pix_per_cta, float2* __restrict__ partials, unsigned int* __restrict__ counters) {
+  extern __shared__ float gn_smem[];  // [pix_par][c_slice] sums + [pix_par][c_slice] squares; later scale[c_slice], shift[c_slice]
+  __shared__ float s_stat[2 * 64];
+  const int part = blockIdx.x % parts;
+  const int slice = (blockIdx.x / parts) % slices;
+  const int img = blockIdx.x / (parts * slices);
+  const int cg = c / groups, gps = c_slice / cg;  // channels per group, groups per slice
+  const int tpp = c_slice / 8, pix_par = GN_THREADS / tpp;
+  const int my_v = threadIdx.x % tpp, my_p = threadIdx.x / tpp;
+  const bool active = my_p < pix_par;
+  const int p0 = part * pix_per_cta;
+  const size_t col = (size_t)slice * c_slice + my_v * 8;
+  const __nv_bfloat16* xb = x + (size_t)img * hw * ldx + col;
+
+  uint4 v[GN_VPT];
+#pragma unroll
+  for (int k = 0; k < GN_VPT; ++k) {
+    const int p = p0 + my_p + k * pix_par;
+    v[k] = (active && p < hw && k * pix_par < pix_per_cta) ? __ldg(reinterpret_cast<const uint4*>(xb + (size_t)p * ldx)) : make_uint4(0, 0, 0, 0);
+  }
+  float* s_sum = gn_smem;
+  float* s_sq = gn_smem + (size_t)pix_par * c_slice;
+  if (active) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+      float f[8];
+      unpack8(v[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] = fmaf(f[j], f[j], ss[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_sum[my_p * c_slice + my_v * 8 + j] = s[j];
+      s_sq[my_p * c_slice + my_v * 8 + j] = ss[j];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double cnt = (double)hw * cg;
+  for (int g = warp; g < gps; g += GN_THREADS / 32) {
+    float a = 0.0f, b = 0.0f;
+    for (int i = lane; i < pix_par * cg; i += 32) {
+      const int pp = i / cg, ch = g * cg + (i - pp * cg);
+      a += s_sum[pp * c_slice + ch];
+      b += s_sq[pp * c_slice + ch];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      if (parts == 1) {
+        const double mean = (double)a / cnt;
+        double var = (double)b / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_stat[g] = (float)mean;
+        s_stat[64 + g] = (float)(1.0 / sqrt(var + (double)eps));
+      } else {
+        partials[(((size_t)img * slices + slice) * parts + part) * gps + g] = make_float2(a, b);
+      }
+    }
+  }
+  if (parts > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned int* ctr = counters + (size_t)img * slices + slice;
+      atomicAdd(ctr, 1u);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        if (seen < (unsigned int)parts) __nanosleep(32);
+      } while (seen < (unsigned int)parts);
+    }
+    __syncthreads();
+    if (threadIdx.x < gps) {
+      const int g = threadIdx.x;
+      double a = 0.0, b = 0.0;
+      for (int q = 0; q < parts; ++q) {
+        const float2 t = __ldcg(&partials[(((size_t)img * slices + slice) * parts + q) * gps + g]);
+        a += (double)t.x;
+        b += (double)t.y;
+      }
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_stat[g] = (float)mean;
+      s_stat[64 + g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  float* s_scale = gn_smem;
+  float* s_shift = gn_smem + c_slice;
+  for (int ch = threadIdx.x; ch < c_slice; ch += GN_THREADS) {
+    const int g = ch / cg, gc = slice * c_slice + ch;
+    const float ga = gamma ? gamma[gc] : 1.0f, be = beta ? beta[gc] : 0.0f;
+    const float sc = s_stat[64 + g] * ga;
+    s_scale[ch] = sc;
+    s_shift[ch] = be - s_stat[g] * sc;
+  }
+  __syncthreads();
+  if (active) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = s_scale[my_v * 8 + j];
+      sh[j] = s_shift[my_v * 8 + j];
+    }
+    __nv_bfloat16* yb = y + (size_t)img * hw * ldy + col;
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+      const int p = p0 + my_p + k * pix_par;
+      if (p < hw && k * pix_par < pix_per_cta) {
+        float f[8];
+        unpack8(v[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(f[j], sc[j], sh[j]);
+          f[j] = (act == SASPA_ACT_SILU) ? silu_f(t) : t;
+        }
+        *reinterpret_cast<uint4*>(yb + (size_t)p * ldy) = pack8(f);
+      }
+    }
+  }
+}
+
+struct GnRegPlan {
+  bool ok;
+  int c_slice, slices, parts, pix_per_cta;
+};
+// Slice = a multiple of lcm(channels per group, 8) that divides c, as close to 320 channels as possible (<= 512).
+GnRegPlan gn_reg_plan(int hw, int c, int groups) {
+  GnRegPlan r = {false, 0, 0, 0, 0};
+  const int cg = c / groups;
+  int a = cg, b = 8;
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  const int unit = cg / a * 8;  // lcm(cg, 8)
+  int best = 0;
+  for (int m = unit; m <= 512 && m <= c; m += unit) {
+    if (c % m != 0) continue;
+    if (best == 0 || abs(m - 320) < abs(best - 320)) best = m;
+  }
+  if (best == 0 || best / cg > 64) return r;
+  r.c_slice = best;
+  r.slices = c / best;
+  const int pix_par = GN_THREADS / (best / 8);
+  r.pix_per_cta = pix_par * GN_VPT;
+  r.parts = (hw + r.pix_per_cta - 1) / r.pix_per_cta;
+  // the parts of one (image, slice) wait for each other: keep them well inside one wave.  Measured (profiles/
+  // r1_groupnorm_ab.txt): one 16-warp CTA per SM wins up to ~1K pixels per image (2-3x at 16x16 / 8x8, where the
+  // two-pass kernel runs one CTA per image); at 64x64 the two-pass kernel's four CTAs per SM overlap better.
+  r.ok = r.parts <= 64 && hw <= 1024;
+  return r;
 }
 
 // workspace layout: [n] u32 arrive counters (padded to 256 B) | [n][ctas_per_img][groups] float2 partials
@@ -236,8 +436,11 @@ GnPlan gn_plan(int n, int hw, int groups) {
   if (per > 32) per = 32;
   p.pix_per_cta = ceil_div(hw, per);
   p.ctas_per_img = ceil_div(hw, p.pix_per_cta);
-  p.counters_bytes = ((size_t)n * 4 + 255) / 256 * 256;
-  p.total_bytes = p.counters_bytes + (size_t)n * p.ctas_per_img * groups * sizeof(float2);
+  // sized for either kernel: counters per (image, slice) with slices <= groups; partials per (image, part, group)
+  // with parts <= max(ctas_per_img, 64) (register-resident variant)
+  p.counters_bytes = ((size_t)n * groups * 4 + 255) / 256 * 256;
+  const int max_parts = p.ctas_per_img > 64 ? p.ctas_per_img : 64;
+  p.total_bytes = p.counters_bytes + (size_t)n * max_parts * groups * sizeof(float2);
   return p;
 }
 
@@ -578,6 +781,13 @@ extern "C" int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, in
   return SASPA_OK;
 }
 
+int g_gn_impl = 0;  // 0 auto, 1 two-pass kernel only (tests / A-B timing)
+extern "C" int saspa_groupnorm_impl(int impl) {
+  const int prev = g_gn_impl;
+  if (impl == 0 || impl == 1) g_gn_impl = impl;
+  return prev;
+}
+
 extern "C" size_t saspa_groupnorm_workspace_bytes(int n, int hw, int groups) {
   if (n <= 0 || hw <= 0 || groups <= 0) return 256;
   return gn_plan(n, hw, groups).total_bytes;
@@ -598,6 +808,22 @@ extern "C" int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, 
   }
   unsigned int* counters = reinterpret_cast<unsigned int*>(stats_ws);
   float2* partials = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats_ws) + p.counters_bytes);
+  const GnRegPlan rp = gn_reg_plan(hw, c, groups);
+  if (rp.ok && g_gn_impl != 1) {
+    if (rp.parts > 1) SASPA_CUDA(cudaMemsetAsync(counters, 0, (size_t)n * rp.slices * 4, stream));
+    const int pp = GN_THREADS / (rp.c_slice / 8);
+    const size_t sm = sizeof(float) * 2 * (size_t)pp * rp.c_slice;
+    static size_t sm_configured = 0;
+    if (sm > 48 * 1024 && sm > sm_configured) {
+      SASPA_CUDA(cudaFuncSetAttribute(gn_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      sm_configured = sm;
+    }
+    gn_reg_kernel<<<n * rp.slices * rp.parts, GN_THREADS, sm, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, eps, gamma, beta, act,
+                                                                       static_cast<__nv_bfloat16*>(y), ldy, rp.c_slice, rp.slices, rp.parts, rp.pix_per_cta,
+                                                                       partials, counters);
+    SASPA_LAUNCH_CHECK();
+    return SASPA_OK;
+  }
   SASPA_CUDA(cudaMemsetAsync(counters, 0, (size_t)n * 4, stream));
   const int pix_par = GN_THREADS / (c / 8);
   const size_t smem = sizeof(float) * 2 * (size_t)(pix_par > 1 ? pix_par : 1) * c;

@@ -7,23 +7,30 @@
 // AutoencoderKL forward (reference: pipe(**pipe_args), run_aug/run_aug.py:278) and the filter nets
 // (all_utils/utils.py:361 WSDAN_CAL, :152-164 CLIP).
 //
-// Structure per CTA (320 threads, 1 CTA / SM, grid = min(tiles, #SM)):
-//   warp 0   : TMA producer  - cp.async.bulk.tensor (2-D for GEMM, 4-D NHWC boxes for conv: the 3x3 taps are
-//              nine shifted boxes and TMA's out-of-bounds zero fill IS the conv padding) into a
-//              STAGES-deep ring of 128B-swizzled smem tiles, signalled by mbarrier complete_tx.
-//   warp 1   : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::f16
-//              (128 x BN x 16 per instruction, fp32 accumulate in TMEM), tcgen05.commit frees smem
-//              stages and publishes the accumulator.  Two accumulator buffers (columns 0 / 256) let the
-//              epilogue of tile i overlap the main loop of tile i+1.
+// Structure per CTA (320 threads, 1 CTA / SM):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor into a ring of 128B-swizzled smem tiles, signalled by mbarrier
+//              complete_tx.  GEMM: 2-D boxes.  Conv, per-tap mode: nine shifted 4-D NHWC boxes per 64-channel chunk
+//              (TMA's out-of-bounds zero fill IS the conv padding).  Conv, halo mode (3x3): ONE box of (16+2)x(8+2)
+//              pixels per chunk; the nine taps are row-shifted UMMA descriptors into it (the 128B swizzle is a
+//              function of the absolute smem address, so shifted windows read back what TMA wrote) -- operand
+//              traffic out of L2 is what bounds these kernels.
+//   warp 1   : allocates 512 TMEM columns; one lane issues tcgen05.mma.kind::f16 (fp32 accumulate in TMEM),
+//              tcgen05.commit frees smem stages and publishes the accumulator.  Two accumulator buffers (columns
+//              0 / 256) let the epilogue of tile i overlap the main loop of tile i+1.
 //   warps 2-9: epilogue, two groups of four warps (one warp per TMEM lane quadrant); group g owns the
 //              32-column output panels k = g, g+2, ...:  tcgen05.ld 32x32b.x32 (one output row per thread),
 //              fused bias / per-image row bias (time embedding) / activation / GEGLU / alpha / residual.
 //              bf16 outputs leave through shared memory: each thread writes its 64-byte row slice into a
-//              64B-swizzled [128 x 32] staging panel and one thread issues a TMA store (coalesced, clipped at
-//              the tensor edge by the hardware); the residual arrives the same way (TMA load into the staging
-//              panel, prefetched two panels ahead, across tile boundaries).  Most of this model's GEMMs
-//              have K <= 1280 and M >= 32768, i.e. they are bound by how fast the epilogue drains TMEM.
+//              64B-swizzled [128 x 32] staging panel and one thread issues a TMA store; the residual arrives the
+//              same way (TMA load into the staging panel, prefetched two panels ahead, across tile boundaries).
 //              fp32 / unaligned outputs take the direct (row-per-thread, 16-byte) global path.
+//
+// CTAS = 2 (cta_group::2): two CTAs of a cluster (one TPC) compute a 256 x BN tile.  Each CTA loads its own 128 rows
+// of A and HALF of the B tile; the leader CTA issues tcgen05.mma.cta_group::2, which reads B from both CTAs' shared
+// memory and writes each CTA's 128 accumulator rows into that CTA's TMEM.  This halves the B bytes every SM pulls
+// from L2 and reads from shared memory per MMA -- the single-CTA 128 x 160 tile is shared-memory-bandwidth bound.
+// TMA loads of both CTAs complete on the leader's "full" barrier; tcgen05.commit multicasts "empty" / "accumulator
+// ready" to both CTAs; the peer's epilogue warps release the accumulator with a remote mbarrier arrive.
 #include "tc_ptx.cuh"
 #include "../../include/saspa_b200.h"
 
@@ -75,12 +82,12 @@ struct GemmParams {
 
 using namespace tcx;
 
-template <int BN>
+template <int BN, int CTAS>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2 / CTAS;  // per CTA: its share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // staging panels per epilogue group: 4 (residual prefetch distance 2) unless the operand ring needs the room
-  static constexpr int NBUF = BN > 160 ? 2 : 4;
+  static constexpr int NBUF = (BN > 160 && CTAS == 1) ? 2 : 4;
   static constexpr int PD = NBUF / 2;
   static constexpr int STAGING_BYTES = 2 * NBUF * PANEL_BYTES;
   static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
@@ -91,6 +98,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512;
   static_assert(STAGES >= 3 && HB_STAGES >= 4, "operand ring too shallow");
   static_assert(BN % PANEL == 0, "BN must be a multiple of the staging panel width");
+  static_assert((BN / CTAS) % 8 == 0, "each CTA's B share must be whole 8-row core matrices");
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -120,12 +128,79 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <int BN>
+// ---- operand loads / MMA / commit, one- and two-CTA flavours.  `bar` is a shared::cluster address: the CTA's own
+// barrier for CTAS == 1, the leader CTA's barrier (mapa rank 0) for CTAS == 2. ----
+template <int CTAS>
+__device__ __forceinline__ void op_load_2d(const CUtensorMap* tm, void* dst, uint32_t bar, int c0, int c1) {
+  if constexpr (CTAS == 1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void op_load_4d(const CUtensorMap* tm, void* dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+  if constexpr (CTAS == 1) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void op_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CTAS == 1) {
+    tc_mma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrives (once the MMAs issued so far have completed) on `bar` of this CTA and, for CTAS == 2, of the peer CTA too
+template <int CTAS>
+__device__ __forceinline__ void op_commit(uint64_t* bar) {
+  if constexpr (CTAS == 1) {
+    tc_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                    const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   constexpr int STAGES = C::STAGES;
   constexpr int NBUF = C::NBUF;
   constexpr int PD = C::PD;
@@ -138,19 +213,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint8_t* sBh = smem + HALO_STAGES * HALO_STAGE_BYTES;     // ... then HB_STAGES weight k-blocks
   uint8_t* sStage = smem + C::RING_BYTES;                   // 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + C::STAGING_BYTES);
-  uint64_t* full = bars;         // [8]
+  uint64_t* full = bars;         // [8]   (CTAS == 2: only the leader's are waited on)
   uint64_t* empty = bars + 8;    // [8]
   uint64_t* afull = bars + 16;   // [HALO_STAGES]
   uint64_t* aempty = bars + 18;  // [HALO_STAGES]
   uint64_t* tfull = bars + 20;
-  uint64_t* tempty = bars + 22;
-  uint64_t* rfull = bars + 24;  // [2 groups][NBUF]
+  uint64_t* tempty = bars + 22;  // (CTAS == 2: only the leader's are waited on)
+  uint64_t* rfull = bars + 24;   // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  uint32_t rank = 0;
+  if constexpr (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool is_leader = rank == 0;
+  // persistent schedule over (group of CTAS m-tiles, n-tile); both CTAs of a pair walk the same sequence
+  const int num_clusters = gridDim.x / CTAS, cid = blockIdx.x / CTAS;
+  const int total_tiles = ((p.num_m_tiles + CTAS - 1) / CTAS) * p.num_n_tiles;
   const int cchunks = (p.mode != 0) ? (p.c0 + p.c1 + BK - 1) / BK : 0;
   const int num_kb = (p.mode != 0) ? p.ksize * p.ksize * cchunks : (p.K + BK - 1) / BK;
+  auto tile_m = [&](int tile) { return (tile / p.num_n_tiles) * CTAS + (int)rank; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -170,46 +251,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], EPI_WARPS);
+      mbar_init(&tempty[a], EPI_WARPS * CTAS);
     }
     for (int i = 0; i < 2 * NBUF; ++i) mbar_init(&rfull[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (each CTA fills its own smem; completion lands on the leader's barrier) =====================
+    const int b_rows = BN / CTAS;  // this CTA's share of the B tile
     if (lane == 0 && p.mode == 2) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int ctot = p.c0 + p.c1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      for (int tile = cid; tile < total_tiles; tile += num_clusters) {
+        const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
         const int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
         const int ty = r % p.tiles_y, tn = r / p.tiles_y;
         for (int cc = 0; cc < cchunks; ++cc) {
           const int c = cc * BK;
           mbar_wait(&aempty[sa], pa ^ 1);
-          mbar_expect_tx(&afull[sa], HALO_TX_BYTES);
+          if (is_leader) mbar_expect_tx(&afull[sa], HALO_TX_BYTES * CTAS);
+          const uint32_t abar = (CTAS == 2) ? mapa_rank(smem_u32(&afull[sa]), 0) : smem_u32(&afull[sa]);
           if (c < p.c0)
-            tma_load_4d(&tmA0, sHalo + sa * HALO_STAGE_BYTES, &afull[sa], c, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+            op_load_4d<CTAS>(&tmA0, sHalo + sa * HALO_STAGE_BYTES, abar, c, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
           else
-            tma_load_4d(&tmA1, sHalo + sa * HALO_STAGE_BYTES, &afull[sa], c - p.c0, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+            op_load_4d<CTAS>(&tmA1, sHalo + sa * HALO_STAGE_BYTES, abar, c - p.c0, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
           if (++sa == HALO_STAGES) {
             sa = 0;
             pa ^= 1;
           }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&empty[sb], pb ^ 1);
-            mbar_expect_tx(&full[sb], C::B_BYTES);
-            tma_load_2d(&tmB, sBh + sb * C::B_BYTES, &full[sb], tap * ctot + c, n_blk * BN);
+            if (is_leader) mbar_expect_tx(&full[sb], C::B_BYTES * CTAS);
+            const uint32_t bbar = (CTAS == 2) ? mapa_rank(smem_u32(&full[sb]), 0) : smem_u32(&full[sb]);
+            op_load_2d<CTAS>(&tmB, sBh + sb * C::B_BYTES, bbar, tap * ctot + c, n_blk * BN + (int)rank * b_rows);
             if (++sb == C::HB_STAGES) {
               sb = 0;
               pb ^= 1;
@@ -220,8 +310,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      for (int tile = cid; tile < total_tiles; tile += num_clusters) {
+        const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
         int x0 = 0, y0 = 0, n0 = 0;
         if (p.mode == 1) {
           int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
@@ -233,24 +323,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int pad = p.ksize >> 1;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (is_leader) mbar_expect_tx(&full[stage], C::STAGE_BYTES * CTAS);
+          const uint32_t fbar = (CTAS == 2) ? mapa_rank(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
           uint8_t* a_dst = sA + stage * A_BYTES;
           uint8_t* b_dst = sB + stage * C::B_BYTES;
           int kB;
           if (p.mode == 0) {
             kB = kb * BK;
-            tma_load_2d(&tmA0, a_dst, &full[stage], kB, m_blk * BM);
+            op_load_2d<CTAS>(&tmA0, a_dst, fbar, kB, m_blk * BM);
           } else {
             int tap = kb / cchunks, cc = kb - tap * cchunks;
             int ky = tap / p.ksize, kx = tap - ky * p.ksize;
             int c = cc * BK;
             kB = tap * (p.c0 + p.c1) + c;
             if (c < p.c0)
-              tma_load_4d(&tmA0, a_dst, &full[stage], c, x0 + kx - pad, y0 + ky - pad, n0);
+              op_load_4d<CTAS>(&tmA0, a_dst, fbar, c, x0 + kx - pad, y0 + ky - pad, n0);
             else
-              tma_load_4d(&tmA1, a_dst, &full[stage], c - p.c0, x0 + kx - pad, y0 + ky - pad, n0);
+              op_load_4d<CTAS>(&tmA1, a_dst, fbar, c - p.c0, x0 + kx - pad, y0 + ky - pad, n0);
           }
-          tma_load_2d(&tmB, b_dst, &full[stage], kB, n_blk * BN);
+          op_load_2d<CTAS>(&tmB, b_dst, fbar, kB, n_blk * BN + (int)rank * b_rows);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -259,13 +350,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && p.mode == 2) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
+    if (lane == 0 && is_leader && p.mode == 2) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cid; tile < total_tiles; tile += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -282,32 +373,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const int ky = tap / 3, kx = tap - 3 * ky;
             // output pixel (ly, lx) reads halo pixel (ly + ky, lx + kx): a row shift inside the halo tile.  Each
             // 8-row core-matrix group is one image row of the tile (8 px x 128 B contiguous); groups are one halo
-            // row ((HALO_BW + 2) x 128 B) apart.  The 128B swizzle is a function of the absolute smem address, so
-            // row-shifted start addresses read back exactly what TMA wrote.
+            // row ((HALO_BW + 2) x 128 B) apart.
             const uint64_t a_desc = make_smem_desc_sbo(halo + (ky * (HALO_BW + 2) + kx) * 128, (HALO_BW + 2) * 128);
             const uint64_t b_desc = make_smem_desc(smem_u32(sBh + sb * C::B_BYTES));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
-            tc_commit(&empty[sb]);
+            for (int k = 0; k < BK / 16; ++k) op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+            op_commit<CTAS>(&empty[sb]);
             if (++sb == C::HB_STAGES) {
               sb = 0;
               pb ^= 1;
             }
           }
-          tc_commit(&aempty[sa]);
+          op_commit<CTAS>(&aempty[sa]);
           if (++sa == HALO_STAGES) {
             sa = 0;
             pa ^= 1;
           }
         }
-        tc_commit(&tfull[acc]);
+        op_commit<CTAS>(&tfull[acc]);
       }
-    } else if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    } else if (lane == 0 && is_leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cid; tile < total_tiles; tile += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -321,15 +410,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128B swizzle atom = +2 in the 16-byte start-address field
-            tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);
+          op_commit<CTAS>(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull[acc]);
+        op_commit<CTAS>(&tfull[acc]);
       }
     }
   } else {
@@ -354,7 +443,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       for (;;) {
         k += 2;
         if (k >= NP) {
-          tile += gridDim.x;
+          tile += num_clusters;
           k = grp;
           if (tile >= total_tiles) return;
         }
@@ -362,7 +451,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     };
     auto panel_coords = [&](int tile, int k, int& col, int& c1, int& c2, int& c3) {
-      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
       col = n_blk * out_bn + k * PANEL;
       if (p.mode == 0) {
         c1 = m_blk * BM;
@@ -386,7 +475,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     };
 
     // residual prefetch state (leader only)
-    int pf_tile = blockIdx.x, pf_k = grp - 2, pf_n = 0;
+    int pf_tile = cid, pf_k = grp - 2, pf_n = 0;
     if (tma_res && leader) {
       panel_next(pf_tile, pf_k);
       for (int i = 0; i < PD && pf_tile < total_tiles; ++i) {
@@ -398,10 +487,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
     int n_seq = 0;  // panels processed by this group so far
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cid; tile < total_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
       long long pix;
       bool row_ok;
       int group;
@@ -417,7 +506,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         int x = tx * p.bw + lx, y = ty * p.bh + ly, n = tn * p.bn + ln;
         row_ok = (x < p.W) && (y < p.H) && (n < p.n_img);
         pix = ((long long)n * p.H + y) * p.W + x;
-        group = n;
+        group = row_ok ? n : 0;
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -594,16 +683,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (CTAS == 1) {
+          mbar_arrive(&tempty[acc]);
+        } else {
+          mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));  // the MMA issuer lives in the leader CTA
+        }
+      }
     }
     if (use_tma && leader) bulk_wait_read<0>();  // staging panels must outlive the stores that read them
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // neither CTA may exit while the pair's MMAs / commits can still touch it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CTAS == 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
   }
 }
 
@@ -670,18 +770,31 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, l
   return SASPA_OK;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r, const GemmParams& p,
            cudaStream_t stream) {
+  using C = Cfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    SASPA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    SASPA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  int total = p.num_m_tiles * p.num_n_tiles;
-  int grid = total < saspa_num_sms() ? total : saspa_num_sms();
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a0, a1, b, d, r, p);
-  SASPA_LAUNCH_CHECK();
+  const int total = ceil_div(p.num_m_tiles, CTAS) * p.num_n_tiles;  // tiles of CTAS x 128 rows
+  const int max_clusters = saspa_num_sms() / CTAS;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CTAS, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SASPA_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, a0, a1, b, d, r, p));
   return SASPA_OK;
 }
 
@@ -689,39 +802,58 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 // ResNets are powers of two; GEGLU needs value|gate halves in one tile (256 = 128 + 128).
 int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 
-int pick_bn(int N, int act) {
-  if (act == SASPA_ACT_GEGLU) return 256;
+// Tile width along N.  Measured per-tile main-loop time relative to BN = 256 (same K): 0.72 for BN <= 128, 0.80 for
+// BN = 160 (profiles/r1_bn_sweep.txt) -- so the widest tile wins unless it pads columns (320 = 2 x 160) or leaves
+// SMs idle in the last wave (small-M problems).  cost = waves x per-tile time.
+int pick_bn(int N, int act, int num_m_tiles) {
+  if (act == SASPA_ACT_GEGLU) return 256;  // value | gate halves in one tile
   if (g_force_bn) return g_force_bn;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N % 160 == 0 && N % 256 != 0) return 160;
-  if (N <= 128) return 128;
-  if (N % 256 == 0) return 256;
-  if (N % 128 == 0) return 128;
-  // general: minimise padded columns, prefer the wider tile
-  int best = 256, best_waste = (ceil_div(N, 256) * 256 - N);
-  const int cands[3] = {160, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    int waste = ceil_div(N, cands[i]) * cands[i] - N;
-    if (waste < best_waste) {
+  const int cands[4] = {256, 160, 128, 64};
+  const double t_rel[4] = {1.0, 0.80, 0.72, 0.72};
+  const int sms = saspa_num_sms();
+  int best = 256;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const long long tiles = (long long)num_m_tiles * ceil_div(N, cands[i]);
+    // whole waves while the problem is small; the persistent schedule averages out once there are many
+    const double waves = tiles <= 4LL * sms ? (double)ceil_div_ll(tiles, sms) : (double)tiles / sms;
+    const double cost = waves * t_rel[i];
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
       best = cands[i];
-      best_waste = waste;
     }
   }
   return best;
 }
 
-int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r,
-             const GemmParams& p, cudaStream_t stream) {
+int g_force_ctas = 0;  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
+
+// Two-CTA tiles (cta_group::2, 256 x BN): measured +7% at BN = 256 on the plain GEMM main loop, a loss for narrower
+// tiles and for the halo conv (profiles/r1_bn_sweep.txt), so only the widest GEMM tiles pair up.
+int pick_ctas(int num_m_tiles, int bn, int mode) {
+  if (g_force_ctas) return num_m_tiles >= 2 || g_force_ctas == 1 ? g_force_ctas : 1;
+  return (bn == 256 && mode == 0 && num_m_tiles >= 2) ? 2 : 1;
+}
+
+template <int CTAS>
+int dispatch_bn(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r,
+                const GemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 32: return launch<32>(a0, a1, b, d, r, p, stream);
-    case 64: return launch<64>(a0, a1, b, d, r, p, stream);
-    case 128: return launch<128>(a0, a1, b, d, r, p, stream);
-    case 160: return launch<160>(a0, a1, b, d, r, p, stream);
-    case 256: return launch<256>(a0, a1, b, d, r, p, stream);
+    case 32: return launch<32, CTAS>(a0, a1, b, d, r, p, stream);
+    case 64: return launch<64, CTAS>(a0, a1, b, d, r, p, stream);
+    case 128: return launch<128, CTAS>(a0, a1, b, d, r, p, stream);
+    case 160: return launch<160, CTAS>(a0, a1, b, d, r, p, stream);
+    case 256: return launch<256, CTAS>(a0, a1, b, d, r, p, stream);
   }
   saspa_set_error("internal: no kernel for BN=%d", bn);
   return SASPA_ERR_UNSUPPORTED;
+}
+
+int dispatch(int bn, int ctas, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d, const CUtensorMap& r,
+             const GemmParams& p, cudaStream_t stream) {
+  return ctas == 2 ? dispatch_bn<2>(bn, a0, a1, b, d, r, p, stream) : dispatch_bn<1>(bn, a0, a1, b, d, r, p, stream);
 }
 
 int g_conv_impl = 0;  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
@@ -777,22 +909,23 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, N, D, ldd);
   if (rc) return rc;
-  const int bn = pick_bn(N, p.act);
   p.M = M;
   p.N = N;
   p.K = K;
   p.mode = 0;
   p.num_m_tiles = ceil_div(M, BM);
+  const int bn = pick_bn(N, p.act, p.num_m_tiles);
   p.num_n_tiles = ceil_div(N, bn);
   CUtensorMap tmA, tmB;
   if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
-  if ((rc = encode_2d(&tmB, B, N, K, ldb, bn))) return rc;
+  const int ctas = pick_ctas(p.num_m_tiles, bn, 0);
+  if ((rc = encode_2d(&tmB, B, N, K, ldb, bn / ctas))) return rc;  // each CTA of a pair loads its share of the B tile
   CUtensorMap tmD = tmA, tmR = tmA;
   if (p.tma_store) {
     if ((rc = encode_2d(&tmD, D, M, p.n_out, ldd, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (p.residual && (rc = encode_2d(&tmR, p.residual, M, p.n_out, p.ld_res, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
-  return dispatch(bn, tmA, tmA, tmB, tmD, tmR, p, stream);
+  return dispatch(bn, ctas, tmA, tmA, tmB, tmD, tmR, p, stream);
 }
 
 extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int h, int w,
@@ -812,7 +945,6 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, cout, out, ldo);
   if (rc) return rc;
-  const int bn_tile = pick_bn(cout, p.act);
   // M tile = bw x bh x bnimg = 128 output pixels; minimise padded work, tie-break towards square tiles.
   int best_bw = 0, best_bh = 0, best_bi = 0;
   long long best_cost = -1;
@@ -861,6 +993,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   p.tiles_y = ceil_div(h, p.bh);
   const int tiles_n = ceil_div(n, p.bn);
   p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+  const int bn_tile = pick_bn(cout, p.act, p.num_m_tiles);
   p.num_n_tiles = ceil_div(cout, bn_tile);
   p.N = cout;
   p.K = ksize * ksize * (c0 + c1);
@@ -873,14 +1006,15 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   } else {
     tmA1 = tmA0;
   }
-  if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile))) return rc;
+  const int ctas = pick_ctas(p.num_m_tiles, bn_tile, p.mode);
+  if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile / ctas))) return rc;
   CUtensorMap tmD = tmA0, tmR = tmA0;
   if (p.tma_store) {
     if ((rc = encode_nhwc(&tmD, out, n, h, w, p.n_out, ldo, p.bn, p.bh, p.bw, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (p.residual && (rc = encode_nhwc(&tmR, p.residual, n, h, w, p.n_out, p.ld_res, p.bn, p.bh, p.bw, PANEL, CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
   }
-  return dispatch(bn_tile, tmA0, tmA1, tmB, tmD, tmR, p, stream);
+  return dispatch(bn_tile, ctas, tmA0, tmA1, tmB, tmD, tmR, p, stream);
 }
 
 extern "C" int saspa_conv_impl(int impl) {
@@ -893,5 +1027,12 @@ extern "C" int saspa_conv_impl(int impl) {
 extern "C" int saspa_gemm_force_bn(int bn) {
   const int prev = g_force_bn;
   if (bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256) g_force_bn = bn;
+  return prev;
+}
+
+// Tuning hook: force one- or two-CTA tiles (0 restores the heuristic).  Not part of the product API.
+extern "C" int saspa_gemm_force_ctas(int ctas) {
+  const int prev = g_force_ctas;
+  if (ctas >= 0 && ctas <= 2) g_force_ctas = ctas;
   return prev;
 }

@@ -177,6 +177,21 @@ __device__ __forceinline__ void tc_ld32p(uint32_t taddr, uint32_t* r) {
       : TCX_R16(r, 0), TCX_R16(r, 16)
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+}
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + r via the 1.5 * 2^23 magic constant, cubic minimax for
+// 2^r on [-0.5, 0.5] (relative error 7.5e-5), exponent spliced in with one integer add.  x is clamped at -125 (the
+// cubic's exponent field may be 126, and 126 - 125 must stay positive), i.e. masked / far-away keys weigh ~2e-38.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(r, 0.0551716648f, 0.2426111251f);
+  p = fmaf(p, r, 0.6932609677f);
+  p = fmaf(p, r, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

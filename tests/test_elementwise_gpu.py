@@ -24,10 +24,20 @@ def _close(got, ref, atol, rtol=1e-2):
     assert not bad.any(), f"max err {err.max().item():.4g} at {int(bad.sum())} elements"
 
 
-@pytest.mark.parametrize("cfg", [(2, 4096, 320, 1e-5), (3, 1024, 640, 1e-5), (2, 256, 1280, 1e-6), (2, 64, 2560, 1e-5), (2, 1024, 1920, 1e-5),
+@pytest.fixture(params=[0, 1], ids=["gn-auto-registers", "gn-two-pass"])
+def gn_impl(request):
+    """Runs a GroupNorm test once per kernel (saspa_groupnorm_impl: 0 = auto / register-resident where eligible, 1 = two-pass)."""
+    from saspa_aug_b200 import _lib
+
+    prev = _lib.load().saspa_groupnorm_impl(request.param)
+    yield request.param
+    _lib.load().saspa_groupnorm_impl(prev)
+
+
+@pytest.mark.parametrize("cfg", [(2, 5632, 320, 1e-5), (3, 200, 1280, 1e-5), (2, 4096, 320, 1e-5), (3, 1024, 640, 1e-5), (2, 256, 1280, 1e-6), (2, 64, 2560, 1e-5), (2, 1024, 1920, 1e-5),
                                  (2, 1024, 960, 1e-5), (1, 16384, 128, 1e-6), (5, 77, 512, 1e-6), (2, 100, 256, 1e-6)])
 @pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_SILU])
-def test_groupnorm(cuda_device, cfg, act):
+def test_groupnorm(cuda_device, gn_impl, cfg, act):
     n, hw, c, eps = cfg
     x = _rand((n, hw, c), 1, 2.0, 0.7)
     gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
@@ -38,7 +48,7 @@ def test_groupnorm(cuda_device, cfg, act):
     _close(got, ref.permute(0, 2, 1), 2e-2)
 
 
-def test_groupnorm_is_batch_invariant_and_repeatable(cuda_device):
+def test_groupnorm_is_batch_invariant_and_repeatable(cuda_device, gn_impl):
     """Fixed-order reductions: an image's result must not depend on which images share the launch (the sharded driver
     regroups micro-batches) nor change between runs."""
     x = _rand((7, 1024, 640), 9, 2.0, 0.3)
@@ -53,7 +63,7 @@ def test_groupnorm_is_batch_invariant_and_repeatable(cuda_device):
     assert torch.equal(pair, full[2:4])
 
 
-def test_groupnorm_strided_into_concat_buffer(cuda_device):
+def test_groupnorm_strided_into_concat_buffer(cuda_device, gn_impl):
     n, hw, c = 2, 256, 640
     buf = _rand((n, hw, 1920), 2)
     x = buf[:, :, 1280:]

@@ -73,6 +73,16 @@ def test_gemm_geglu(cuda_device):
     _check(got, ref)
 
 
+@pytest.fixture(params=[0, 1], ids=["ctas-auto-pair", "ctas-single"], autouse=True)
+def gemm_ctas(request):
+    """Every test of this file runs with two-CTA (cta_group::2) tiles where eligible and with single-CTA tiles only."""
+    from saspa_aug_b200 import _lib
+
+    prev = _lib.load().saspa_gemm_force_ctas(request.param)
+    yield request.param
+    _lib.load().saspa_gemm_force_ctas(prev)
+
+
 @pytest.fixture(params=[0, 1], ids=["conv-auto-halo", "conv-per-tap"])
 def conv_impl(request):
     """Runs a conv test once per 3x3 main loop (saspa_conv_impl: 0 = auto / halo tile where eligible, 1 = one TMA box per tap)."""

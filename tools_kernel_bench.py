@@ -115,9 +115,15 @@ def hbm(B):
         x = rnd(n, hw, c)
         out = torch.empty_like(x)
         g, bt = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
-        ms = timeit(lambda: ops.groupnorm(x, 32, 1e-5, g, bt, ops.ACT_SILU, out=out))
-        gb = 2.0 * x.numel() * 2 / ms / 1e6  # algorithmic: read once + write once
-        print(f"groupnorm+silu {n}x{hw}x{c}: {ms:.3f} ms {gb:.0f} GB/s algorithmic ({gb / PEAKS['hbm_gbs']:.2f})")
+        from saspa_aug_b200 import _lib
+        res = []
+        for impl in (1, 0):
+            _lib.load().saspa_groupnorm_impl(impl)
+            ms = timeit(lambda: ops.groupnorm(x, 32, 1e-5, g, bt, ops.ACT_SILU, out=out))
+            res.append((ms, 2.0 * x.numel() * 2 / ms / 1e6))  # algorithmic: read once + write once
+        _lib.load().saspa_groupnorm_impl(0)
+        print(f"groupnorm+silu {n}x{hw}x{c}: two-pass {res[0][0]:.3f} ms {res[0][1]:.0f} GB/s | auto {res[1][0]:.3f} ms {res[1][1]:.0f} GB/s algorithmic "
+              f"({res[1][1] / PEAKS['hbm_gbs']:.2f} of HBM peak)")
     for rows_, c in [(B * 4096, 320), (B * 1024, 640), (B * 256, 1280), (B * 77, 768)]:
         x = rnd(rows_, c)
         out = torch.empty_like(x)
