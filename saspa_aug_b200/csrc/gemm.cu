@@ -90,12 +90,12 @@ struct Cfg {
   static constexpr int NBUF = (BN > 160 && CTAS == 1) ? 2 : 4;
   static constexpr int PD = NBUF / 2;
   static constexpr int STAGING_BYTES = 2 * NBUF * PANEL_BYTES;
-  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/ - 2048 /*bias*/;
   static constexpr int RING_BYTES = RING_BUDGET / 1024 * 1024;
   static constexpr int STAGES = (RING_BYTES / STAGE_BYTES) > 8 ? 8 : (RING_BYTES / STAGE_BYTES);
   // halo mode (3x3 conv): 2 halo stages of the activation + a ring of weight k-blocks
   static constexpr int HB_STAGES = ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES) > 8 ? 8 : ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES);
-  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512 + 2048;
   static_assert(STAGES >= 3 && HB_STAGES >= 4, "operand ring too shallow");
   static_assert(BN % PANEL == 0, "BN must be a multiple of the staging panel width");
   static_assert((BN / CTAS) % 8 == 0, "each CTA's B share must be whole 8-row core matrices");
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tempty = bars + 22;  // (CTAS == 2: only the leader's are waited on)
   uint64_t* rfull = bars + 24;   // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
+  float* sBias = reinterpret_cast<float*>(bars) + 128;  // [2][256]: the tile's bias slice, staged once per tile (512 B past the barriers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank = 0;
@@ -508,11 +509,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         pix = ((long long)n * p.H + y) * p.W + x;
         group = row_ok ? n : 0;
       }
+      const int col_base_in = n_blk * BN;       // column in the (interleaved) weight / bias space
+      const int col_base_out = n_blk * out_bn;  // column in the output
+      // the bias slice of this tile goes through shared memory: its global-load latency is paid once per tile, off the
+      // accumulator-drain path (it used to stall every panel).  Two buffers: nobody runs more than a tile ahead.
+      float* sb = sBias + (it & 1) * 256;
+      if (p.bias) {
+        const int t = (int)threadIdx.x - 64;
+        if (t < BN) sb[t] = (col_base_in + t < p.N) ? __ldg(p.bias + col_base_in + t) : 0.0f;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
-      const int col_base_in = n_blk * BN;       // column in the (interleaved) weight / bias space
-      const int col_base_out = n_blk * out_bn;  // column in the output
 #pragma unroll 1
       for (int k = grp; k < NP; k += 2) {
         const int c0 = k * PANEL;
@@ -529,22 +538,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            int n = col_base_in + c0 + j;
-            if (n + 3 < p.N) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            } else {
-              for (int e = 0; e < 4; ++e)
-                if (n + e < p.N) f[j + e] += __ldg(p.bias + n + e);
-            }
+            const float4 b = *reinterpret_cast<const float4*>(sb + c0 + j);
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
         }
         if (geglu) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            int n = col_base_in + BN / 2 + c0 + j;
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));  // N % 256 == 0 for GEGLU
+            if (p.bias) b = *reinterpret_cast<const float4*>(sb + BN / 2 + c0 + j);
             f[j] *= gelu_erf_f(__uint_as_float(gt[j]) + b.x);
             f[j + 1] *= gelu_erf_f(__uint_as_float(gt[j + 1]) + b.y);
             f[j + 2] *= gelu_erf_f(__uint_as_float(gt[j + 2]) + b.z);
@@ -802,27 +804,45 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 // ResNets are powers of two; GEGLU needs value|gate halves in one tile (256 = 128 + 128).
 int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 
-// Tile width along N.  Measured per-tile main-loop time relative to BN = 256 (same K): 0.72 for BN <= 128, 0.80 for
-// BN = 160 (profiles/r1_bn_sweep.txt) -- so the widest tile wins unless it pads columns (320 = 2 x 160) or leaves
-// SMs idle in the last wave (small-M problems).  cost = waves x per-tile time.
-int pick_bn(int N, int act, int num_m_tiles) {
+// Tile width along N.
+//  * main-loop-bound problems (convs, K >= 2048): measured per-tile time relative to BN = 256 is 0.72 for BN <= 128 and
+//    0.80 for BN = 160 (profiles/r1_bn_sweep.txt), so cost = waves x per-tile time decides -- the widest tile unless it
+//    pads columns or leaves SMs idle in the last wave of a small-M problem;
+//  * short-K GEMMs are bound by the epilogue / stores, where padded columns cost real time: exact tilings first
+//    (SD channel counts are multiples of 320 -> 160; powers of two -> 256 / 128).
+int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound) {
   if (act == SASPA_ACT_GEGLU) return 256;  // value | gate halves in one tile
   if (g_force_bn) return g_force_bn;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  const int cands[4] = {256, 160, 128, 64};
-  const double t_rel[4] = {1.0, 0.80, 0.72, 0.72};
-  const int sms = saspa_num_sms();
-  int best = 256;
-  double best_cost = 1e30;
-  for (int i = 0; i < 4; ++i) {
-    const long long tiles = (long long)num_m_tiles * ceil_div(N, cands[i]);
-    // whole waves while the problem is small; the persistent schedule averages out once there are many
-    const double waves = tiles <= 4LL * sms ? (double)ceil_div_ll(tiles, sms) : (double)tiles / sms;
-    const double cost = waves * t_rel[i];
-    if (cost < best_cost * 0.999) {
-      best_cost = cost;
+  if (mainloop_bound) {
+    const int cands[4] = {256, 160, 128, 64};
+    const double t_rel[4] = {1.0, 0.80, 0.72, 0.72};
+    const int sms = saspa_num_sms();
+    int best = 256;
+    double best_cost = 1e30;
+    for (int i = 0; i < 4; ++i) {
+      const long long tiles = (long long)num_m_tiles * ceil_div(N, cands[i]);
+      const double waves = tiles <= 4LL * sms ? (double)ceil_div_ll(tiles, sms) : (double)tiles / sms;
+      const double cost = waves * t_rel[i];
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        best = cands[i];
+      }
+    }
+    return best;
+  }
+  if (N % 160 == 0 && N % 256 != 0) return 160;
+  if (N <= 128) return 128;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  int best = 256, best_waste = (ceil_div(N, 256) * 256 - N);
+  const int cands[3] = {160, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int waste = ceil_div(N, cands[i]) * cands[i] - N;
+    if (waste < best_waste) {
       best = cands[i];
+      best_waste = waste;
     }
   }
   return best;
@@ -831,10 +851,11 @@ int pick_bn(int N, int act, int num_m_tiles) {
 int g_force_ctas = 0;  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
 
 // Two-CTA tiles (cta_group::2, 256 x BN): measured +7% at BN = 256 on the plain GEMM main loop, a loss for narrower
-// tiles and for the halo conv (profiles/r1_bn_sweep.txt), so only the widest GEMM tiles pair up.
-int pick_ctas(int num_m_tiles, int bn, int mode) {
+// tiles and for the halo conv (profiles/r1_bn_sweep.txt), so only the widest long-K GEMM tiles pair up.
+int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K) {
   if (g_force_ctas) return num_m_tiles >= 2 || g_force_ctas == 1 ? g_force_ctas : 1;
-  return (bn == 256 && mode == 0 && num_m_tiles >= 2) ? 2 : 1;
+  // epilogue-bound launches (GEGLU, short K) lose from coupling two CTAs (measured 325 -> 381 us on the 64x64 GEGLU GEMM)
+  return (bn == 256 && mode == 0 && act != SASPA_ACT_GEGLU && K >= 1024 && num_m_tiles >= 2) ? 2 : 1;
 }
 
 template <int CTAS>
@@ -914,11 +935,11 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   p.K = K;
   p.mode = 0;
   p.num_m_tiles = ceil_div(M, BM);
-  const int bn = pick_bn(N, p.act, p.num_m_tiles);
+  const int bn = pick_bn(N, p.act, p.num_m_tiles, K >= 2048);
   p.num_n_tiles = ceil_div(N, bn);
   CUtensorMap tmA, tmB;
   if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
-  const int ctas = pick_ctas(p.num_m_tiles, bn, 0);
+  const int ctas = pick_ctas(p.num_m_tiles, bn, 0, p.act, K);
   if ((rc = encode_2d(&tmB, B, N, K, ldb, bn / ctas))) return rc;  // each CTA of a pair loads its share of the B tile
   CUtensorMap tmD = tmA, tmR = tmA;
   if (p.tma_store) {
@@ -993,7 +1014,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   p.tiles_y = ceil_div(h, p.bh);
   const int tiles_n = ceil_div(n, p.bn);
   p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
-  const int bn_tile = pick_bn(cout, p.act, p.num_m_tiles);
+  const int bn_tile = pick_bn(cout, p.act, p.num_m_tiles, ksize == 3 || c0 + c1 >= 2048);
   p.num_n_tiles = ceil_div(cout, bn_tile);
   p.N = cout;
   p.K = ksize * ksize * (c0 + c1);
@@ -1006,7 +1027,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   } else {
     tmA1 = tmA0;
   }
-  const int ctas = pick_ctas(p.num_m_tiles, bn_tile, p.mode);
+  const int ctas = pick_ctas(p.num_m_tiles, bn_tile, p.mode, p.act, p.K);
   if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile / ctas))) return rc;
   CUtensorMap tmD = tmA0, tmR = tmA0;
   if (p.tma_store) {
