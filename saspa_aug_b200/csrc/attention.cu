@@ -236,6 +236,183 @@ int launch_flash(const void* q, int ldq, const void* k, int ldk, const void* v, 
   return SASPA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-attention over a SHORT key sequence (tkv <= 128: the 77 text tokens), non-causal.
+// The work is HBM-bound (read Q, write O; 4*tq*77*d FLOP is nothing), and the per-CTA fixed cost dominated the
+// generic kernels (one CTA per 64 / 256 queries re-staging K and V).  Here K and V of one (batch, head) are staged in
+// shared memory ONCE per CTA (padded to 80 or 128 keys) and the CTA then streams `qt_per_cta` consecutive 64-query tiles
+// through them: Q tiles double-buffered with cp.async, the whole score row / one-pass softmax / P V in registers
+// (mma.sync m16n8k16, 16 query rows per warp), O staged through the consumed Q buffer so it leaves as 16-byte
+// row-contiguous stores.
+// ------------------------------------------------------------------------------------------------
+template <int DP, int NK16>  // NK16 = key groups of 16 held resident (5 -> up to 80 keys: the 77 text tokens; 8 -> up to 128)
+__global__ void __launch_bounds__(ATT_THREADS) xattn_resident_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k,
+                                                                      int ldk, const __nv_bfloat16* __restrict__ v, int ldv,
+                                                                      __nv_bfloat16* __restrict__ o, int ldo, int heads, int tq, int tkv, int d,
+                                                                      float scale_log2, int qt_per_cta) {
+  constexpr int ROWB = DP * 2 + 16;
+  constexpr int KS = DP / 16;
+  constexpr int NT = DP / 8;
+  constexpr int NKEY = NK16 * 16;
+  constexpr int CH = DP / 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  uint8_t* sQ = att_smem;                  // 2 buffers of 64 rows
+  uint8_t* sK = att_smem + 2 * 64 * ROWB;  // NKEY rows (keys >= tkv zero-filled)
+  uint8_t* sV = sK + NKEY * ROWB;          // NKEY rows
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
+  const int n_qt = (tq + BQ - 1) / BQ;
+  const int qt0 = blockIdx.x * qt_per_cta, qt1 = min(qt0 + qt_per_cta, n_qt);
+  const __nv_bfloat16* qg = q + ((long long)b * tq) * ldq + (long long)h * d;
+  const __nv_bfloat16* kg = k + ((long long)b * tkv) * ldk + (long long)h * d;
+  const __nv_bfloat16* vg = v + ((long long)b * tkv) * ldv + (long long)h * d;
+  __nv_bfloat16* og = o + ((long long)b * tq) * ldo + (long long)h * d;
+
+  for (int i = tid; i < NKEY * CH; i += ATT_THREADS) {
+    const int r = i / CH, c = i % CH;
+    const bool ok = (r < tkv) && (c * 8 < d);
+    cp_async16(sK + r * ROWB + c * 16, ok ? kg + (long long)r * ldk + c * 8 : kg, ok);
+    cp_async16(sV + r * ROWB + c * 16, ok ? vg + (long long)r * ldv + c * 8 : vg, ok);
+  }
+  load_tile<DP>(reinterpret_cast<__nv_bfloat16*>(sQ), qg + (long long)qt0 * BQ * ldq, ldq, min(BQ, tq - qt0 * BQ), d, tid);
+  cp_async_commit();
+
+  for (int qt = qt0; qt < qt1; ++qt) {
+    const int buf = (qt - qt0) & 1;
+    const int q0 = qt * BQ;
+    if (qt + 1 < qt1) {
+      load_tile<DP>(reinterpret_cast<__nv_bfloat16*>(sQ + (buf ^ 1) * 64 * ROWB), qg + (long long)(q0 + BQ) * ldq, ldq, min(BQ, tq - q0 - BQ), d, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint8_t* qb = sQ + buf * 64 * ROWB;
+    uint32_t qf[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      int col = ks * 16 + (lane >> 4) * 8;
+      ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], qb + row * ROWB + col * 2);
+    }
+    // ---- S = Q K^T over all resident keys (16 x NKEY per warp), one softmax pass, no running rescale ----
+    float sacc[NK16 * 2][4];
+#pragma unroll
+    for (int i = 0; i < NK16 * 2; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < NK16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        int col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(b0, b1, b2, b3, sK + key * ROWB + col * 2);
+        mma_bf16_16816(sacc[np * 2], qf[ks], b0, b1);
+        mma_bf16_16816(sacc[np * 2 + 1], qf[ks], b2, b3);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NK16 * 2; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + (lane & 3) * 2 + (e & 1);
+        const float sv = key < tkv ? sacc[nt][e] * scale_log2 : -INFINITY;
+        sacc[nt][e] = sv;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sv);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      if (mx[r] == -INFINITY) mx[r] = 0.0f;
+    }
+    float rs[2] = {0.0f, 0.0f};
+    uint32_t pf[NK16][4];
+#pragma unroll
+    for (int nt = 0; nt < NK16 * 2; ++nt) {
+      const float p0 = exp2f(sacc[nt][0] - mx[0]);
+      const float p1 = exp2f(sacc[nt][1] - mx[0]);
+      const float p2 = exp2f(sacc[nt][2] - mx[1]);
+      const float p3 = exp2f(sacc[nt][3] - mx[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    float oacc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < NK16; ++ks) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        int col = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(b0, b1, b2, b3, sV + key * ROWB + col * 2);
+        mma_bf16_16816(oacc[np * 2], pf[ks], b0, b1);
+        mma_bf16_16816(oacc[np * 2 + 1], pf[ks], b2, b3);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+    }
+    const float inv0 = rs[0] > 0.0f ? 1.0f / rs[0] : 0.0f;
+    const float inv1 = rs[1] > 0.0f ? 1.0f / rs[1] : 0.0f;
+    // O through this warp's own 16 rows of the consumed Q buffer (its fragments are in registers), then out in rows
+    __syncwarp();
+    const int lr = warp * 16 + (lane >> 2);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + (lane & 3) * 2;
+      *reinterpret_cast<uint32_t*>(qb + lr * ROWB + col * 2) = pack_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+      *reinterpret_cast<uint32_t*>(qb + (lr + 8) * ROWB + col * 2) = pack_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+    }
+    __syncwarp();
+    const int ch = d / 8;  // 16-byte chunks per output row
+    for (int i = lane; i < 16 * ch; i += 32) {
+      const int r = i / ch, c = i - r * ch;
+      const int row = q0 + warp * 16 + r;
+      if (row < tq) *reinterpret_cast<uint4*>(og + (long long)row * ldo + c * 8) = *reinterpret_cast<const uint4*>(qb + (warp * 16 + r) * ROWB + c * 16);
+    }
+    __syncthreads();  // every warp is done with sQ[buf] before the prefetch of tile qt + 2 lands in it
+  }
+}
+
+template <int DP, int NK16>
+int launch_xattn_n(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+                   int d, float scale, cudaStream_t stream) {
+  constexpr int ROWB = DP * 2 + 16;
+  constexpr int SMEM = (2 * 64 + 2 * NK16 * 16) * ROWB;
+  static bool configured = false;
+  if (!configured) {
+    SASPA_CUDA(cudaFuncSetAttribute((xattn_resident_kernel<DP, NK16>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int n_qt = ceil_div(tq, BQ);
+  // enough CTAs for ~4 waves of the machine, at most 16 query tiles per CTA
+  int per = 16;
+  while (per > 1 && (long long)ceil_div(n_qt, per) * batch * heads < 4LL * saspa_num_sms()) per >>= 1;
+  dim3 grid(ceil_div(n_qt, per), batch * heads);
+  xattn_resident_kernel<DP, NK16><<<grid, ATT_THREADS, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
+                                                                       ldk, static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(o), ldo,
+                                                                       heads, tq, tkv, d, scale * 1.4426950408889634f, per);
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+template <int DP>
+int launch_xattn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+                 int d, float scale, cudaStream_t stream) {
+  if (tkv <= 80) return launch_xattn_n<DP, 5>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+  return launch_xattn_n<DP, 8>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+}
+
 // ---- row softmax (in place capable), one warp per row, fp32 math ----
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                                                            long long rows, int cols, float scale) {
@@ -288,7 +465,7 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-int g_attention_impl = 0;  // 0 = auto (tcgen05 when the shape has an instantiation), 1 = mma.sync flash kernel, 2 = tcgen05 only
+int g_attention_impl = 0;  // 0 = auto (K/V-resident kernel for tkv <= 128, else tcgen05 when the shape has an instantiation), 1 = mma.sync flash kernel, 2 = tcgen05 only
 
 }  // namespace
 
@@ -312,6 +489,14 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
                       (reinterpret_cast<uintptr_t>(o) & 3) == 0,
                   "saspa_attention_bf16: q/k/v must be 16-byte aligned");
   SASPA_CHECK_ARG((long long)batch * heads <= 65535, "saspa_attention_bf16: batch*heads must be <= 65535");
+  // short key sequences (cross-attention over the text tokens): K/V-resident streaming kernel
+  if (g_attention_impl == 0 && !causal && tkv <= 128 && tq >= 256 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    if (d <= 48) return launch_xattn<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    if (d <= 64) return launch_xattn<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    if (d <= 80) return launch_xattn<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    if (d <= 128) return launch_xattn<128>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    return launch_xattn<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+  }
   if (g_attention_impl != 1) {
     const int rc = saspa_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);
     if (rc != SASPA_ERR_UNSUPPORTED) return rc;
