@@ -173,9 +173,9 @@ int saspa_pool2d_nhwc_bf16(const void* x, int n, int h, int w, int c, int k, int
  * ------------------------------------------------------------------------------------------ */
 int saspa_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch,
                          int heads, int tq, int tkv, int d, float scale, int causal /* CLIP text tower */, cudaStream_t stream);
-/* Selects the attention kernel: 0 = auto (tcgen05/TMEM kernel for head_dim 40/64/80/128/160, else mma.sync),
- * 1 = mma.sync flash kernel only, 2 = tcgen05 only (error when the shape has no instantiation).  Returns the
- * previous setting; a negative argument only queries.  Process-wide; meant for tests and A/B timing. */
+/* Selects the attention kernel: 0 = auto (K/V-resident streaming kernel for non-causal tkv <= 128; tcgen05/TMEM kernel for
+ * head_dim 40/64/80/128/160; else mma.sync), 1 = mma.sync flash kernel only, 2 = tcgen05 only (error when the shape has
+ * no instantiation).  Returns the previous setting; a negative argument only queries.  Process-wide; for tests and A/B timing. */
 int saspa_attention_impl(int impl);
 
 /* Row softmax y = softmax(x * scale) (bf16, fp32 math) and batched 2-D transpose: the d = 512 single-head VAE

@@ -21,12 +21,12 @@ def main():
             k, v = kv[..., :c], kv[..., c:]
         out = torch.empty(b, tq, c, dtype=torch.bfloat16, device="cuda")
         res = []
-        for impl in (1, 2):
+        for impl in (1, 2, 0):
             lib.saspa_attention_impl(impl)
             ms = timeit(lambda: ops.attention(q, k, v, heads, out=out))
             res.append((ms, 4.0 * b * heads * tq * tkv * d / ms / 1e9))
         lib.saspa_attention_impl(0)
-        print(f"attn b{b} h{heads} {tq}x{tkv} d{d}: mma.sync {res[0][0]:.3f} ms {res[0][1]:.0f} TF/s | tcgen05 {res[1][0]:.3f} ms {res[1][1]:.0f} TF/s  (x{res[0][0]/res[1][0]:.2f})")
+        print(f"attn b{b} h{heads} {tq}x{tkv} d{d}: mma.sync {res[0][0]:.3f} ms | tcgen05 {res[1][0]:.3f} ms {res[1][1]:.0f} TF/s | auto {res[2][0]:.3f} ms {res[2][1]:.0f} TF/s")
 
 
 if __name__ == "__main__":
