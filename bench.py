@@ -276,9 +276,25 @@ def roofline_leg(pipe, dev_in, args):
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     per_kind = {k: {"launches": v[2], "ms": round(v[1], 3), "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None} for k, v in agg.items()}
     unet_step_ms = loop_ms / steps
+    # DRAM traffic per launch of the same kernel from the committed ncu capture of one step (never measured under bench.py)
+    traffic, traffic_src = None, None
+    try:
+        import glob
+
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_summary_*_dram.json")))
+        if cands:
+            js = json.load(open(cands[-1]))
+            ks = [k for k in js["kernels"] if "gemm_tc_kernel" in k["kernel"] and k.get("dram_bytes_per_launch")]
+            n = sum(k["launches"] for k in ks)
+            if n:
+                traffic = round(sum(k["dram_bytes_per_launch"] * k["launches"] for k in ks) / n)
+                traffic_src = os.path.relpath(cands[-1], ROOT)
+    except Exception:
+        pass
     roof = {
         "bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05 GEMM + implicit-GEMM conv), all launches of one micro-batch generation",
-        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
+        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's gemm_tc_kernel launches)",
+        "traffic_source": traffic_src, "algorithmic_flop_per_launch": round(tc_flops / max(tc_n, 1)),
         "peak_source": which, "launches_timed": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "per_kind": per_kind,
         "step_tensor_frac": round(GFLOP_PER_IMAGE_STEP * mb / (unet_step_ms * 1e-3) / 1e3 / peak, 4),
         "note": "step_tensor_frac = 2135 GFLOP x micro_batch / UNet-step time / peak (whole denoise step incl. attention + memory-bound glue)",

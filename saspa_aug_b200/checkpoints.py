@@ -48,6 +48,14 @@ class UNetConfig:
                           num_attention_heads=(5, 10, 20), cross_attention_dim=2048, use_linear_projection=True, addition_embed_type="text_time")
 
     @staticmethod
+    def tiny_xl() -> "UNetConfig":  # SDXL topology at toy width: cross dim 64 + 128 (two text encoders), pooled 96 + 6 x 32 time ids
+        return UNetConfig(block_out_channels=(64, 128, 128), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                          up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"), transformer_layers_per_block=(1, 2, 3),
+                          num_attention_heads=(1, 2, 2), cross_attention_dim=192, use_linear_projection=True, addition_embed_type="text_time",
+                          addition_time_embed_dim=32, projection_class_embeddings_input_dim=96 + 6 * 32,
+                          conditioning_embedding_out_channels=(16, 32, 32, 64))
+
+    @staticmethod
     def tiny(cross_attention_dim: int = 64) -> "UNetConfig":
         return UNetConfig(block_out_channels=(64, 128, 128, 128), num_attention_heads=(4, 4, 4, 4), cross_attention_dim=cross_attention_dim,
                           conditioning_embedding_out_channels=(16, 32, 32, 64))
@@ -86,14 +94,25 @@ class CLIPTextConfig:
     max_position_embeddings: int = 77
     hidden_act: str = "quick_gelu"
     layer_norm_eps: float = 1e-5
+    projection_dim: int = 0  # > 0: CLIPTextModelWithProjection (text_projection.weight [proj, hidden], no bias)
 
     @staticmethod
     def sd15() -> "CLIPTextConfig":  # openai/clip-vit-large-patch14 text tower
         return CLIPTextConfig()
 
     @staticmethod
+    def sdxl_g() -> "CLIPTextConfig":  # SDXL text_encoder_2: OpenCLIP ViT-bigG/14 text tower (CLIPTextModelWithProjection)
+        return CLIPTextConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20, hidden_act="gelu",
+                              projection_dim=1280)
+
+    @staticmethod
     def tiny() -> "CLIPTextConfig":
         return CLIPTextConfig(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4)
+
+    @staticmethod
+    def tiny_g() -> "CLIPTextConfig":
+        return CLIPTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, hidden_act="gelu",
+                              projection_dim=96)
 
 
 Shapes = Iterator[Tuple[str, Tuple[int, ...]]]
@@ -271,6 +290,8 @@ def clip_text_shapes(cfg: CLIPTextConfig) -> Shapes:
         yield from _lin(q + "mlp.fc2", cfg.intermediate_size, cfg.hidden_size)
         yield from _norm(q + "layer_norm2", cfg.hidden_size)
     yield from _norm(p + "final_layer_norm", cfg.hidden_size)
+    if cfg.projection_dim > 0:
+        yield "text_projection.weight", (cfg.projection_dim, cfg.hidden_size)
 
 
 _RESIDUAL_OUT = ("conv2.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight", "out_proj.weight", "mlp.fc2.weight", "conv3.weight", "c_proj.weight")

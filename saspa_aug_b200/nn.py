@@ -542,16 +542,23 @@ class CLIPTextEncoder:
                 "fc1": Linear(sd, q + "mlp.fc1", dev), "fc2": Linear(sd, q + "mlp.fc2", dev)})
             i += 1
         self.ln_final = Norm(sd, p + "final_layer_norm", dev)
+        # CLIPTextModelWithProjection (SDXL's second encoder): text_embeds = text_projection(final_ln(last)[eos])
+        self.proj = Linear(sd, "", dev, weight=sd["text_projection.weight"], bias=None) if "text_projection.weight" in sd else None
 
-    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
-        """ids int64 [n, 77] (device) -> last_hidden_state bf16 [n, 77, width]."""
+    def __call__(self, ids: torch.Tensor, penultimate: bool = False, pooled: bool = False):
+        """ids int64 [n, 77] (device) -> last_hidden_state bf16 [n, 77, width].
+        penultimate=True returns hidden_states[-2] instead (the input of the last layer, no final LayerNorm: what the SDXL
+        pipelines feed the UNet); pooled=True additionally returns text_embeds bf16 [n, proj] (EOS token = argmax id)."""
         n, t = ids.shape
         c = self.tok.shape[1]
         # embedding gather is index plumbing (no arithmetic): torch indexing, then our add kernel
         e = self.tok.index_select(0, ids.reshape(-1))
         pos = self.pos[:t].repeat(n, 1)
         h = ops.add(e, pos)
-        for L in self.layers:
+        pen = None
+        for li, L in enumerate(self.layers):
+            if penultimate and li == len(self.layers) - 1:
+                pen = h.clone().view(n, t, c)  # placement: the residual stream is updated in place below
             y = ops.layernorm(h, self.eps, L["ln1"].g, L["ln1"].b)
             qkv = L["qkv"](y).view(n, t, 3 * c)
             a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads, causal=True)
@@ -559,4 +566,10 @@ class CLIPTextEncoder:
             y = ops.layernorm(h, self.eps, L["ln2"].g, L["ln2"].b)
             f = L["fc1"](y, act=self.act)
             L["fc2"](f, out=h, residual=h, beta=1.0)
-        return ops.layernorm(h, self.eps, self.ln_final.g, self.ln_final.b).view(n, t, c)
+        last = ops.layernorm(h, self.eps, self.ln_final.g, self.ln_final.b).view(n, t, c)
+        out = pen if penultimate else last
+        if not pooled:
+            return out
+        eos = ids.argmax(dim=-1)  # index plumbing (transformers: input_ids.argmax(-1) for the legacy eos id)
+        rows = last.reshape(n * t, c).index_select(0, torch.arange(n, device=ids.device) * t + eos)
+        return out, (self.proj(rows) if self.proj is not None else rows)
