@@ -205,6 +205,13 @@ typedef struct saspa_lincomb {
 } saspa_lincomb;
 int saspa_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc_host, size_t count,
                          cudaStream_t stream);
+/* Same, plus ONE clamped term (DDIMScheduler clip_sample=True -- the DDIM defaults SD-XL-turbo's scheduler config inherits
+ * through DDIMScheduler.from_config at run_aug/run_aug.py:228: pred_original_sample.clamp(-clip_sample_range, clip_sample_range)):
+ *   c      = clamp(sum_i pre[i] * in[i], -clip_range, clip_range)
+ *   out[j] = sum_i coef[j*n_in + i] * in[i] + post[j] * c
+ * pre_host [n_in], post_host [n_out]; clip_range <= 0 disables the term (pre/post may then be NULL). */
+int saspa_cfg_sched_step_clip(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc_host,
+                              const float* pre_host, const float* post_host, float clip_range, size_t count, cudaStream_t stream);
 /* img2img start (diffusers prepare_latents of StableDiffusionControlNetImg2ImgPipeline): posterior sample of the VAE
  * encoder moments (fp32 NHWC [n,h,w,2*lc]: mean | logvar) times scaling_factor, then scheduler.add_noise:
  *   z0 = (mean + exp(0.5*clamp(logvar,-30,20)) * noise_posterior) * scaling;  latents = alpha*z0 + sigma*noise_diffusion

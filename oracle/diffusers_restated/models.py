@@ -331,7 +331,7 @@ class _Encoder(nn.Module):
         t = timestep
         if not torch.is_tensor(t):
             t = torch.tensor([t], dtype=torch.float32, device=sample.device)
-        t = t.reshape(-1).expand(sample.shape[0]).float()
+        t = t.to(sample.device).reshape(-1).expand(sample.shape[0]).float()
         emb = self.time_embedding(get_timestep_embedding(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift).to(sample.dtype))
         if cfg.addition_embed_type == "text_time":
             text_embeds, time_ids = added_cond["text_embeds"], added_cond["time_ids"]

@@ -27,7 +27,11 @@ class DDIMScheduler:
     order = 1
     init_noise_sigma = 1.0
 
-    def __init__(self, num_train_timesteps=1000, steps_offset=1, timestep_spacing="leading", set_alpha_to_one=False):
+    def __init__(self, num_train_timesteps=1000, steps_offset=1, timestep_spacing="leading", set_alpha_to_one=False, clip_sample=False,
+                 clip_sample_range=1.0):
+        # diffusers' own DDIM defaults are set_alpha_to_one=True, clip_sample=True; SD v1.5's scheduler config pins both to
+        # False (the defaults here).  sdxl-turbo's EulerAncestral config omits both keys => DDIM defaults apply there.
+        self.clip_sample, self.clip_sample_range = clip_sample, clip_sample_range
         self.num_train = num_train_timesteps
         self.steps_offset = steps_offset
         self.spacing = timestep_spacing
@@ -59,7 +63,9 @@ class DDIMScheduler:
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         x0 = (x - (1 - a_t).sqrt() * eps) / a_t.sqrt()
-        return a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps  # eta = 0
+        if self.clip_sample:
+            x0 = x0.clamp(-self.clip_sample_range, self.clip_sample_range)
+        return a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps  # eta = 0, use_clipped_model_output = False
 
 
 class PNDMScheduler:

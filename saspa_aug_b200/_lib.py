@@ -93,6 +93,7 @@ SIGNATURES = {
     "saspa_transpose_bf16": (c_int, [_P, c_int, ctypes.c_longlong, _P, c_int, ctypes.c_longlong, c_int, c_int, c_int, _P]),
     "saspa_timestep_sinusoid_bf16": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),
     "saspa_cfg_sched_step": (c_int, [_P, _P, c_float, POINTER(LinComb), c_size_t, _P]),
+    "saspa_cfg_sched_step_clip": (c_int, [_P, _P, c_float, POINTER(LinComb), POINTER(c_float), POINTER(c_float), c_float, c_size_t, _P]),
     "saspa_vae_sample_add_noise": (c_int, [_P, _P, _P, c_float, c_float, c_float, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "saspa_vae_quantize_u8": (c_int, [_P, c_int, c_int, c_size_t, _P, _P]),
     "saspa_bap_head": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),

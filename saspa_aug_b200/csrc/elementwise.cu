@@ -702,6 +702,9 @@ struct LinCombDev {
   const float* in[8];
   float* out[4];
   float coef[32];
+  float pre[8];   // clip term: out[j] += post[j] * clamp(sum_i pre[i] * in[i], -clip, clip)   (clip <= 0: off)
+  float post[4];
+  float clip;
   int n_in, n_out;
 };
 
@@ -715,10 +718,17 @@ __global__ void cfg_sched_kernel(const float* __restrict__ eu, const float* __re
     v[1] = e;
 #pragma unroll
     for (int k = 2; k < 8; ++k) v[k] = (k < lc.n_in && lc.in[k]) ? lc.in[k][i] : 0.0f;
+    float clipped = 0.0f;
+    if (lc.clip > 0.0f) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < lc.n_in) clipped += lc.pre[k] * v[k];
+      clipped = fminf(fmaxf(clipped, -lc.clip), lc.clip);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < lc.n_out) {
-        float acc = 0.0f;
+        float acc = lc.clip > 0.0f ? lc.post[j] * clipped : 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (k < lc.n_in) acc += lc.coef[j * lc.n_in + k] * v[k];
@@ -923,8 +933,22 @@ extern "C" int saspa_timestep_sinusoid_bf16(const float* t, int rows, int dim, i
   return SASPA_OK;
 }
 
+static int cfg_sched_launch(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc, const float* pre,
+                            const float* post, float clip, size_t count, cudaStream_t stream);
+
 extern "C" int saspa_cfg_sched_step(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc, size_t count,
                                     cudaStream_t stream) {
+  return cfg_sched_launch(eps_uncond, eps_cond, guidance, lc, nullptr, nullptr, 0.0f, count, stream);
+}
+
+extern "C" int saspa_cfg_sched_step_clip(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc,
+                                         const float* pre_host, const float* post_host, float clip_range, size_t count, cudaStream_t stream) {
+  SASPA_CHECK_ARG(clip_range <= 0.0f || (pre_host && post_host), "saspa_cfg_sched_step_clip: clip_range > 0 needs pre and post rows");
+  return cfg_sched_launch(eps_uncond, eps_cond, guidance, lc, pre_host, post_host, clip_range, count, stream);
+}
+
+static int cfg_sched_launch(const float* eps_uncond, const float* eps_cond, float guidance, const saspa_lincomb* lc, const float* pre,
+                            const float* post, float clip, size_t count, cudaStream_t stream) {
   SASPA_CHECK_ARG(lc && eps_cond, "saspa_cfg_sched_step: null pointer");
   SASPA_CHECK_ARG(lc->n_in >= 2 && lc->n_in <= 8 && lc->n_out >= 1 && lc->n_out <= 4, "saspa_cfg_sched_step: n_in in [2,8], n_out in [1,4]");
   if (count == 0) return SASPA_OK;
@@ -934,6 +958,9 @@ extern "C" int saspa_cfg_sched_step(const float* eps_uncond, const float* eps_co
   for (int i = 0; i < 32; ++i) d.coef[i] = lc->coef[i];
   d.n_in = lc->n_in;
   d.n_out = lc->n_out;
+  d.clip = clip > 0.0f ? clip : 0.0f;
+  for (int i = 0; i < 8; ++i) d.pre[i] = (d.clip > 0.0f && i < d.n_in) ? pre[i] : 0.0f;
+  for (int j = 0; j < 4; ++j) d.post[j] = (d.clip > 0.0f && j < d.n_out) ? post[j] : 0.0f;
   for (int j = 0; j < d.n_out; ++j) SASPA_CHECK_ARG(d.out[j], "saspa_cfg_sched_step: out[%d] is null", j);
   cfg_sched_kernel<<<grid_for((long long)count, 256), 256, 0, stream>>>(eps_uncond, eps_cond, guidance, d, count);
   SASPA_LAUNCH_CHECK();

@@ -259,20 +259,27 @@ class _EncoderBase:
                 out.append((c, i + 1))
         return out
 
-    def time_embed(self, t: torch.Tensor, added: Optional[dict] = None) -> torch.Tensor:
-        """t fp32 [n] -> fp32 [n, sum(cout of every resnet)]: all time_emb_proj(silu(emb)) in one GEMM."""
+    def added_embed(self, added: Optional[dict]) -> Optional[torch.Tensor]:
+        """SDXL "text_time" (diffusers unet_2d_condition.get_aug_embed): add_embedding(cat[pooled text embeds, sinusoid(time_ids)])
+        -> bf16 [n, temb].  Step-invariant: computed once per image, consumed as the residual of ``time_embed``."""
+        if self.add_emb is None:
+            return None
+        cfg = self.cfg
+        te = added["text_embeds"]  # bf16 [n, proj]
+        n = te.shape[0]
+        tid = ops.timestep_sinusoid(added["time_ids"].reshape(-1).float().contiguous(), cfg.addition_time_embed_dim, cfg.flip_sin_to_cos, cfg.freq_shift)
+        buf = torch.empty((n, te.shape[1] + tid.numel() // n), dtype=BF16, device=te.device)
+        buf[:, : te.shape[1]].copy_(te)  # concatenation = data placement only
+        buf[:, te.shape[1] :].copy_(tid.view(n, -1))
+        return self.add_emb[1](self.add_emb[0](buf, act=ACT_SILU))
+
+    def time_embed(self, t: torch.Tensor, aug: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """t fp32 [n] -> fp32 [n, sum(cout of every resnet)]: all time_emb_proj(silu(emb)) in one GEMM.
+        ``aug`` = ``added_embed(...)`` for SDXL (emb = time_embedding(t) + aug)."""
         cfg = self.cfg
         s = ops.timestep_sinusoid(t, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift)
-        emb = self.t_lin2(self.t_lin1(s, act=ACT_SILU))
-        if self.add_emb is not None:
-            # SDXL "text_time": emb += add_embedding(cat[pooled text embeds, sinusoid(time_ids)])
-            n = t.shape[0]
-            te = added["text_embeds"]  # bf16 [n, 1280]
-            tid = ops.timestep_sinusoid(added["time_ids"].reshape(-1).float(), cfg.addition_time_embed_dim, cfg.flip_sin_to_cos, cfg.freq_shift)
-            buf = torch.empty((n, te.shape[1] + tid.numel() // n), dtype=BF16, device=t.device)
-            buf[:, : te.shape[1]].copy_(te)  # concatenation = data placement only
-            buf[:, te.shape[1] :].copy_(tid.view(n, -1))
-            emb = self.add_emb[1](self.add_emb[0](buf, act=ACT_SILU), residual=emb, beta=1.0)
+        h = self.t_lin1(s, act=ACT_SILU)
+        emb = self.t_lin2(h, residual=aug, beta=1.0) if aug is not None else self.t_lin2(h)
         return ops.gemm(ops.act(emb, ACT_SILU), self.temb_w, bias=self.temb_b, out_fp32=True)
 
     def text_kv(self, text: torch.Tensor):
@@ -545,14 +552,22 @@ class CLIPTextEncoder:
         # CLIPTextModelWithProjection (SDXL's second encoder): text_embeds = text_projection(final_ln(last)[eos])
         self.proj = Linear(sd, "", dev, weight=sd["text_projection.weight"], bias=None) if "text_projection.weight" in sd else None
 
-    def __call__(self, ids: torch.Tensor, penultimate: bool = False, pooled: bool = False):
+    def __call__(self, ids: torch.Tensor, penultimate: bool = False, pooled: bool = False, ctx_embeddings: Optional[torch.Tensor] = None,
+                 ctx_begin_pos: int = 2):
         """ids int64 [n, 77] (device) -> last_hidden_state bf16 [n, 77, width].
+        ctx_embeddings bf16 [n, q, width] (BLIP-Diffusion's ContextCLIPTextModel, diffusers modeling_ctx_clip.py): inserted after
+        ``ctx_begin_pos`` token embeddings; ids are then [n, 77 - q] and positions run over the spliced sequence.
         penultimate=True returns hidden_states[-2] instead (the input of the last layer, no final LayerNorm: what the SDXL
         pipelines feed the UNet); pooled=True additionally returns text_embeds bf16 [n, proj] (EOS token = argmax id)."""
         n, t = ids.shape
         c = self.tok.shape[1]
         # embedding gather is index plumbing (no arithmetic): torch indexing, then our add kernel
         e = self.tok.index_select(0, ids.reshape(-1))
+        if ctx_embeddings is not None:  # splice = data placement
+            q = ctx_embeddings.shape[1]
+            e3 = e.view(n, t, c)
+            e = torch.cat([e3[:, :ctx_begin_pos], ctx_embeddings.to(BF16), e3[:, ctx_begin_pos:]], dim=1).reshape(n * (t + q), c)
+            t = t + q
         pos = self.pos[:t].repeat(n, 1)
         h = ops.add(e, pos)
         pen = None
@@ -573,3 +588,152 @@ class CLIPTextEncoder:
         eos = ids.argmax(dim=-1)  # index plumbing (transformers: input_ids.argmax(-1) for the legacy eos id)
         rows = last.reshape(n * t, c).index_select(0, torch.arange(n, device=ids.device) * t + eos)
         return out, (self.proj(rows) if self.proj is not None else rows)
+
+
+# ------------------------------------------------------------------------------------------------
+# ViT encoder (BLIP-2 vision tower of the Q-Former; CLIP ViT-L/14 image tower of the filter)
+# ------------------------------------------------------------------------------------------------
+class ViTEncoder:
+    """Pre-LayerNorm ViT: patch conv (stride = kernel, no bias) + class token + learned positions -> pre-LN -> L x
+    [LN, fused-QKV attention, +; LN, MLP, +] -> (post-LN).  Built from already-gathered tensors so one class serves the
+    BLIP-2 key layout (``from_blip2``) and the CLIP vision layouts (filter_nets)."""
+
+    def __init__(self, dev, *, patch_w, class_emb, pos_emb, pre_ln, layers, post_ln, heads: int, act: int, eps: float):
+        self.dev, self.heads, self.act, self.eps = dev, heads, act, eps
+        self.width, _, self.patch, _ = patch_w.shape
+        self.patch_conv = Conv({}, "", dev, stride=self.patch, padding=0, weight=patch_w, bias=None)
+        # token 0 = class embedding + position 0 (constant row); patch rows get position 1.. in the GEMM epilogue
+        self.cls_row = _bf(class_emb.reshape(1, -1).float() + pos_emb.reshape(-1, self.width)[:1].float(), dev)
+        self.pos_patches = _bf(pos_emb.reshape(-1, self.width)[1:], dev)
+        self.pre_ln, self.post_ln, self.layers = pre_ln, post_ln, layers
+
+    @staticmethod
+    def _layer(sd, dev, wqkv, bqkv, o, ln1, ln2, fc1, fc2):
+        return {"ln1": Norm(sd, ln1, dev), "ln2": Norm(sd, ln2, dev), "qkv": Linear(sd, "", dev, weight=wqkv, bias=bqkv), "o": Linear(sd, o, dev),
+                "fc1": Linear(sd, fc1, dev), "fc2": Linear(sd, fc2, dev)}
+
+    @classmethod
+    def from_blip2(cls, sd: SD, p: str, dev, heads: int, eps: float = 1e-5):
+        """diffusers modeling_blip2.Blip2VisionModel keys under prefix ``p`` (e.g. "visual_encoder.")."""
+        layers = []
+        i = 0
+        while f"{p}encoder.layers.{i}.layer_norm1.weight" in sd:
+            q = f"{p}encoder.layers.{i}."
+            layers.append(cls._layer(sd, dev, sd[q + "self_attn.qkv.weight"], sd[q + "self_attn.qkv.bias"], q + "self_attn.projection", q + "layer_norm1",
+                                     q + "layer_norm2", q + "mlp.fc1", q + "mlp.fc2"))
+            i += 1
+        return cls(dev, patch_w=sd[p + "embeddings.patch_embedding.weight"], class_emb=sd[p + "embeddings.class_embedding"],
+                   pos_emb=sd[p + "embeddings.position_embedding"], pre_ln=Norm(sd, p + "pre_layernorm", dev), layers=layers,
+                   post_ln=Norm(sd, p + "post_layernorm", dev), heads=heads, act=ACT_QUICKGELU, eps=eps)
+
+    def __call__(self, x: torch.Tensor, apply_post_ln: bool = True) -> torch.Tensor:
+        """x bf16 NHWC [n, S, S, 3] (normalised pixels) -> hidden states bf16 [n, 1 + (S/patch)^2, width]."""
+        n = x.shape[0]
+        c = self.width
+        pt = self.patch_conv(x)  # [n, g, g, width]
+        g2 = pt.shape[1] * pt.shape[2]
+        assert g2 == self.pos_patches.shape[0], "image size does not match the position table"
+        t = g2 + 1
+        h3 = torch.empty((n, t, c), dtype=BF16, device=x.device)
+        h3[:, 0] = self.cls_row  # placement
+        h3[:, 1:] = ops.add(pt.view(n * g2, c), self.pos_patches.repeat(n, 1)).view(n, g2, c)
+        h = ops.layernorm(h3.view(n * t, c), self.eps, self.pre_ln.g, self.pre_ln.b) if self.pre_ln is not None else h3.view(n * t, c)
+        for L in self.layers:
+            y = ops.layernorm(h, self.eps, L["ln1"].g, L["ln1"].b)
+            qkv = L["qkv"](y).view(n, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads)
+            L["o"](a.view(n * t, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, self.eps, L["ln2"].g, L["ln2"].b)
+            L["fc2"](L["fc1"](y, act=self.act), out=h, residual=h, beta=1.0)
+        if apply_post_ln and self.post_ln is not None:
+            h = ops.layernorm(h, self.eps, self.post_ln.g, self.post_ln.b)
+        return h.view(n, t, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# BLIP-2 Q-Former (diffusers pipelines/blip_diffusion/modeling_blip2.py)
+# ------------------------------------------------------------------------------------------------
+class _BertAttn:
+    """BERT attention block, post-LayerNorm: LN(dense(attn(x, ctx)) + x).  q/k/v fused where they share an input."""
+
+    def __init__(self, sd: SD, p: str, dev, heads: int, eps: float, cross: bool):
+        self.heads, self.eps, self.cross = heads, eps, cross
+        a = p + ".attention."
+        if cross:
+            self.q = Linear(sd, a + "query", dev)
+            self.kv = Linear(sd, "", dev, weight=torch.cat([sd[a + "key.weight"], sd[a + "value.weight"]], 0),
+                             bias=torch.cat([sd[a + "key.bias"], sd[a + "value.bias"]], 0))
+        else:
+            self.qkv = Linear(sd, "", dev, weight=torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0),
+                              bias=torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0))
+        self.o = Linear(sd, p + ".output.dense", dev)
+        self.ln = Norm(sd, p + ".output.LayerNorm", dev)
+
+    def __call__(self, x2: torch.Tensor, n: int, ctx2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        rows, c = x2.shape
+        t = rows // n
+        if self.cross:
+            q = self.q(x2).view(n, t, c)
+            kv = self.kv(ctx2).view(n, ctx2.shape[0] // n, 2 * c)
+            a = ops.attention(q, kv[..., :c], kv[..., c:], self.heads)
+        else:
+            qkv = self.qkv(x2).view(n, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads)
+        y = self.o(a.view(rows, c), residual=x2, beta=1.0)
+        return ops.layernorm(y, self.eps, self.ln.g, self.ln.b)
+
+
+class _BertFFN:
+    def __init__(self, sd: SD, p_int: str, p_out: str, dev, eps: float):
+        self.fc1, self.fc2, self.ln, self.eps = Linear(sd, p_int + ".dense", dev), Linear(sd, p_out + ".dense", dev), Norm(sd, p_out + ".LayerNorm", dev), eps
+
+    def __call__(self, x2):
+        y = self.fc2(self.fc1(x2, act=ops.ACT_GELU), residual=x2, beta=1.0)
+        return ops.layernorm(y, self.eps, self.ln.g, self.ln.b)
+
+
+class QFormer:
+    """Blip2QFormerModel.forward(image_input, text_input) -> proj_layer(sequence_output[:, :num_query_tokens]): the 16 subject
+    embeddings BLIP-Diffusion splices into the CLIP prompt.  Step-invariant and prompt-invariant: computed once per
+    (reference image, source subject)."""
+
+    def __init__(self, sd: SD, cfg, dev):
+        self.cfg, self.dev = cfg, dev
+        e = cfg.layer_norm_eps
+        self.word = _bf(sd["embeddings.word_embeddings.weight"], dev)
+        self.pos = _bf(sd["embeddings.position_embeddings.weight"], dev)
+        self.emb_ln = Norm(sd, "embeddings.LayerNorm", dev)
+        self.query_tokens = _bf(sd["query_tokens"].reshape(cfg.num_query_tokens, cfg.hidden_size), dev)
+        self.vision = ViTEncoder.from_blip2(sd, "visual_encoder.", dev, cfg.vision_num_attention_heads, cfg.vision_layer_norm_eps)
+        self.layers = []
+        for i in range(cfg.num_hidden_layers):
+            p = f"encoder.layer.{i}"
+            self.layers.append({
+                "attn": _BertAttn(sd, p + ".attention", dev, cfg.num_attention_heads, e, cross=False),
+                "cross": _BertAttn(sd, p + ".crossattention", dev, cfg.num_attention_heads, e, cross=True) if i % cfg.cross_attention_frequency == 0 else None,
+                "ffn_text": _BertFFN(sd, p + ".intermediate", p + ".output", dev, e),
+                "ffn_query": _BertFFN(sd, p + ".intermediate_query", p + ".output_query", dev, e)})
+        self.proj_ln = Norm(sd, "proj_layer.LayerNorm", dev)
+        self.proj1, self.proj2 = Linear(sd, "proj_layer.dense1", dev), Linear(sd, "proj_layer.dense2", dev)
+
+    def __call__(self, image: torch.Tensor, subject_ids: torch.Tensor) -> torch.Tensor:
+        """image bf16 NHWC [n,S,S,3] (BlipImageProcessor-normalised), subject_ids int64 [n,L] (no padding) -> bf16 [n,16,hidden]."""
+        n, L = subject_ids.shape
+        c, nq = self.cfg.hidden_size, self.cfg.num_query_tokens
+        t = nq + L
+        img = self.vision(image)
+        img2 = img.reshape(n * img.shape[1], img.shape[2])
+        txt = ops.add(self.word.index_select(0, subject_ids.reshape(-1).to(self.dev)), self.pos[:L].repeat(n, 1)).view(n, L, c)
+        e = torch.cat([self.query_tokens[None].expand(n, -1, -1), txt], dim=1).reshape(n * t, c)  # placement
+        h = ops.layernorm(e, self.cfg.layer_norm_eps, self.emb_ln.g, self.emb_ln.b)
+        for Lr in self.layers:
+            a = Lr["attn"](h, n).view(n, t, c)
+            q = a[:, :nq].reshape(n * nq, c)
+            if Lr["cross"] is not None:
+                q = Lr["cross"](q, n, img2)
+            q = Lr["ffn_query"](q)
+            tx = Lr["ffn_text"](a[:, nq:].reshape(n * L, c))
+            h = torch.cat([q.view(n, nq, c), tx.view(n, L, c)], dim=1).reshape(n * t, c)
+        q = h.view(n, t, c)[:, :nq].reshape(n * nq, c)
+        y = ops.layernorm(q, 1e-12, self.proj_ln.g, self.proj_ln.b)
+        return self.proj2(self.proj1(y, act=ACT_QUICKGELU), residual=q, beta=1.0).view(n, nq, c)

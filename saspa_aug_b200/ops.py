@@ -335,9 +335,9 @@ def timestep_sinusoid(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, f
     return out
 
 
-def cfg_sched_step(eps_uncond, eps_cond, guidance: float, inputs, outputs, coef) -> None:
-    """outputs[j] = sum_i coef[j][i] * in_i with in = [x, cfg(eps), *history]; ``inputs`` = [x, None, hist...]
-    (slot 1 is the CFG-combined eps, produced inside the kernel)."""
+def cfg_sched_step(eps_uncond, eps_cond, guidance: float, inputs, outputs, coef, clip_pre=None, clip_post=None, clip_range: float = 0.0) -> None:
+    """outputs[j] = sum_i coef[j][i] * in_i  (+ clip_post[j] * clamp(sum_i clip_pre[i] * in_i, +-clip_range) when clip_range > 0)
+    with in = [x, cfg(eps), *history]; ``inputs`` = [x, None, hist...] (slot 1 is the CFG-combined eps, produced inside the kernel)."""
     _need_cuda(eps_cond)
     lc = LinComb()
     n_in, n_out = len(inputs), len(outputs)
@@ -357,7 +357,14 @@ def cfg_sched_step(eps_uncond, eps_cond, guidance: float, inputs, outputs, coef)
     assert eps_cond.dtype == torch.float32 and eps_cond.is_contiguous()
     if eps_uncond is not None:
         assert eps_uncond.dtype == torch.float32 and eps_uncond.is_contiguous() and eps_uncond.numel() == count
-    check(_lib.load().saspa_cfg_sched_step(_ptr(eps_uncond), _ptr(eps_cond), float(guidance), ctypes.byref(lc), count, _stream()), "saspa_cfg_sched_step")
+    if clip_range > 0.0:
+        assert len(clip_pre) == n_in and len(clip_post) == n_out
+        pre = (ctypes.c_float * n_in)(*[float(v) for v in clip_pre])
+        post = (ctypes.c_float * n_out)(*[float(v) for v in clip_post])
+        check(_lib.load().saspa_cfg_sched_step_clip(_ptr(eps_uncond), _ptr(eps_cond), float(guidance), ctypes.byref(lc), pre, post, float(clip_range), count,
+                                                    _stream()), "saspa_cfg_sched_step_clip")
+    else:
+        check(_lib.load().saspa_cfg_sched_step(_ptr(eps_uncond), _ptr(eps_cond), float(guidance), ctypes.byref(lc), count, _stream()), "saspa_cfg_sched_step")
     _count()
 
 

@@ -31,8 +31,9 @@ class SyntheticTokenizer:
     non-alphanumerics, maps each word to 1 + crc32(word) % (vocab-3); BOS = vocab-2, EOS = pad = vocab-1,
     truncation at ``model_max_length`` (77).  A real CLIPTokenizer can be passed to the pipeline instead."""
 
-    def __init__(self, vocab_size: int = 49408, model_max_length: int = 77):
+    def __init__(self, vocab_size: int = 49408, model_max_length: int = 77, pad_id: Optional[int] = None):
         self.vocab_size, self.model_max_length = vocab_size, model_max_length
+        self.pad_id = vocab_size - 1 if pad_id is None else pad_id  # SDXL's tokenizer_2 pads with "!" (id 0)
 
     def encode(self, text: str) -> List[int]:
         import re
@@ -40,7 +41,7 @@ class SyntheticTokenizer:
         words = [w for w in re.split(r"[^0-9a-zA-Z]+", text.lower()) if w]
         ids = [1 + zlib.crc32(w.encode()) % (self.vocab_size - 3) for w in words][: self.model_max_length - 2]
         ids = [self.vocab_size - 2] + ids + [self.vocab_size - 1]
-        return ids + [self.vocab_size - 1] * (self.model_max_length - len(ids))
+        return ids + [self.pad_id] * (self.model_max_length - len(ids))
 
     def __call__(self, texts: Union[str, Sequence[str]]) -> torch.Tensor:
         if isinstance(texts, str):
@@ -121,6 +122,16 @@ class SaspaControlNetPipeline:
             self._neg_cache[key] = self.encode_prompt_ids(self.tokenizer([key]))
         return self._neg_cache[key].expand(n, -1, -1)
 
+    def _encode_call(self, prompt, prompt_ids, negative_prompt, negative_prompt_ids, do_cfg: bool, H: int, W: int):
+        """encode_prompt of the pipeline call -> (text bf16 [B,77,D], neg or None, added-cond dict or None)."""
+        if prompt_ids is None:
+            prompt_ids = self.tokenizer([prompt] if isinstance(prompt, str) else list(prompt))
+        text = self.encode_prompt_ids(prompt_ids)
+        neg = None
+        if do_cfg:
+            neg = self.encode_prompt_ids(negative_prompt_ids) if negative_prompt_ids is not None else self._neg_embeds(negative_prompt, text.shape[0]).contiguous()
+        return text, neg, None
+
     # ---- image helpers -----------------------------------------------------------------------------
     def _to_u8_batch(self, image) -> torch.Tensor:
         """PIL | ndarray | list thereof | u8 tensor -> u8 [n,H,W,3] on the device."""
@@ -148,9 +159,10 @@ class SaspaControlNetPipeline:
                        source_u8: Optional[torch.Tensor] = None, *, noise: torch.Tensor, noise_posterior: Optional[torch.Tensor] = None,
                        num_inference_steps: int = 50, guidance_scale: float = 7.5, strength: float = 1.0,
                        controlnet_conditioning_scale: float = 1.0, control_bf16: Optional[torch.Tensor] = None,
-                       step_callback: Optional[Callable] = None, decode: bool = True):
+                       step_callback: Optional[Callable] = None, decode: bool = True, added: Optional[dict] = None):
         """B images in one launch list.
         text_embeds/neg_embeds bf16 [B,77,D]; control_u8/source_u8 u8 [B,H,W,3]; noise fp32 NCHW [B,4,H/8,W/8] (device).
+        added (SDXL only): {"text_embeds": bf16 [rows, proj], "time_ids": fp32 [rows, 6]} with rows ordered like the text rows.
         Returns u8 [B,H,W,3] (device) -- or the final latents when decode=False."""
         dev = self.device
         B = text_embeds.shape[0]
@@ -167,10 +179,13 @@ class SaspaControlNetPipeline:
         text = torch.cat([neg_embeds, text_embeds], 0).contiguous() if do_cfg else text_embeds.contiguous()
         rows = text.shape[0]
         kv_u = self.unet.text_kv(text)
+        aug_u = self.unet.added_embed(added)
         cond_emb = None
         kv_c = None
+        aug_c = None
         if self.controlnet is not None:
             kv_c = self.controlnet.text_kv(text)
+            aug_c = self.controlnet.added_embed(added)
             if control_bf16 is None:
                 H, W = control_u8.shape[1:3]
                 control_bf16 = ops.crop_normalize(control_u8, 0, 0, H, W, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), out_c=3)
@@ -197,26 +212,27 @@ class SaspaControlNetPipeline:
         for i in range(start, len(sched.timesteps)):
             t = float(sched.timesteps[i])
             tvec.fill_(t)
-            eps = self._eps(latents, x2, tvec, kv_u, kv_c, cond_emb, controlnet_conditioning_scale, B, do_cfg, lh, lw)
+            eps = self._eps(latents, x2, tvec, kv_u, kv_c, cond_emb, controlnet_conditioning_scale, B, do_cfg, lh, lw, aug_u, aug_c)
             plan = sched.plan(i)
             ops.cfg_sched_step(eps[:B] if do_cfg else None, eps[B:] if do_cfg else eps, guidance_scale,
-                               [None if nm is None else bufs[nm] for nm in plan.inputs], [bufs[nm] for nm in plan.outputs], plan.coef)
+                               [None if nm is None else bufs[nm] for nm in plan.inputs], [bufs[nm] for nm in plan.outputs], plan.coef,
+                               plan.clip_pre, plan.clip_post, plan.clip_range)
             if step_callback is not None:
                 step_callback(i, t, latents)
         if not decode:
             return latents
         return self.decode_latents(latents)
 
-    def _eps(self, latents, x2, tvec, kv_u, kv_c, cond_emb, cond_scale, B, do_cfg, lh, lw) -> torch.Tensor:
+    def _eps(self, latents, x2, tvec, kv_u, kv_c, cond_emb, cond_scale, B, do_cfg, lh, lw, aug_u=None, aug_c=None) -> torch.Tensor:
         """One UNet(+ControlNet) evaluation -> eps fp32 NCHW [rows,4,h,w] (rows = 2B with CFG: uncond first)."""
         rows = x2.shape[0]
         ops.nchw_f32_to_nhwc_bf16(latents, out=x2[:B])
         if do_cfg:
             ops.nchw_f32_to_nhwc_bf16(latents, out=x2[B:])
-        temb_u = self.unet.time_embed(tvec)
+        temb_u = self.unet.time_embed(tvec, aug_u)
         st = self.unet.encode(x2, temb_u, kv_u, rows, lh, lw)
         if self.controlnet is not None:
-            temb_c = self.controlnet.time_embed(tvec)
+            temb_c = self.controlnet.time_embed(tvec, aug_c)
             self.controlnet.inject(x2, temb_c, kv_c, cond_emb, cond_scale, st)
         eps_nhwc = self.unet.decode(st, temb_u, kv_u)
         return ops.nhwc_to_nchw_f32(eps_nhwc)
@@ -243,17 +259,12 @@ class SaspaControlNetPipeline:
             control, source = image, None
         else:
             control, source = control_image, image
-        if prompt_ids is None:
-            prompt_ids = self.tokenizer([prompt] if isinstance(prompt, str) else list(prompt))
-        B = prompt_ids.shape[0]
-        text = self.encode_prompt_ids(prompt_ids)
-        neg = None
-        if guidance_scale > 1.0:
-            neg = self.encode_prompt_ids(negative_prompt_ids) if negative_prompt_ids is not None else self._neg_embeds(negative_prompt, B).contiguous()
         control_u8 = self._to_u8_batch(control) if control is not None else None
         source_u8 = self._to_u8_batch(source) if source is not None else None
         ref = control_u8 if control_u8 is not None else source_u8
         H, W = (ref.shape[1], ref.shape[2]) if ref is not None else (height or 512, width or 512)
+        text, neg, added = self._encode_call(prompt, prompt_ids, negative_prompt, negative_prompt_ids, guidance_scale > 1.0, H, W)
+        B = text.shape[0]
         shape = (B, self.vae_cfg.latent_channels, H // 8, W // 8)
         # diffusers randn_tensor: CPU generator -> sample on CPU, then move.  img2img draws the VAE posterior noise first.
         post = torch.randn(shape, generator=generator, dtype=torch.float32).to(self.device) if source_u8 is not None else None
@@ -263,7 +274,7 @@ class SaspaControlNetPipeline:
         cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
         out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, num_inference_steps=num_inference_steps,
                                   guidance_scale=guidance_scale, strength=strength, controlnet_conditioning_scale=controlnet_conditioning_scale,
-                                  step_callback=cb)
+                                  step_callback=cb, added=added)
         arr = out.cpu().numpy()
         if output_type == "pil":
             from PIL import Image
@@ -274,7 +285,102 @@ class SaspaControlNetPipeline:
         return PipelineOutput(images=images, nsfw_content_detected=None, latents_per_step=per_step)
 
 
+class SaspaSDXLControlNetPipeline(SaspaControlNetPipeline):
+    """SD-XL(-turbo) ControlNet pipeline, text2img and img2img (run_aug.py:188-199 builds diffusers'
+    StableDiffusionXLControlNet{,Img2Img}Pipeline; same call kwargs as the SD v1.5 pipelines, run_aug.py:235-279).
+
+    Differences from SD v1.5, following diffusers 0.32.2 pipelines/controlnet/pipeline_controlnet_sd_xl{,_img2img}.py:
+      * two text encoders: CLIP ViT-L (CLIPTextModel) and OpenCLIP bigG (CLIPTextModelWithProjection); encoder_hidden_states =
+        concat(hidden_states[-2] of both) [B,77,2048]; pooled ``text_embeds`` of the second;
+      * added conditioning ("text_time"): add_time_ids = [H, W, 0, 0, H, W] (original_size, crop top-left, target_size;
+        requires_aesthetics_score=False for the base/turbo UNet), same kwargs to ControlNet and UNet;
+      * sd_xl-turbo runs guidance_scale 0 => no CFG rows (run_aug.py:567-570); default sampler "ddim_sdxl_turbo" (schedulers.py);
+      * VAE scaling 0.13025 (madebyollin/sdxl-vae-fp16-fix, run_aug.py:189); upcast_vae() is a no-op (fp32 accumulation everywhere).
+    """
+
+    def __init__(self, *a, text_encoder_2: snn.CLIPTextEncoder = None, tokenizer_2=None, **k):
+        super().__init__(*a, **k)
+        self.text_encoder_2 = text_encoder_2
+        self.tokenizer_2 = tokenizer_2 or SyntheticTokenizer(pad_id=0)
+
+    @classmethod
+    def from_state_dicts(cls, unet_sd, controlnet_sd, vae_sd, text_sd, text2_sd, *, unet_cfg=None, vae_cfg=None, text_cfg=None, text2_cfg=None,
+                         sampler="ddim_sdxl_turbo", device="cuda", tokenizer=None, tokenizer_2=None, img2img=True):
+        unet_cfg = unet_cfg or ck.UNetConfig.sdxl()
+        vae_cfg = vae_cfg or ck.VAEConfig.sdxl()
+        text_cfg = text_cfg or ck.CLIPTextConfig.sd15()
+        text2_cfg = text2_cfg or ck.CLIPTextConfig.sdxl_g()
+        dev = torch.device(device)
+        unet = snn.UNet(unet_sd, unet_cfg, dev)
+        cn = snn.ControlNet(controlnet_sd, unet_cfg, dev) if controlnet_sd is not None else None
+        dec = snn.VAEDecoder(vae_sd, vae_cfg, dev)
+        enc = snn.VAEEncoder(vae_sd, vae_cfg, dev) if img2img else None
+        te = snn.CLIPTextEncoder(text_sd, dev, text_cfg.num_attention_heads, text_cfg.hidden_act, text_cfg.layer_norm_eps)
+        te2 = snn.CLIPTextEncoder(text2_sd, dev, text2_cfg.num_attention_heads, text2_cfg.hidden_act, text2_cfg.layer_norm_eps)
+        tok = tokenizer or SyntheticTokenizer(text_cfg.vocab_size, text_cfg.max_position_embeddings)
+        tok2 = tokenizer_2 or SyntheticTokenizer(text2_cfg.vocab_size, text2_cfg.max_position_embeddings, pad_id=0)
+        return cls(unet, cn, dec, enc, te, tok, sampler, device, vae_cfg, text_encoder_2=te2, tokenizer_2=tok2)
+
+    @classmethod
+    def random_init(cls, config: str = "sdxl", seed: int = 1234, **kw):
+        cfgs = sdxl_configs(config)
+        sds = random_state_dicts(config, seed)
+        return cls.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["text2"], unet_cfg=cfgs[0], vae_cfg=cfgs[1],
+                                    text_cfg=cfgs[2], text2_cfg=cfgs[3], **kw)
+
+    def encode_prompt_ids(self, ids, ids_2=None):
+        """-> (encoder_hidden_states bf16 [B,77,D1+D2], pooled text_embeds bf16 [B,proj])."""
+        ids_2 = ids if ids_2 is None else ids_2
+        h1 = self.text_encoder(ids.to(self.device), penultimate=True)
+        h2, pooled = self.text_encoder_2(ids_2.to(self.device), penultimate=True, pooled=True)
+        return torch.cat([h1, h2], dim=-1), pooled  # channel concat of finished tensors: placement only
+
+    def time_ids(self, n: int, H: int, W: int) -> torch.Tensor:
+        return torch.tensor([[H, W, 0, 0, H, W]], dtype=torch.float32).repeat(n, 1).to(self.device)
+
+    def _encode_call(self, prompt, prompt_ids, negative_prompt, negative_prompt_ids, do_cfg: bool, H: int, W: int):
+        def split(x):
+            return x if isinstance(x, (tuple, list)) else (x, x)
+
+        if prompt_ids is None:
+            ps = [prompt] if isinstance(prompt, str) else list(prompt)
+            prompt_ids = (self.tokenizer(ps), self.tokenizer_2(ps))
+        text, pooled = self.encode_prompt_ids(*split(prompt_ids))
+        B = text.shape[0]
+        neg = None
+        if do_cfg:
+            if negative_prompt_ids is None:
+                key = negative_prompt or ""
+                if key not in self._neg_cache:
+                    # diffusers zeroes the negative embeddings only when negative_prompt is None and force_zeros_for_empty_prompt;
+                    # the reference always passes its NEGATIVE_PROMPT string (run_aug.py:47,240), so it is encoded.
+                    self._neg_cache[key] = self.encode_prompt_ids(self.tokenizer([key]), self.tokenizer_2([key]))
+                neg, npooled = (t.expand(B, *t.shape[1:]).contiguous() for t in self._neg_cache[key])
+            else:
+                neg, npooled = self.encode_prompt_ids(*split(negative_prompt_ids))
+            pooled = torch.cat([npooled, pooled], 0)
+        added = {"text_embeds": pooled.contiguous(), "time_ids": self.time_ids(pooled.shape[0], H, W)}
+        return text, neg, added
+
+
+def sdxl_configs(config: str):
+    if config == "sdxl":
+        return ck.UNetConfig.sdxl(), ck.VAEConfig.sdxl(), ck.CLIPTextConfig.sd15(), ck.CLIPTextConfig.sdxl_g()
+    if config == "tiny_xl":
+        return ck.UNetConfig.tiny_xl(), ck.VAEConfig.tiny(), ck.CLIPTextConfig.tiny(), ck.CLIPTextConfig.tiny_g()
+    raise ValueError(config)
+
+
 def random_state_dicts(config: str = "sd15", seed: int = 1234) -> dict:
+    if config in ("sdxl", "tiny_xl"):
+        ucfg, vcfg, tcfg, t2cfg = sdxl_configs(config)
+        return {
+            "unet": ck.random_state_dict(ck.unet_shapes(ucfg), seed),
+            "controlnet": ck.random_state_dict(ck.controlnet_shapes(ucfg), seed + 1),
+            "vae": ck.random_state_dict(ck.vae_shapes(vcfg), seed + 2),
+            "text": ck.random_state_dict(ck.clip_text_shapes(tcfg), seed + 3),
+            "text2": ck.random_state_dict(ck.clip_text_shapes(t2cfg), seed + 4),
+        }
     if config == "tiny":
         ucfg, vcfg, tcfg = ck.UNetConfig.tiny(), ck.VAEConfig.tiny(), ck.CLIPTextConfig.tiny()
     elif config == "sd15":

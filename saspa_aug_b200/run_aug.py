@@ -140,12 +140,21 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
     """run_aug.py:128-230 for the ControlNet-canny SD v1.5 architecture.  ``use_compile`` is accepted and ignored (the
     launch list is replayed by CUDA graphs, not traced).  Weights: ``state_dicts`` (diffusers-keyed) or deterministic
     random init -- no checkpoints exist offline."""
-    from .pipelines import SaspaControlNetPipeline, random_state_dicts
+    from .pipelines import SaspaControlNetPipeline, SaspaSDXLControlNetPipeline, random_state_dicts, sdxl_configs
 
     assert sampler in ["ddim", "unipcmultistep"]
-    if base_model not in ("sd_v1.5", "blip_diffusion", "tiny"):
-        raise NotImplementedError(f"base_model {base_model!r}: only the SD v1.5-architecture ControlNet path is built in round 1 (see DESIGN.md)")
     assert controlnet in ("canny",), "only the canny ControlNet is on the hot path"
+    if base_model in ("sd_xl-turbo", "sd_xl", "tiny_xl"):
+        # run_aug.py:188-199 (+ :223-228: for sd_xl-turbo the scheduler is rebuilt from the turbo config => trailing spacing)
+        cfg = "tiny_xl" if base_model == "tiny_xl" else "sdxl"
+        sds = state_dicts or random_state_dicts(cfg, 1234)
+        u, v, t1, t2 = sdxl_configs(cfg)
+        turbo = base_model != "sd_xl"
+        smp = ("unipc_sdxl_turbo" if sampler == "unipcmultistep" else "ddim_sdxl_turbo") if turbo else ("unipc" if sampler == "unipcmultistep" else "ddim")
+        return SaspaSDXLControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["text2"], unet_cfg=u, vae_cfg=v,
+                                                            text_cfg=t1, text2_cfg=t2, sampler=smp, device=device, img2img=bool(SDEdit))
+    if base_model not in ("sd_v1.5", "blip_diffusion", "tiny"):
+        raise NotImplementedError(f"base_model {base_model!r}: SD v1.5, SD-XL(-turbo) and BLIP-Diffusion ControlNet paths are built (see DESIGN.md)")
     cfg = "tiny" if base_model == "tiny" else "sd15"
     sds = state_dicts or random_state_dicts(cfg, 1234)
     from . import checkpoints as ck

@@ -31,6 +31,10 @@ class StepPlan:
     inputs: List[Optional[str]]   # buffer names per slot ("x", None for eps, history names)
     outputs: List[str]            # buffer names written
     coef: List[List[float]]
+    # optional clamped term (DDIM clip_sample): out[j] += clip_post[j] * clamp(sum_i clip_pre[i] * in[i], +-clip_range)
+    clip_pre: Optional[List[float]] = None
+    clip_post: Optional[List[float]] = None
+    clip_range: float = 0.0
 
 
 class _Lin:
@@ -67,12 +71,17 @@ class SchedulerBase:
     order = 1
     history_buffers: Sequence[str] = ()
 
-    def __init__(self, num_train_timesteps: int = 1000, steps_offset: int = 1, timestep_spacing: str = "leading"):
+    def __init__(self, num_train_timesteps: int = 1000, steps_offset: int = 1, timestep_spacing: str = "leading", set_alpha_to_one: bool = False,
+                 clip_sample: bool = False, clip_sample_range: float = 1.0):
         self.num_train = num_train_timesteps
         self.steps_offset = steps_offset
         self.spacing = timestep_spacing
         self.ac = alphas_cumprod(num_train_timesteps)
-        self.final_alpha_cumprod = self.ac[0]  # set_alpha_to_one = False
+        # SD v1.5's scheduler_config.json pins set_alpha_to_one=False, clip_sample=False.  SD-XL-turbo ships an
+        # EulerAncestral config without those keys, so DDIMScheduler.from_config (run_aug.py:228) falls back to DDIM's own
+        # defaults set_alpha_to_one=True, clip_sample=True (range 1.0): see make_scheduler("ddim_sdxl_turbo").
+        self.final_alpha_cumprod = 1.0 if set_alpha_to_one else self.ac[0]
+        self.clip_sample, self.clip_sample_range = clip_sample, clip_sample_range
         self.timesteps: np.ndarray = np.zeros(0, dtype=np.int64)
 
     # img2img (diffusers get_timesteps): keep the last int(n*strength) steps
@@ -106,6 +115,9 @@ class DDIMScheduler(SchedulerBase):
         a_p = self.ac[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         x, e = _Lin.basis(0, 2), _Lin.basis(1, 2)
         x0 = (x - np.sqrt(1 - a_t) * e) / np.sqrt(a_t)
+        if self.clip_sample:  # x_prev = sqrt(a_p) * clamp(x0) + sqrt(1-a_p) * e   (use_clipped_model_output=False: eps is kept)
+            return StepPlan(["x", None], ["x"], [(np.sqrt(1 - a_p) * e).v.tolist()], clip_pre=x0.v.tolist(), clip_post=[float(np.sqrt(a_p))],
+                            clip_range=float(self.clip_sample_range))
         nxt = np.sqrt(a_p) * x0 + np.sqrt(1 - a_p) * e
         return StepPlan(["x", None], ["x"], [nxt.v.tolist()])
 
@@ -304,6 +316,10 @@ def make_scheduler(name: str, **kw) -> SchedulerBase:
     name = name.lower()
     if name == "ddim":
         return DDIMScheduler(**kw)
+    if name == "ddim_sdxl_turbo":  # DDIMScheduler.from_config(<sdxl-turbo EulerAncestral config>): trailing spacing + DDIM defaults
+        return DDIMScheduler(**{**dict(timestep_spacing="trailing", set_alpha_to_one=True, clip_sample=True), **kw})
+    if name == "unipc_sdxl_turbo":
+        return UniPCMultistepScheduler(**{**dict(timestep_spacing="trailing"), **kw})
     if name in ("unipc", "unipcmultistep"):
         return UniPCMultistepScheduler(**kw)
     if name in ("pndm", "plms"):

@@ -131,6 +131,11 @@ def test_cfg_sched_step(cuda_device):
     assert torch.allclose(o1, e, atol=1e-6)
     ops.cfg_sched_step(None, ec, 0.0, [x, None], [o0], [[1.0, 2.0]])
     assert torch.allclose(o0, x + 2 * ec, atol=1e-6)
+    # clamped term (DDIM clip_sample): out = 0.6*e + 0.8*clamp(1.3*x - 0.7*e, -1, 1)
+    ops.cfg_sched_step(eu, ec, 2.0, [x, None], [o0], [[0.0, 0.6]], clip_pre=[1.3, -0.7], clip_post=[0.8], clip_range=1.0)
+    e2 = eu + 2.0 * (ec - eu)
+    ref = 0.6 * e2 + 0.8 * (1.3 * x - 0.7 * e2).clamp(-1, 1)
+    assert torch.allclose(o0, ref, atol=1e-5, rtol=1e-5) and ((1.3 * x - 0.7 * e2).abs() > 1).any()
 
 
 def test_vae_quantize(cuda_device):

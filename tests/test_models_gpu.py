@@ -51,7 +51,7 @@ def _bound(mine, ref32, refbf, floor=1e-2):
     return e_mine, e_bf
 
 
-def _unet_controlnet_case(ucfg_p, n, h, w, seed, text_dim):
+def _unet_controlnet_case(ucfg_p, n, h, w, seed, text_dim, pooled_dim=0):
     g = torch.Generator().manual_seed(seed)
     usd = ck.random_state_dict(ck.unet_shapes(ucfg_p), seed)
     csd = ck.random_state_dict(ck.controlnet_shapes(ucfg_p), seed + 1)
@@ -63,22 +63,31 @@ def _unet_controlnet_case(ucfg_p, n, h, w, seed, text_dim):
     cond = (torch.rand((n, 3, 8 * h, 8 * w), generator=g) > 0.9).float()
     t = 481.0
     scale = 0.75
+    added = addedb = addedm = None
+    if pooled_dim:  # SDXL "text_time" conditioning
+        pooled = torch.randn((n, pooled_dim), generator=g)
+        tid = torch.tensor([[8.0 * h, 8.0 * w, 0, 0, 8.0 * h, 8.0 * w]]).repeat(n, 1)
+        added = {"text_embeds": pooled, "time_ids": tid}
+        addedb = {"text_embeds": pooled.to(DEV, torch.bfloat16), "time_ids": tid.to(DEV)}
+        addedm = {"text_embeds": pooled.to(DEV, torch.bfloat16), "time_ids": tid.to(DEV)}
     with torch.no_grad():
-        d32, m32 = oc(lat, t, text, cond, scale)
-        e32 = ou(lat, t, text, d32, m32)
+        d32, m32 = oc(lat, t, text, cond, scale, added_cond_kwargs=added)
+        e32 = ou(lat, t, text, d32, m32, added_cond_kwargs=added)
         oub, ocb = copy.deepcopy(ou).to(DEV, torch.bfloat16), copy.deepcopy(oc).to(DEV, torch.bfloat16)
         lb, tb, cb = lat.to(DEV, torch.bfloat16), text.to(DEV, torch.bfloat16), cond.to(DEV, torch.bfloat16)
-        db, mb = ocb(lb, t, tb, cb, scale)
-        ebf = oub(lb, t, tb, db, mb).float().cpu()
+        db, mb = ocb(lb, t, tb, cb, scale, added_cond_kwargs=addedb)
+        ebf = oub(lb, t, tb, db, mb, added_cond_kwargs=addedb).float().cpu()
+        del oub, ocb
     unet, cn = snn.UNet(usd, ucfg_p, torch.device(DEV)), snn.ControlNet(csd, ucfg_p, torch.device(DEV))
     textb = text.to(DEV, torch.bfloat16)
     kv_u, kv_c = unet.text_kv(textb), cn.text_kv(textb)
     x2 = ops.nchw_f32_to_nhwc_bf16(lat.to(DEV))
     tv = torch.full((n,), t, dtype=torch.float32, device=DEV)
     ce = cn.cond_embedding(cond.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16))
-    st = unet.encode(x2, unet.time_embed(tv), kv_u, n, h, w)
-    cn.inject(x2, cn.time_embed(tv), kv_c, ce, scale, st)
-    eps = ops.nhwc_to_nchw_f32(unet.decode(st, unet.time_embed(tv), kv_u)).cpu()
+    aug_u, aug_c = unet.added_embed(addedm), cn.added_embed(addedm)
+    st = unet.encode(x2, unet.time_embed(tv, aug_u), kv_u, n, h, w)
+    cn.inject(x2, cn.time_embed(tv, aug_c), kv_c, ce, scale, st)
+    eps = ops.nhwc_to_nchw_f32(unet.decode(st, unet.time_embed(tv, aug_u), kv_u)).cpu()
     torch.cuda.synchronize()
     return eps, e32, ebf
 
@@ -99,6 +108,21 @@ def test_unet_controlnet_sd15_full_size(cuda_device):
     eps, e32, ebf = _unet_controlnet_case(ck.UNetConfig.sd15(), 2, 64, 64, 11, 768)
     e_mine, e_bf = _bound(eps, e32, ebf)
     print(f"sd15 UNet+ControlNet eps max-abs err: ours {e_mine:.4g}, torch-bf16 {e_bf:.4g}, max|eps| {e32.abs().max().item():.4g}")
+
+
+def test_unet_controlnet_tiny_xl(cuda_device):
+    """SDXL topology (DownBlock first, transformer depth 1/2/3, linear projections, text_time added conditioning), non-square."""
+    eps, e32, ebf = _unet_controlnet_case(ck.UNetConfig.tiny_xl(), 3, 16, 24, 12, 192, pooled_dim=96)
+    _bound(eps, e32, ebf)
+
+
+def test_unet_controlnet_sdxl_full_size(cuda_device):
+    """The real SDXL UNet (2.57 B) + ControlNet-canny-sdxl (1.25 B) architectures at 512x512 (latent 64x64; sd_xl-turbo's
+    training resolution and the reference's RESOLUTION, run_aug.py:536), batch 1, no CFG."""
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    eps, e32, ebf = _unet_controlnet_case(ck.UNetConfig.sdxl(), 1, 64, 64, 13, 2048, pooled_dim=1280)
+    e_mine, e_bf = _bound(eps, e32, ebf)
+    print(f"sdxl UNet+ControlNet eps max-abs err: ours {e_mine:.4g}, torch-bf16 {e_bf:.4g}, max|eps| {e32.abs().max().item():.4g}")
 
 
 @pytest.mark.parametrize("vcfg_name", ["tiny", "sd15"])
@@ -139,9 +163,43 @@ def test_clip_text_encoder(cuda_device, name):
     _bound(mine, r32, rbf)
 
 
+@pytest.mark.parametrize("name", ["tiny_g", "sdxl_g"])
+def test_clip_text_with_projection(cuda_device, name):
+    """SDXL text_encoder_2 (CLIPTextModelWithProjection, gelu): hidden_states[-2] and pooled text_embeds vs transformers."""
+    from tests.test_sdxl_cpu import text_models
+
+    tcfg = ck.CLIPTextConfig.tiny_g() if name == "tiny_g" else ck.CLIPTextConfig.sdxl_g()
+    sd = ck.random_state_dict(ck.clip_text_shapes(tcfg), 33)
+    _, ref = text_models(ck.CLIPTextConfig.tiny(), tcfg, ck.random_state_dict(ck.clip_text_shapes(ck.CLIPTextConfig.tiny()), 1), sd)
+    ids = synthetic_token_ids(6, batch=3, vocab=tcfg.vocab_size)
+    with torch.no_grad():
+        o32 = ref(ids, output_hidden_states=True)
+        obf = copy.deepcopy(ref).to(DEV, torch.bfloat16)(ids.to(DEV), output_hidden_states=True)
+    te = snn.CLIPTextEncoder(sd, torch.device(DEV), tcfg.num_attention_heads, tcfg.hidden_act, tcfg.layer_norm_eps)
+    pen, pooled = te(ids.to(DEV), penultimate=True, pooled=True)
+    _bound(pen.float().cpu(), o32.hidden_states[-2], obf.hidden_states[-2].float().cpu())
+    _bound(pooled.float().cpu(), o32[0], obf[0].float().cpu())
+    last = te(ids.to(DEV)).float().cpu()
+    _bound(last, o32.last_hidden_state, obf.last_hidden_state.float().cpu())
+
+
 def _psnr(a, b):
     mse = ((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean()
     return 99.0 if mse == 0 else 10 * math.log10(255.0 ** 2 / mse)
+
+
+def _check_pipeline(out, img_o, lat_o, img_b, lat_b, tag):
+    """Calibrated tolerance (module docstring): per-step latent max-abs error <= max(2 x stock-torch-bf16's error on the same graph,
+    1e-2 x max|latent|); image PSNR >= min(torch-bf16's PSNR - 3 dB, 40 dB).  (The recurrence amplifies bf16 rounding and tiny
+    random-init nets are not contractive, so an absolute bound would be a guess.)"""
+    assert len(out.latents_per_step) == len(lat_o)
+    for k, (a, b, c) in enumerate(zip(out.latents_per_step, lat_o, lat_b)):
+        e_mine, e_bf = (a.cpu() - b).abs().max().item(), (c - b).abs().max().item()
+        lim = max(2.0 * e_bf, 1e-2 * b.abs().max().item())
+        assert math.isfinite(e_mine) and e_mine <= lim, f"{tag} step {k}: ours {e_mine:.4g} vs torch-bf16 {e_bf:.4g} (max|x| {b.abs().max().item():.4g})"
+    p, p_bf = _psnr(np.stack(out.images), img_o), _psnr(img_b, img_o)
+    print(f"{tag}: final-latent err ours {e_mine:.4g} / torch-bf16 {e_bf:.4g}; image PSNR ours {p:.1f} dB / torch-bf16 {p_bf:.1f} dB")
+    assert p >= min(p_bf - 3.0, 40.0), (p, p_bf)
 
 
 @pytest.mark.parametrize("mode,sampler,steps,strength", [("t2i", "ddim", 6, 1.0), ("img2img", "unipc", 10, 0.5), ("t2i", "pndm", 5, 1.0)])
@@ -166,11 +224,35 @@ def test_pipeline_tiny_matches_oracle(cuda_device, mode, sampler, steps, strengt
         out = pipe(image=src, control_image=ctrl, **call)
     else:
         out = pipe(image=ctrl, **call)
-    assert len(out.latents_per_step) == len(lat_o)
-    # latents: relative max-abs per step (the recurrence amplifies bf16 rounding; tiny random-init nets are not contractive)
-    for k, (a, b) in enumerate(zip(out.latents_per_step, lat_o)):
-        rel = (a.cpu() - b).abs().max().item() / b.abs().max().item()
-        assert rel < 0.08, (k, rel)
-    p = _psnr(np.stack(out.images), img_o)
-    print(f"{mode}/{sampler}: final-latent rel err {rel:.4g}, image PSNR {p:.1f} dB")
-    assert p > 28.0, p
+    img_b, lat_b = opipe.to(DEV, torch.bfloat16)(ids, nids, ctrl, src if mode == "img2img" else None, generator=torch.Generator().manual_seed(1), **kw)
+    _check_pipeline(out, img_o, lat_o, img_b, lat_b, f"{mode}/{sampler}")
+
+
+@pytest.mark.parametrize("mode,sampler,steps,strength,gs", [("t2i", "ddim_sdxl_turbo", 4, 1.0, 0.0), ("img2img", "ddim_sdxl_turbo", 4, 0.5, 0.0),
+                                                            ("t2i", "unipc_sdxl_turbo", 3, 1.0, 5.0)])
+def test_pipeline_tiny_xl_matches_oracle(cuda_device, mode, sampler, steps, strength, gs):
+    """SD-XL(-turbo) pipeline (tiny same-topology models, two text encoders, added conditioning, 128x192) vs the fp32 oracle:
+    turbo settings (guidance 0 => no CFG, DDIM trailing with the clip_sample clamp), SDEdit, and a CFG run (negative pooled path)."""
+    from oracle.diffusers_restated.pipelines import OracleSDXLPipeline
+    from saspa_aug_b200.pipelines import SaspaSDXLControlNetPipeline, sdxl_configs
+    from tests.test_sdxl_cpu import text_models
+
+    sds = random_state_dicts("tiny_xl", 200)
+    ucfg, vcfg, tcfg, t2cfg = sdxl_configs("tiny_xl")
+    ou, oc, ov = om.UNet2DConditionModel(_ocfg(ucfg)), om.ControlNetModel(_ocfg(ucfg)), om.AutoencoderKL(_vcfg(vcfg))
+    ou.load_state_dict(sds["unet"]); oc.load_state_dict(sds["controlnet"]); ov.load_state_dict(sds["vae"])
+    t1, t2 = text_models(tcfg, t2cfg, sds["text"], sds["text2"])
+    opipe = OracleSDXLPipeline(ou, oc, ov, t1, t2, sampler)
+    src = np.stack([synthetic_source(s, 128, 192) for s in (3, 4)])
+    from oracle import clib
+    ctrl = np.repeat(clib.canny(src, 120, 200)[..., None], 3, axis=3)
+    ids = (synthetic_token_ids(9, batch=2, vocab=tcfg.vocab_size), synthetic_token_ids(11, batch=2, vocab=t2cfg.vocab_size))
+    nids = (synthetic_token_ids(10, batch=1, vocab=tcfg.vocab_size).expand(2, -1), synthetic_token_ids(12, batch=1, vocab=t2cfg.vocab_size).expand(2, -1))
+    kw = dict(num_inference_steps=steps, guidance_scale=gs, strength=strength, controlnet_conditioning_scale=0.75)
+    img_o, lat_o = opipe(ids, nids, ctrl, src if mode == "img2img" else None, generator=torch.Generator().manual_seed(1), **kw)
+    pipe = SaspaSDXLControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["text2"], unet_cfg=ucfg, vae_cfg=vcfg,
+                                                        text_cfg=tcfg, text2_cfg=t2cfg, sampler=sampler)
+    call = dict(prompt_ids=ids, negative_prompt_ids=nids, generator=torch.Generator().manual_seed(1), return_latents_per_step=True, output_type="np", **kw)
+    out = pipe(image=src, control_image=ctrl, **call) if mode == "img2img" else pipe(image=ctrl, **call)
+    img_b, lat_b = opipe.to(DEV, torch.bfloat16)(ids, nids, ctrl, src if mode == "img2img" else None, generator=torch.Generator().manual_seed(1), **kw)
+    _check_pipeline(out, img_o, lat_o, img_b, lat_b, f"sdxl {mode}/{sampler}")

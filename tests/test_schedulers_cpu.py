@@ -17,6 +17,12 @@ def _apply(plan, bufs, eps):
         for c, t in zip(row, ins):
             acc = acc + c * t
         outs.append(acc)
+    if plan.clip_range > 0:
+        c = torch.zeros_like(eps)
+        for w, t in zip(plan.clip_pre, ins):
+            c = c + w * t
+        c = c.clamp(-plan.clip_range, plan.clip_range)
+        outs = [o + w * c for o, w in zip(outs, plan.clip_post)]
     for nm, o in zip(plan.outputs, outs):
         bufs[nm] = o
 
@@ -24,7 +30,9 @@ def _apply(plan, bufs, eps):
 def _run(name, n, strength=None, seed=0):
     g = torch.Generator().manual_seed(seed)
     shape = (2, 4, 8, 8)
-    o = {"ddim": osched.DDIMScheduler, "unipc": osched.UniPCMultistepScheduler, "pndm": osched.PNDMScheduler}[name]()
+    from oracle.diffusers_restated.pipelines import make_scheduler as omake
+
+    o = omake(name)
     p = psched.make_scheduler(name)
     o.set_timesteps(n)
     p.set_timesteps(n)
@@ -61,6 +69,15 @@ def _run(name, n, strength=None, seed=0):
 def test_full_schedule(name, n):
     evals = _run(name, n)
     assert evals == (n + 1 if name == "pndm" else n)
+
+
+@pytest.mark.parametrize("name", ["ddim_sdxl_turbo", "unipc_sdxl_turbo"])
+@pytest.mark.parametrize("n,strength", [(1, None), (2, None), (4, None), (4, 0.5), (10, None)])
+def test_sdxl_turbo_schedules(name, n, strength):
+    """Trailing spacing; DDIM with diffusers' own defaults clip_sample=True / set_alpha_to_one=True (the clamp is active: x0 of
+    random inputs leaves [-1,1])."""
+    evals = _run(name, n, strength)
+    assert evals == (n if strength is None else min(int(n * strength), n))
 
 
 @pytest.mark.parametrize("name", ["ddim", "unipc"])
