@@ -142,15 +142,44 @@ class Transformer(nn.Module):
         return self.resblocks(x)
 
 
+class VisionTransformer(nn.Module):
+    """openai-clip ``VisionTransformer``: patch conv (no bias) -> [class_embedding; patches] + positional_embedding -> ln_pre ->
+    transformer (no mask) -> ln_post on the class token -> @ proj."""
+
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def forward(self, x):
+        x = self.conv1(x.type(self.conv1.weight.dtype))
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        cls = self.class_embedding.to(x.dtype) + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype, device=x.device)
+        x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
+        x = self.ln_pre(x)
+        x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
+        return self.ln_post(x[:, 0, :]) @ self.proj
+
+
 class CLIP(nn.Module):
     """RN50 defaults: embed_dim 1024, image 224, vision layers (3,4,6,3) width 64, context 77, vocab 49408,
-    transformer width 512 / 8 heads / 12 layers."""
+    transformer width 512 / 8 heads / 12 layers.  An int ``vision_layers`` selects the VisionTransformer tower as openai's CLIP.__init__
+    does (ViT-L/14: embed 768, vision_layers 24, vision_width 1024, vision_patch_size 14, text width 768 / 12 heads)."""
 
     def __init__(self, embed_dim=1024, image_resolution=224, vision_layers=(3, 4, 6, 3), vision_width=64, context_length=77, vocab_size=49408,
-                 transformer_width=512, transformer_heads=8, transformer_layers=12):
+                 transformer_width=512, transformer_heads=8, transformer_layers=12, vision_patch_size=None):
         super().__init__()
         self.context_length = context_length
-        self.visual = ModifiedResNet(vision_layers, embed_dim, vision_width * 32 // 64, image_resolution, vision_width)
+        if isinstance(vision_layers, (tuple, list)):
+            self.visual = ModifiedResNet(vision_layers, embed_dim, vision_width * 32 // 64, image_resolution, vision_width)
+        else:
+            self.visual = VisionTransformer(image_resolution, vision_patch_size, vision_width, vision_layers, vision_width // 64, embed_dim)
         mask = torch.empty(context_length, context_length).fill_(float("-inf")).triu_(1)
         self.transformer = Transformer(transformer_width, transformer_layers, transformer_heads, mask)
         self.vocab_size = vocab_size
@@ -173,3 +202,9 @@ class CLIP(nn.Module):
         x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
         x = self.ln_final(x).type(self.dtype)
         return x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ self.text_projection
+
+
+def clip_vit(embed_dim=768, v_width=1024, v_layers=24, patch=14, res=224, t_width=768, t_layers=12, vocab=49408, ctx=77) -> CLIP:
+    """CLIP with a VisionTransformer tower (defaults ViT-L/14); same keyword names as saspa_aug_b200.checkpoints.clip_vit_shapes."""
+    return CLIP(embed_dim=embed_dim, image_resolution=res, vision_layers=v_layers, vision_width=v_width, context_length=ctx, vocab_size=vocab,
+                transformer_width=t_width, transformer_heads=max(1, t_width // 64), transformer_layers=t_layers, vision_patch_size=patch)

@@ -115,6 +115,38 @@ class CLIPTextConfig:
                               projection_dim=96)
 
 
+@dataclass
+class Blip2Config:
+    """Salesforce/blipdiffusion(-controlnet) ``qformer/config.json`` (diffusers pipelines/blip_diffusion/modeling_blip2.py): BERT-style
+    Q-Former with ``num_query_tokens`` learned queries, cross-attending every ``cross_attention_frequency``-th layer to its own ViT."""
+    vocab_size: int = 30523
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    max_position_embeddings: int = 512
+    layer_norm_eps: float = 1e-12
+    cross_attention_frequency: int = 2
+    num_query_tokens: int = 16
+    vision_hidden_size: int = 1024
+    vision_intermediate_size: int = 4096
+    vision_num_hidden_layers: int = 23
+    vision_num_attention_heads: int = 16
+    image_size: int = 224
+    patch_size: int = 14
+    vision_layer_norm_eps: float = 1e-5
+
+    @staticmethod
+    def blipdiffusion() -> "Blip2Config":
+        return Blip2Config()
+
+    @staticmethod
+    def tiny() -> "Blip2Config":
+        return Blip2Config(vocab_size=500, hidden_size=64, num_hidden_layers=4, num_attention_heads=2, intermediate_size=128, max_position_embeddings=32,
+                           num_query_tokens=16, vision_hidden_size=128, vision_intermediate_size=256, vision_num_hidden_layers=3,
+                           vision_num_attention_heads=2, image_size=56, patch_size=14)
+
+
 Shapes = Iterator[Tuple[str, Tuple[int, ...]]]
 
 
@@ -294,6 +326,46 @@ def clip_text_shapes(cfg: CLIPTextConfig) -> Shapes:
         yield "text_projection.weight", (cfg.projection_dim, cfg.hidden_size)
 
 
+def qformer_shapes(cfg: Blip2Config) -> Shapes:
+    """State-dict layout of diffusers' Blip2QFormerModel (qformer/ of Salesforce/blipdiffusion-controlnet)."""
+    h, vh = cfg.hidden_size, cfg.vision_hidden_size
+    yield "query_tokens", (1, cfg.num_query_tokens, h)
+    yield "embeddings.word_embeddings.weight", (cfg.vocab_size, h)
+    yield "embeddings.position_embeddings.weight", (cfg.max_position_embeddings, h)
+    yield from _norm("embeddings.LayerNorm", h)
+    v = "visual_encoder."
+    n_pos = (cfg.image_size // cfg.patch_size) ** 2 + 1
+    yield v + "embeddings.class_embedding", (1, 1, vh)
+    yield v + "embeddings.position_embedding", (1, n_pos, vh)
+    yield v + "embeddings.patch_embedding.weight", (vh, 3, cfg.patch_size, cfg.patch_size)
+    yield from _norm(v + "pre_layernorm", vh)
+    for i in range(cfg.vision_num_hidden_layers):
+        q = f"{v}encoder.layers.{i}."
+        yield from _lin(q + "self_attn.qkv", vh, 3 * vh)
+        yield from _lin(q + "self_attn.projection", vh, vh)
+        yield from _norm(q + "layer_norm1", vh)
+        yield from _lin(q + "mlp.fc1", vh, cfg.vision_intermediate_size)
+        yield from _lin(q + "mlp.fc2", cfg.vision_intermediate_size, vh)
+        yield from _norm(q + "layer_norm2", vh)
+    yield from _norm(v + "post_layernorm", vh)
+    yield from _lin("proj_layer.dense1", h, 4 * h)
+    yield from _lin("proj_layer.dense2", 4 * h, h)
+    yield from _norm("proj_layer.LayerNorm", h)
+    for i in range(cfg.num_hidden_layers):
+        p = f"encoder.layer.{i}."
+        blocks = [("attention", h)] + ([("crossattention", vh)] if i % cfg.cross_attention_frequency == 0 else [])
+        for blk, kv in blocks:
+            yield from _lin(p + blk + ".attention.query", h, h)
+            yield from _lin(p + blk + ".attention.key", kv, h)
+            yield from _lin(p + blk + ".attention.value", kv, h)
+            yield from _lin(p + blk + ".output.dense", h, h)
+            yield from _norm(p + blk + ".output.LayerNorm", h)
+        for sfx in ("", "_query"):
+            yield from _lin(p + "intermediate" + sfx + ".dense", h, cfg.intermediate_size)
+            yield from _lin(p + "output" + sfx + ".dense", cfg.intermediate_size, h)
+            yield from _norm(p + "output" + sfx + ".LayerNorm", h)
+
+
 _RESIDUAL_OUT = ("conv2.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight", "out_proj.weight", "mlp.fc2.weight", "conv3.weight", "c_proj.weight")
 _ZERO_CONV = ("controlnet_down_blocks", "controlnet_mid_block", "controlnet_cond_embedding.conv_out")
 
@@ -306,7 +378,7 @@ def random_state_dict(shapes: Shapes, seed: int, zero_conv_std: float = 0.02, dt
     sd = {}
     for name, shape in shapes:
         if len(shape) >= 2:
-            if "embedding.weight" in name:
+            if "embedding.weight" in name or "embeddings.weight" in name or name.endswith(("class_embedding", "position_embedding", "query_tokens")):
                 std = 0.02
             else:
                 fan_in = 1
@@ -318,7 +390,7 @@ def random_state_dict(shapes: Shapes, seed: int, zero_conv_std: float = 0.02, dt
                 if any(z in name for z in _ZERO_CONV):
                     std = zero_conv_std
             t = torch.randn(shape, generator=g) * std
-        elif "norm" in name and name.endswith("weight"):
+        elif "norm" in name.lower() and name.endswith("weight"):
             t = 1.0 + 0.05 * torch.randn(shape, generator=g)
         else:
             t = 0.02 * torch.randn(shape, generator=g)
@@ -421,6 +493,49 @@ def clip_rn50_shapes(embed_dim=1024, width=64, layers=(3, 4, 6, 3), t_width=512,
     yield from _norm("ln_final", t_width)
 
 
+def _clip_text_tower_shapes(t_width, t_layers, vocab, ctx, embed_dim) -> Shapes:
+    yield "positional_embedding", (ctx, t_width)
+    yield "text_projection", (t_width, embed_dim)
+    yield "logit_scale", ()
+    for i in range(t_layers):
+        q = f"transformer.resblocks.{i}."
+        yield q + "attn.in_proj_weight", (3 * t_width, t_width)
+        yield q + "attn.in_proj_bias", (3 * t_width,)
+        yield from _lin(q + "attn.out_proj", t_width, t_width)
+        yield from _norm(q + "ln_1", t_width)
+        yield from _lin(q + "mlp.c_fc", t_width, 4 * t_width)
+        yield from _lin(q + "mlp.c_proj", 4 * t_width, t_width)
+        yield from _norm(q + "ln_2", t_width)
+    yield "token_embedding.weight", (vocab, t_width)
+    yield from _norm("ln_final", t_width)
+
+
+def clip_vit_shapes(embed_dim=768, v_width=1024, v_layers=24, patch=14, res=224, t_width=768, t_layers=12, vocab=49408, ctx=77) -> Shapes:
+    """openai-clip state-dict layout of a VisionTransformer CLIP (defaults: ViT-L/14, BASELINE config 5): ``clip/model.py``
+    VisionTransformer (conv1 patch embedding without bias, class_embedding, positional_embedding, ln_pre, transformer, ln_post, proj)."""
+    v = "visual."
+    yield v + "conv1.weight", (v_width, 3, patch, patch)
+    yield v + "class_embedding", (v_width,)
+    yield v + "positional_embedding", ((res // patch) ** 2 + 1, v_width)
+    yield from _norm(v + "ln_pre", v_width)
+    for i in range(v_layers):
+        q = f"{v}transformer.resblocks.{i}."
+        yield q + "attn.in_proj_weight", (3 * v_width, v_width)
+        yield q + "attn.in_proj_bias", (3 * v_width,)
+        yield from _lin(q + "attn.out_proj", v_width, v_width)
+        yield from _norm(q + "ln_1", v_width)
+        yield from _lin(q + "mlp.c_fc", v_width, 4 * v_width)
+        yield from _lin(q + "mlp.c_proj", 4 * v_width, v_width)
+        yield from _norm(q + "ln_2", v_width)
+    yield from _norm(v + "ln_post", v_width)
+    yield v + "proj", (v_width, embed_dim)
+    yield from _clip_text_tower_shapes(t_width, t_layers, vocab, ctx, embed_dim)
+
+
+def clip_vit_tiny_kwargs() -> dict:
+    return dict(embed_dim=64, v_width=128, v_layers=2, patch=14, res=56, t_width=64, t_layers=2, vocab=1000, ctx=77)
+
+
 def random_filter_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tensor]:
     """He-normal conv/linear weights (ReLU nets), BatchNorm affine ~ N(1,.1)/N(0,.1) with non-trivial running stats,
     the last BN scale of each residual branch damped (x0.5) so depth does not blow the activations up."""
@@ -435,13 +550,15 @@ def random_filter_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tenso
             t = 0.1 * torch.randn(shape, generator=g)
         elif "positional_embedding" in name or name == "token_embedding.weight":
             t = 0.02 * torch.randn(shape, generator=g)
-        elif name == "text_projection":
+        elif name in ("text_projection", "visual.proj"):
             t = torch.randn(shape, generator=g) * shape[0] ** -0.5
+        elif name == "visual.class_embedding":
+            t = 0.02 * torch.randn(shape, generator=g)
         elif len(shape) >= 2:
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            relu_net = name.startswith(("features.", "visual.", "attentions.")) and "attnpool" not in name
+            relu_net = name.startswith(("features.", "visual.", "attentions.")) and "attnpool" not in name and "transformer." not in name
             std = math.sqrt((2.0 if relu_net else 1.0) / fan_in)
             if name.endswith(_RESIDUAL_OUT) and not relu_net:
                 std /= math.sqrt(2.0)

@@ -42,11 +42,12 @@ class SyntheticUtils(BaseUtils):
     num_classes = 100
 
     def __init__(self, print_func: Callable = print, root: str = None, n_images: int = 16, seed_base: int = 0, size=(512, 512),
-                 wsdan_seed: int = 4242, clip_seed: int = 777, net: str = "resnet50"):
+                 wsdan_seed: int = 4242, clip_seed: int = 777, net: str = "resnet50", clip_model: str = "RN50"):
         super().__init__(print_func)
         self.root = Path(root or os.environ.get("SASPA_SYNTHETIC_ROOT", "/tmp/saspa_synthetic"))
         self.n_images, self.seed_base, self.size = n_images, seed_base, size
         self.wsdan_seed, self.clip_seed, self.net = wsdan_seed, clip_seed, net
+        self.clip_model = clip_model  # "RN50" (the reference, all_utils/utils.py:253) | "ViT-L/14" (BASELINE config 5)
         self.images_path = self.root / "images"
         self.original_images_paths = [str(self.images_path / f"syn_{seed_base + i:07d}.png") for i in range(n_images)]
 
@@ -68,14 +69,19 @@ class SyntheticUtils(BaseUtils):
         return {p: i % self.num_classes for i, p in enumerate(self.original_images_paths)}
 
     def load_filter_models(self, ds_utils, device):
-        """Random-init WSDAN_CAL + CLIP RN50 of the reference architectures (no checkpoints offline)."""
+        """Random-init WSDAN_CAL + CLIP (RN50 | ViT-L/14) of the reference architectures (no checkpoints offline)."""
         from . import checkpoints as ck
-        from .filter_nets import CLIPRN50, WSDANClassifier
+        from .filter_nets import CLIPRN50, CLIPViT, WSDANClassifier
         from .pipelines import SyntheticTokenizer
 
         wsd = ck.random_filter_state_dict(ck.wsdan_shapes(self.num_classes, self.net), self.wsdan_seed)
-        csd = ck.random_filter_state_dict(ck.clip_rn50_shapes(), self.clip_seed)
-        return WSDANClassifier(wsd, self.num_classes, self.net, device), CLIPRN50(csd, device), SyntheticTokenizer()
+        if self.clip_model == "RN50":
+            clip = CLIPRN50(ck.random_filter_state_dict(ck.clip_rn50_shapes(), self.clip_seed), device)
+        elif self.clip_model == "ViT-L/14":
+            clip = CLIPViT(ck.random_filter_state_dict(ck.clip_vit_shapes(), self.clip_seed), device)
+        else:
+            raise ValueError(f"clip_model {self.clip_model!r}: RN50 and ViT-L/14 are built")
+        return WSDANClassifier(wsd, self.num_classes, self.net, device), clip, SyntheticTokenizer()
 
 
 DS_UTILS_DICT: Dict[str, Callable] = {"synthetic": SyntheticUtils}

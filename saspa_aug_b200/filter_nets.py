@@ -96,7 +96,45 @@ class WSDANClassifier:
         return ops.fc_f32(fm, self.fc_w, None)
 
 
-class CLIPRN50:
+class _CLIPTextTower:
+    """openai-clip text side shared by the RN50 and ViT models: token + positional embedding -> causal pre-LN transformer (QuickGELU)
+    -> ln_final -> features at the EOT token (argmax id, all_utils/utils.py:134) @ text_projection."""
+
+    def _init_text(self, sd: SD, dev, text_heads: int):
+        self.text_heads = text_heads
+        self.tok = snn._bf(sd["token_embedding.weight"], dev)
+        self.tpos = snn._bf(sd["positional_embedding"], dev)
+        self.layers = []
+        i = 0
+        while f"transformer.resblocks.{i}.ln_1.weight" in sd:
+            q = f"transformer.resblocks.{i}."
+            self.layers.append({"ln1": snn.Norm(sd, q + "ln_1", dev), "ln2": snn.Norm(sd, q + "ln_2", dev),
+                                "qkv": snn.Linear(sd, "", dev, weight=sd[q + "attn.in_proj_weight"], bias=sd[q + "attn.in_proj_bias"]),
+                                "o": snn.Linear(sd, q + "attn.out_proj", dev), "fc1": snn.Linear(sd, q + "mlp.c_fc", dev),
+                                "fc2": snn.Linear(sd, q + "mlp.c_proj", dev)})
+            i += 1
+        self.ln_final = snn.Norm(sd, "ln_final", dev)
+        self.text_proj_t = snn._bf(sd["text_projection"].t().contiguous(), dev)  # [embed, width] K-major
+        self.logit_scale = float(sd["logit_scale"].exp())
+
+    def encode_text(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids int64 [p, 77] -> fp32 [p, embed]."""
+        p, t = ids.shape
+        c = self.tok.shape[1]
+        h = ops.add(self.tok.index_select(0, ids.reshape(-1)), self.tpos[:t].repeat(p, 1))
+        for L in self.layers:
+            y = ops.layernorm(h, 1e-5, L["ln1"].g, L["ln1"].b)
+            qkv = L["qkv"](y).view(p, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.text_heads, causal=True)
+            L["o"](a.view(p * t, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, 1e-5, L["ln2"].g, L["ln2"].b)
+            L["fc2"](L["fc1"](y, act=ACT_QUICKGELU), out=h, residual=h, beta=1.0)
+        x = ops.layernorm(h, 1e-5, self.ln_final.g, self.ln_final.b).view(p, t, c)
+        eot = x[torch.arange(p, device=x.device), ids.argmax(dim=-1)].contiguous()  # index plumbing
+        return ops.gemm(eot, self.text_proj_t, out_fp32=True)
+
+
+class CLIPRN50(_CLIPTextTower):
     def __init__(self, sd: SD, device="cuda", heads: int = 32, text_heads: int = 8):
         dev = torch.device(device)
         self.dev, self.heads, self.text_heads = dev, heads, text_heads
@@ -116,21 +154,7 @@ class CLIPRN50:
         self.kv = snn.Linear(sd, "", dev, weight=torch.cat([sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0),
                              bias=torch.cat([sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0))
         self.c = snn.Linear(sd, a + "c_proj", dev)
-        # text tower
-        self.tok = snn._bf(sd["token_embedding.weight"], dev)
-        self.tpos = snn._bf(sd["positional_embedding"], dev)
-        self.layers = []
-        i = 0
-        while f"transformer.resblocks.{i}.ln_1.weight" in sd:
-            q = f"transformer.resblocks.{i}."
-            self.layers.append({"ln1": snn.Norm(sd, q + "ln_1", dev), "ln2": snn.Norm(sd, q + "ln_2", dev),
-                                "qkv": snn.Linear(sd, "", dev, weight=sd[q + "attn.in_proj_weight"], bias=sd[q + "attn.in_proj_bias"]),
-                                "o": snn.Linear(sd, q + "attn.out_proj", dev), "fc1": snn.Linear(sd, q + "mlp.c_fc", dev),
-                                "fc2": snn.Linear(sd, q + "mlp.c_proj", dev)})
-            i += 1
-        self.ln_final = snn.Norm(sd, "ln_final", dev)
-        self.text_proj_t = snn._bf(sd["text_projection"].t().contiguous(), dev)  # [embed, width] K-major
-        self.logit_scale = float(sd["logit_scale"].exp())
+        self._init_text(sd, dev, text_heads)
 
     def encode_image(self, x: torch.Tensor) -> torch.Tensor:
         """x bf16 NHWC [n,224,224,8] (CLIP-normalised) -> fp32 [n, 1024]."""
@@ -152,21 +176,37 @@ class CLIPRN50:
         a = ops.attention(q.view(n, 1, c), kv[..., :c], kv[..., c:], self.heads)
         return self.c(a.view(n, c), out_fp32=True)
 
-    def encode_text(self, ids: torch.Tensor) -> torch.Tensor:
-        """ids int64 [p, 77] -> fp32 [p, 1024] (features at the EOT token = argmax id, all_utils/utils.py:134)."""
-        p, t = ids.shape
-        c = self.tok.shape[1]
-        h = ops.add(self.tok.index_select(0, ids.reshape(-1)), self.tpos[:t].repeat(p, 1))
-        for L in self.layers:
-            y = ops.layernorm(h, 1e-5, L["ln1"].g, L["ln1"].b)
-            qkv = L["qkv"](y).view(p, t, 3 * c)
-            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.text_heads, causal=True)
-            L["o"](a.view(p * t, c), out=h, residual=h, beta=1.0)
-            y = ops.layernorm(h, 1e-5, L["ln2"].g, L["ln2"].b)
-            L["fc2"](L["fc1"](y, act=ACT_QUICKGELU), out=h, residual=h, beta=1.0)
-        x = ops.layernorm(h, 1e-5, self.ln_final.g, self.ln_final.b).view(p, t, c)
-        eot = x[torch.arange(p, device=x.device), ids.argmax(dim=-1)].contiguous()  # index plumbing
-        return ops.gemm(eot, self.text_proj_t, out_fp32=True)
+
+class CLIPViT(_CLIPTextTower):
+    """openai-clip VisionTransformer CLIP (ViT-L/14 for BASELINE config 5; ``clip.load`` at all_utils/utils.py:253 takes the model
+    name) on the same kernels: snn.ViTEncoder for the tower, then ln_post on the class token and ``@ proj``."""
+
+    input_channels = 3
+
+    def __init__(self, sd: SD, device="cuda", text_heads: Optional[int] = None):
+        dev = torch.device(device)
+        self.dev = dev
+        v = "visual."
+        width = sd[v + "conv1.weight"].shape[0]
+        layers = []
+        i = 0
+        while f"{v}transformer.resblocks.{i}.ln_1.weight" in sd:
+            q = f"{v}transformer.resblocks.{i}."
+            layers.append(snn.ViTEncoder._layer(sd, dev, sd[q + "attn.in_proj_weight"], sd[q + "attn.in_proj_bias"], q + "attn.out_proj", q + "ln_1", q + "ln_2",
+                                                q + "mlp.c_fc", q + "mlp.c_proj"))
+            i += 1
+        self.tower = snn.ViTEncoder(dev, patch_w=sd[v + "conv1.weight"], class_emb=sd[v + "class_embedding"], pos_emb=sd[v + "positional_embedding"],
+                                    pre_ln=snn.Norm(sd, v + "ln_pre", dev), layers=layers, post_ln=None, heads=width // 64, act=ACT_QUICKGELU, eps=1e-5)
+        self.ln_post = snn.Norm(sd, v + "ln_post", dev)
+        self.proj_t = snn._bf(sd[v + "proj"].t().contiguous(), dev)  # [embed, width] K-major
+        self.resolution = self.tower.patch * int(round((sd[v + "positional_embedding"].shape[0] - 1) ** 0.5))
+        self._init_text(sd, dev, text_heads or max(1, sd["ln_final.weight"].shape[0] // 64))
+
+    def encode_image(self, x: torch.Tensor) -> torch.Tensor:
+        """x bf16 NHWC [n,R,R,3] (CLIP-normalised) -> fp32 [n, embed]."""
+        h = self.tower(x, apply_post_ln=False)
+        cls = ops.layernorm(h[:, 0].contiguous(), 1e-5, self.ln_post.g, self.ln_post.b)
+        return ops.gemm(cls, self.proj_t, out_fp32=True)
 
 
 class AugmentationFilter:
@@ -201,13 +241,14 @@ class AugmentationFilter:
                 margin[i0:i1] = m
             if self.clip is not None:
                 # Resize(224): shorter side -> 224 keeping aspect (bicubic), then CenterCrop(224)
+                R = getattr(self.clip, "resolution", 224)
                 if H <= W:
-                    oh, ow = 224, int(224 * W / H)
+                    oh, ow = R, int(R * W / H)
                 else:
-                    oh, ow = int(224 * H / W), 224
+                    oh, ow = int(R * H / W), R
                 r = ops.resize_pil(img, oh, ow, "bicubic")
-                cy, cx = int(round((oh - 224) / 2.0)), int(round((ow - 224) / 2.0))
-                x = ops.crop_normalize(r, cy, cx, 224, 224, CLIP_MEAN, CLIP_STD, out_c=8)
+                cy, cx = int(round((oh - R) / 2.0)), int(round((ow - R) / 2.0))
+                x = ops.crop_normalize(r, cy, cx, R, R, CLIP_MEAN, CLIP_STD, out_c=getattr(self.clip, "input_channels", 8))
                 feats = self.clip.encode_image(x)
                 lg, arg = ops.clip_score_argmax(feats, self.text_features, self.clip.logit_scale)
                 sem[i0:i1] = (arg == 0).to(torch.uint8)

@@ -35,18 +35,20 @@ class SyntheticTokenizer:
         self.vocab_size, self.model_max_length = vocab_size, model_max_length
         self.pad_id = vocab_size - 1 if pad_id is None else pad_id  # SDXL's tokenizer_2 pads with "!" (id 0)
 
-    def encode(self, text: str) -> List[int]:
+    def encode(self, text: str, max_length: Optional[int] = None) -> List[int]:
         import re
 
+        L = max_length or self.model_max_length
         words = [w for w in re.split(r"[^0-9a-zA-Z]+", text.lower()) if w]
-        ids = [1 + zlib.crc32(w.encode()) % (self.vocab_size - 3) for w in words][: self.model_max_length - 2]
+        ids = [1 + zlib.crc32(w.encode()) % (self.vocab_size - 3) for w in words][: L - 2]
         ids = [self.vocab_size - 2] + ids + [self.vocab_size - 1]
-        return ids + [self.pad_id] * (self.model_max_length - len(ids))
+        return ids + [self.pad_id] * (L - len(ids))
 
-    def __call__(self, texts: Union[str, Sequence[str]]) -> torch.Tensor:
+    def __call__(self, texts: Union[str, Sequence[str]], max_length: Optional[int] = None) -> torch.Tensor:
+        """padding="max_length", truncation=True semantics: BOS + words + EOS, truncated so EOS stays last, padded to max_length."""
         if isinstance(texts, str):
             texts = [texts]
-        return torch.tensor([self.encode(t) for t in texts], dtype=torch.int64)
+        return torch.tensor([self.encode(t, max_length) for t in texts], dtype=torch.int64)
 
 
 @dataclass
@@ -363,6 +365,164 @@ class SaspaSDXLControlNetPipeline(SaspaControlNetPipeline):
         return text, neg, added
 
 
+class SyntheticBertTokenizer:
+    """Deterministic stand-in for the Q-Former's BertTokenizer (no vocabulary offline): [CLS]=101, words -> 103 + crc32 % (vocab-103),
+    [SEP]=102; no padding (the subject category is one short string per dataset, run_aug.py:444-456)."""
+
+    def __init__(self, vocab_size: int = 30523, max_length: int = 32):
+        self.vocab_size, self.max_length = vocab_size, max_length
+
+    def encode(self, text: str) -> List[int]:
+        import re
+
+        words = [w for w in re.split(r"[^0-9a-zA-Z]+", text.lower()) if w][: self.max_length - 2]
+        return [101] + [103 + zlib.crc32(w.encode()) % (self.vocab_size - 103) for w in words] + [102]
+
+    def __call__(self, texts: Union[str, Sequence[str]]) -> List[torch.Tensor]:
+        if isinstance(texts, str):
+            texts = [texts]
+        return [torch.tensor(self.encode(t), dtype=torch.int64) for t in texts]
+
+
+def build_blip_prompt(prompts: Sequence[str], tgt_subjects: Sequence[str], prompt_strength: float = 1.0, prompt_reps: int = 20) -> List[str]:
+    """BlipDiffusionControlNetPipeline._build_prompt: "a {target subject} {prompt}", repeated int(strength*reps) times, comma-joined
+    (the repetition amplifies the prompt against the 16 subject tokens)."""
+    out = []
+    for prompt, tgt in zip(prompts, tgt_subjects):
+        one = f"a {tgt} {prompt.strip()}"
+        out.append(", ".join([one] * int(prompt_strength * prompt_reps)))
+    return out
+
+
+class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
+    """BLIP-Diffusion + ControlNet-canny (run_aug.py:185-187 builds diffusers' BlipDiffusionControlNetPipeline from
+    "Salesforce/blipdiffusion-controlnet"; called with the kwargs of run_aug.py:243-250,268-271).
+
+    Following diffusers 0.32.2 pipelines/controlnet/pipeline_controlnet_blip_diffusion.py:
+      * reference_image -> BlipImageProcessor (PIL bicubic to 224, /255, CLIP mean/std) -> Blip2QFormerModel(image, source subject)
+        -> 16 subject embeddings [B,16,768];
+      * prompt = _build_prompt(prompt, target subject); CLIP ids padded/truncated to 77-16; ContextCLIPTextModel splices the subject
+        embeddings after ``ctx_begin_pos`` (=2) token embeddings -> text [B,77,768];
+      * CFG against ``neg_prompt`` (plain CLIP encode, 77 ids); PNDM with skip_prk_steps (PLMS); ControlNet conditioning scale 1.0
+        (the pipeline passes none); latents = randn * init_noise_sigma; VAE decode; postprocess.
+    The subject embedding is step- and prompt-invariant: it is cached per (reference image bytes, subject ids)."""
+
+    def __init__(self, *a, qformer: snn.QFormer = None, qformer_tokenizer=None, ctx_begin_pos: int = 2, **k):
+        k.setdefault("sampler", "pndm")
+        super().__init__(*a, **k)
+        self.qformer = qformer
+        self.qformer_tokenizer = qformer_tokenizer or SyntheticBertTokenizer(qformer.cfg.vocab_size, qformer.cfg.max_position_embeddings)
+        self.ctx_begin_pos = ctx_begin_pos
+        self._subject_cache = {}
+
+    @classmethod
+    def from_state_dicts(cls, unet_sd, controlnet_sd, vae_sd, text_sd, qformer_sd, *, unet_cfg=None, vae_cfg=None, text_cfg=None, qformer_cfg=None,
+                         device="cuda", tokenizer=None, qformer_tokenizer=None, ctx_begin_pos: int = 2):
+        unet_cfg = unet_cfg or ck.UNetConfig.sd15()
+        vae_cfg = vae_cfg or ck.VAEConfig.sd15()
+        text_cfg = text_cfg or ck.CLIPTextConfig.sd15()
+        qformer_cfg = qformer_cfg or ck.Blip2Config.blipdiffusion()
+        dev = torch.device(device)
+        unet = snn.UNet(unet_sd, unet_cfg, dev)
+        cn = snn.ControlNet(controlnet_sd, unet_cfg, dev) if controlnet_sd is not None else None
+        dec = snn.VAEDecoder(vae_sd, vae_cfg, dev)
+        te = snn.CLIPTextEncoder(text_sd, dev, text_cfg.num_attention_heads, text_cfg.hidden_act, text_cfg.layer_norm_eps)
+        qf = snn.QFormer(qformer_sd, qformer_cfg, dev)
+        tok = tokenizer or SyntheticTokenizer(text_cfg.vocab_size, text_cfg.max_position_embeddings)
+        return cls(unet, cn, dec, None, te, tok, "pndm", device, vae_cfg, qformer=qf, qformer_tokenizer=qformer_tokenizer, ctx_begin_pos=ctx_begin_pos)
+
+    @classmethod
+    def random_init(cls, config: str = "blip", seed: int = 1234, **kw):
+        cfgs = blip_configs(config)
+        sds = random_state_dicts(config, seed)
+        return cls.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["qformer"], unet_cfg=cfgs[0], vae_cfg=cfgs[1],
+                                    text_cfg=cfgs[2], qformer_cfg=cfgs[3], **kw)
+
+    # ---- subject embedding (once per reference image x subject) ------------------------------------------------------------
+    def preprocess_reference(self, reference_u8: torch.Tensor) -> torch.Tensor:
+        """u8 [n,H,W,3] (device) -> bf16 NHWC [n,S,S,3]: BlipImageProcessor.preprocess (bit-exact PIL bicubic on the device)."""
+        from .filter_nets import CLIP_MEAN, CLIP_STD
+
+        S = self.qformer.cfg.image_size
+        r = reference_u8 if reference_u8.shape[1:3] == (S, S) else ops.resize_pil(reference_u8, S, S, "bicubic")
+        return ops.crop_normalize(r, 0, 0, S, S, CLIP_MEAN, CLIP_STD, out_c=3)
+
+    def get_query_embeddings(self, reference_u8: torch.Tensor, subject_ids: Sequence[torch.Tensor]) -> torch.Tensor:
+        """-> bf16 [n,16,hidden].  Samples are grouped by subject length (the reference pads + masks; subjects of one run are one string)."""
+        n = reference_u8.shape[0]
+        out = torch.empty((n, self.qformer.cfg.num_query_tokens, self.qformer.cfg.hidden_size), dtype=BF16, device=self.device)
+        groups = {}
+        for i, ids in enumerate(subject_ids):
+            groups.setdefault(int(ids.numel()), []).append(i)
+        for _, idx in groups.items():
+            sel = torch.tensor(idx, device=self.device)
+            img = self.preprocess_reference(reference_u8.index_select(0, sel).contiguous())
+            ids = torch.stack([subject_ids[i].reshape(-1) for i in idx]).to(self.device)
+            out[sel] = self.qformer(img, ids)
+        return out
+
+    def encode_subject_prompt(self, prompt_ids: torch.Tensor, query_embeds: torch.Tensor) -> torch.Tensor:
+        return self.text_encoder(prompt_ids.to(self.device), ctx_embeddings=query_embeds, ctx_begin_pos=self.ctx_begin_pos)
+
+    @torch.no_grad()
+    def __call__(self, prompt: Union[str, List[str], None] = None, reference_image=None, condtioning_image=None,
+                 source_subject_category: Union[str, List[str], None] = None, target_subject_category: Union[str, List[str], None] = None,
+                 latents: Optional[torch.Tensor] = None, guidance_scale: float = 7.5, height: int = 512, width: int = 512,
+                 num_inference_steps: int = 50, generator: Optional[torch.Generator] = None, neg_prompt: Optional[str] = "",
+                 prompt_strength: float = 1.0, prompt_reps: int = 20, output_type: str = "pil", prompt_ids: Optional[torch.Tensor] = None,
+                 neg_ids: Optional[torch.Tensor] = None, subject_ids=None, return_latents_per_step: bool = False, **unused) -> PipelineOutput:
+        ref_u8 = self._to_u8_batch(reference_image)
+        control_u8 = self._to_u8_batch(condtioning_image)
+        nq = self.qformer.cfg.num_query_tokens
+        if prompt_ids is None:
+            prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+            tgt = [target_subject_category] * len(prompts) if isinstance(target_subject_category, str) else list(target_subject_category)
+            full = build_blip_prompt(prompts, tgt, prompt_strength, prompt_reps)
+            prompt_ids = self.tokenizer(full, max_length=self.tokenizer.model_max_length - nq)  # encode_prompt: max_len = 77 - 16
+        B = prompt_ids.shape[0]
+        if subject_ids is None:
+            src = [source_subject_category] * B if isinstance(source_subject_category, str) else list(source_subject_category)
+            subject_ids = self.qformer_tokenizer(src)
+        elif isinstance(subject_ids, torch.Tensor):
+            subject_ids = list(subject_ids)
+        if ref_u8.shape[0] == 1 and B > 1:
+            ref_u8 = ref_u8.expand(B, -1, -1, -1).contiguous()
+        if control_u8.shape[0] == 1 and B > 1:
+            control_u8 = control_u8.expand(B, -1, -1, -1).contiguous()
+        if control_u8.shape[1:3] != (height, width):
+            raise ValueError(f"condtioning_image is {tuple(control_u8.shape[1:3])}, height/width say {(height, width)}: the reference passes the "
+                             "control image's own size (run_aug.py:270-271)")
+        query = self.get_query_embeddings(ref_u8, subject_ids)
+        text = self.encode_subject_prompt(prompt_ids, query)
+        neg = None
+        if guidance_scale > 1.0:
+            neg = self.encode_prompt_ids(neg_ids) if neg_ids is not None else self._neg_embeds(neg_prompt, B).contiguous()
+        shape = (B, self.vae_cfg.latent_channels, height // 8, width // 8)
+        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=torch.float32)
+        per_step = [] if return_latents_per_step else None
+        cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
+        out = self.generate_batch(text, neg, control_u8, None, noise=noise.to(self.device), num_inference_steps=num_inference_steps,
+                                  guidance_scale=guidance_scale, controlnet_conditioning_scale=1.0, step_callback=cb)
+        arr = out.cpu().numpy()
+        if output_type == "pil":
+            from PIL import Image
+
+            images = [Image.fromarray(a) for a in arr]
+        else:
+            images = [a for a in arr]
+        res = PipelineOutput(images=images, nsfw_content_detected=None, latents_per_step=per_step)
+        res.query_embeds, res.text_embeds = query, (torch.cat([neg, text]) if neg is not None else text)
+        return res
+
+
+def blip_configs(config: str):
+    if config == "blip":
+        return ck.UNetConfig.sd15(), ck.VAEConfig.sd15(), ck.CLIPTextConfig.sd15(), ck.Blip2Config.blipdiffusion()
+    if config == "tiny_blip":
+        return ck.UNetConfig.tiny(), ck.VAEConfig.tiny(), ck.CLIPTextConfig.tiny(), ck.Blip2Config.tiny()
+    raise ValueError(config)
+
+
 def sdxl_configs(config: str):
     if config == "sdxl":
         return ck.UNetConfig.sdxl(), ck.VAEConfig.sdxl(), ck.CLIPTextConfig.sd15(), ck.CLIPTextConfig.sdxl_g()
@@ -380,6 +540,15 @@ def random_state_dicts(config: str = "sd15", seed: int = 1234) -> dict:
             "vae": ck.random_state_dict(ck.vae_shapes(vcfg), seed + 2),
             "text": ck.random_state_dict(ck.clip_text_shapes(tcfg), seed + 3),
             "text2": ck.random_state_dict(ck.clip_text_shapes(t2cfg), seed + 4),
+        }
+    if config in ("blip", "tiny_blip"):
+        ucfg, vcfg, tcfg, qcfg = blip_configs(config)
+        return {
+            "unet": ck.random_state_dict(ck.unet_shapes(ucfg), seed),
+            "controlnet": ck.random_state_dict(ck.controlnet_shapes(ucfg), seed + 1),
+            "vae": ck.random_state_dict(ck.vae_shapes(vcfg), seed + 2),
+            "text": ck.random_state_dict(ck.clip_text_shapes(tcfg), seed + 3),
+            "qformer": ck.random_state_dict(ck.qformer_shapes(qcfg), seed + 5),
         }
     if config == "tiny":
         ucfg, vcfg, tcfg = ck.UNetConfig.tiny(), ck.VAEConfig.tiny(), ck.CLIPTextConfig.tiny()

@@ -140,7 +140,8 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
     """run_aug.py:128-230 for the ControlNet-canny SD v1.5 architecture.  ``use_compile`` is accepted and ignored (the
     launch list is replayed by CUDA graphs, not traced).  Weights: ``state_dicts`` (diffusers-keyed) or deterministic
     random init -- no checkpoints exist offline."""
-    from .pipelines import SaspaControlNetPipeline, SaspaSDXLControlNetPipeline, random_state_dicts, sdxl_configs
+    from .pipelines import (SaspaBlipControlNetPipeline, SaspaControlNetPipeline, SaspaSDXLControlNetPipeline, blip_configs, random_state_dicts,
+                            sdxl_configs)
 
     assert sampler in ["ddim", "unipcmultistep"]
     assert controlnet in ("canny",), "only the canny ControlNet is on the hot path"
@@ -153,7 +154,14 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
         smp = ("unipc_sdxl_turbo" if sampler == "unipcmultistep" else "ddim_sdxl_turbo") if turbo else ("unipc" if sampler == "unipcmultistep" else "ddim")
         return SaspaSDXLControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["text2"], unet_cfg=u, vae_cfg=v,
                                                             text_cfg=t1, text2_cfg=t2, sampler=smp, device=device, img2img=bool(SDEdit))
-    if base_model not in ("sd_v1.5", "blip_diffusion", "tiny"):
+    if base_model in ("blip_diffusion", "tiny_blip"):
+        # run_aug.py:185-187: BlipDiffusionControlNetPipeline; the sampler stays the checkpoint's PNDM (run_aug.py:217 skips the swap)
+        cfg = "tiny_blip" if base_model == "tiny_blip" else "blip"
+        sds = state_dicts or random_state_dicts(cfg, 1234)
+        u, v, t, q = blip_configs(cfg)
+        return SaspaBlipControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sds["qformer"], unet_cfg=u, vae_cfg=v,
+                                                            text_cfg=t, qformer_cfg=q, device=device)
+    if base_model not in ("sd_v1.5", "tiny"):
         raise NotImplementedError(f"base_model {base_model!r}: SD v1.5, SD-XL(-turbo) and BLIP-Diffusion ControlNet paths are built (see DESIGN.md)")
     cfg = "tiny" if base_model == "tiny" else "sd15"
     sds = state_dicts or random_state_dicts(cfg, 1234)
@@ -162,7 +170,7 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
     kw = {}
     if cfg == "tiny":
         kw = dict(unet_cfg=ck.UNetConfig.tiny(), vae_cfg=ck.VAEConfig.tiny(), text_cfg=ck.CLIPTextConfig.tiny())
-    smp = "pndm" if base_model == "blip_diffusion" else ("unipc" if sampler == "unipcmultistep" else "ddim")
+    smp = "unipc" if sampler == "unipcmultistep" else "ddim"
     return SaspaControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sampler=smp, device=device, img2img=bool(SDEdit), **kw)
 
 
@@ -171,10 +179,19 @@ def pass_thorugh_pipe(base_model, pipe, prompt, orig_img, SDEdit, SDEdit_strengt
     """run_aug.py:233-279 (same kwargs assembly, same return)."""
     pipe_args = {"prompt": str(prompt), "num_inference_steps": num_inference_steps, "generator": generator, "guidance_scale": guidance_scale,
                  "negative_prompt": negative_prompt}
+    blip = "blip" in base_model
+    if blip:  # run_aug.py:243-250
+        pipe_args.update(reference_image=orig_img, source_subject_category=blip_src_category, target_subject_category=blip_target_category,
+                         height=orig_img.size[1], width=orig_img.size[0], neg_prompt=NEGATIVE_PROMPT)
+        del pipe_args["negative_prompt"]
     if control_image is not None:
         if SDEdit:
             pipe_args["control_image"] = control_image
             pipe_args["controlnet_conditioning_scale"] = control_cond_scale
+        elif blip:  # run_aug.py:268-271 (the parameter really is spelled "condtioning_image")
+            pipe_args["condtioning_image"] = control_image
+            pipe_args["height"] = control_image.size[1]
+            pipe_args["width"] = control_image.size[0]
         else:
             pipe_args["image"] = control_image
             pipe_args["controlnet_conditioning_scale"] = control_cond_scale

@@ -142,3 +142,64 @@ def test_filter_decisions_identical_to_oracle(cuda_device):
     assert torch.equal(out["in_topk"].cpu(), keep_topk)
     assert torch.equal(out["semantic"].cpu(), keep_sem)
     assert torch.equal(out["keep"].cpu(), keep_topk & keep_sem)
+
+
+@pytest.mark.parametrize("name", ["tiny", "vit_l14"])
+def test_clip_vit_matches_oracle(cuda_device, name):
+    """CLIP with a VisionTransformer tower (BASELINE config 5: ViT-L/14) vs the fp32 oracle restatement (pinned to transformers.CLIPModel
+    in tests/test_filter_oracle_cpu.py): image / text features within max(2 x stock-torch-bf16's own error, 1e-2 x max|ref|)."""
+    import copy
+
+    from oracle import clip_rn50
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200.filter_nets import CLIPViT
+    from saspa_aug_b200.synthetic import synthetic_token_ids
+    from tests.test_models_gpu import _bound
+
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    kw = ck.clip_vit_tiny_kwargs() if name == "tiny" else {}
+    sd = ck.random_filter_state_dict(ck.clip_vit_shapes(**kw), 9)
+    oc = clip_rn50.clip_vit(**kw).eval()
+    oc.load_state_dict(sd)
+    R = kw.get("res", 224)
+    vocab = kw.get("vocab", 49408)
+    x = torch.randn((3, 3, R, R), generator=torch.Generator().manual_seed(0))
+    ids = torch.cat([synthetic_token_ids(s, vocab=vocab) for s in range(7)])
+    with torch.no_grad():
+        fi, ft = oc.encode_image(x), oc.encode_text(ids)
+        ob = copy.deepcopy(oc).to("cuda", torch.bfloat16)
+        fib, ftb = ob.encode_image(x.cuda().bfloat16()).float().cpu(), ob.encode_text(ids.cuda()).float().cpu()
+    m = CLIPViT(sd)
+    assert m.resolution == R
+    gi = m.encode_image(x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()).cpu()
+    gt = m.encode_text(ids.cuda()).cpu()
+    e1, b1 = _bound(gi, fi, fib)
+    e2, b2 = _bound(gt, ft, ftb)
+    print(f"clip {name}: image feat err ours {e1:.4g} / torch-bf16 {b1:.4g}; text feat err ours {e2:.4g} / torch-bf16 {b2:.4g}")
+
+
+def test_filter_semantic_decisions_identical_vit_l14(cuda_device):
+    """Semantic keep/drop (argmax over [basic prompt + 6 negatives] == 0) with the ViT-L/14 CLIP on 24 synthetic images: identical to the
+    fp32 oracle; the smallest top1-top2 logit gap is printed."""
+    from oracle import clip_rn50
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200.filter_nets import AugmentationFilter, CLIPViT
+    from saspa_aug_b200.synthetic import synthetic_token_ids
+    from tests.test_filter_oracle_cpu import preprocess_clip
+
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    sd = ck.random_filter_state_dict(ck.clip_vit_shapes(), 777)
+    oc = clip_rn50.clip_vit().eval()
+    oc.load_state_dict(sd)
+    n = 24
+    src = np.stack([synthetic_source(900 + i, kind=("blobs", "noise", "smooth")[i % 3]) for i in range(n)])
+    ids = torch.cat([synthetic_token_ids(s) for s in range(40, 47)])
+    with torch.no_grad():
+        fi = torch.cat([oc.encode_image(torch.stack([preprocess_clip(s) for s in src[i:i + 8]])) for i in range(0, n, 8)])
+        cl = oc.logit_scale.exp() * F.normalize(fi, dim=-1) @ F.normalize(oc.encode_text(ids), dim=-1).t()
+    flt = AugmentationFilter(None, CLIPViT(sd), ids)
+    out = flt(torch.from_numpy(src).cuda(), torch.zeros(n, dtype=torch.int32, device="cuda"))
+    top2 = cl.topk(2, dim=-1)[0]
+    err = (out["clip_logits"].cpu() - cl).abs().max().item()
+    print(f"ViT-L/14 CLIP logits max err {err:.4g}; min top1-top2 gap {(top2[:, 0] - top2[:, 1]).min().item():.4g}; kept {int((cl.argmax(-1) == 0).sum())}/{n}")
+    assert torch.equal(out["semantic"].cpu(), (cl.argmax(-1) == 0).to(torch.uint8))

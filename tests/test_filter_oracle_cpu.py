@@ -80,3 +80,57 @@ def test_topk_rule():
     logits = torch.tensor([[0.1, 0.9, 0.5, 0.4], [1.0, 0.7, 0.8, 0.9]])
     assert wsdan.in_topk(logits, [2, 1], 2).tolist() == [1, 0]
     assert wsdan.in_topk(logits, [3, 3], 2).tolist() == [0, 1]
+
+
+def _openai_to_hf_clip(sd, v_layers, t_layers):
+    """openai-clip state-dict keys -> transformers.CLIPModel keys (the published conversion: in_proj split into q/k/v, proj transposed)."""
+    out = {"logit_scale": sd["logit_scale"], "text_projection.weight": sd["text_projection"].t(), "visual_projection.weight": sd["visual.proj"].t(),
+           "text_model.embeddings.token_embedding.weight": sd["token_embedding.weight"], "text_model.embeddings.position_embedding.weight": sd["positional_embedding"],
+           "text_model.final_layer_norm.weight": sd["ln_final.weight"], "text_model.final_layer_norm.bias": sd["ln_final.bias"],
+           "vision_model.embeddings.class_embedding": sd["visual.class_embedding"], "vision_model.embeddings.patch_embedding.weight": sd["visual.conv1.weight"],
+           "vision_model.embeddings.position_embedding.weight": sd["visual.positional_embedding"],
+           "vision_model.pre_layrnorm.weight": sd["visual.ln_pre.weight"], "vision_model.pre_layrnorm.bias": sd["visual.ln_pre.bias"],
+           "vision_model.post_layernorm.weight": sd["visual.ln_post.weight"], "vision_model.post_layernorm.bias": sd["visual.ln_post.bias"]}
+    for src, dst, n in (("transformer.resblocks.", "text_model.encoder.layers.", t_layers), ("visual.transformer.resblocks.", "vision_model.encoder.layers.", v_layers)):
+        for i in range(n):
+            a, b = f"{src}{i}.", f"{dst}{i}."
+            w, bias = sd[a + "attn.in_proj_weight"], sd[a + "attn.in_proj_bias"]
+            c = w.shape[1]
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                out[b + f"self_attn.{nm}.weight"], out[b + f"self_attn.{nm}.bias"] = w[j * c:(j + 1) * c], bias[j * c:(j + 1) * c]
+            for s_, d_ in (("attn.out_proj", "self_attn.out_proj"), ("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"), ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+                out[b + d_ + ".weight"], out[b + d_ + ".bias"] = sd[a + s_ + ".weight"], sd[a + s_ + ".bias"]
+    return out
+
+
+def test_clip_vit_oracle_matches_transformers_clipmodel():
+    """The ViT CLIP restatement (openai layout; BASELINE config 5 uses ViT-L/14) against transformers.CLIPModel on the same weights."""
+    from transformers import CLIPConfig, CLIPModel
+
+    kw = ck.clip_vit_tiny_kwargs()
+    sd = ck.random_filter_state_dict(ck.clip_vit_shapes(**kw), 9)
+    c = clip_rn50.clip_vit(**kw).eval()
+    c.load_state_dict(sd, strict=True)
+    cfg = CLIPConfig(projection_dim=kw["embed_dim"],
+                     text_config=dict(vocab_size=kw["vocab"], hidden_size=kw["t_width"], intermediate_size=4 * kw["t_width"], num_hidden_layers=kw["t_layers"],
+                                      num_attention_heads=max(1, kw["t_width"] // 64), max_position_embeddings=kw["ctx"], hidden_act="quick_gelu",
+                                      bos_token_id=kw["vocab"] - 2, eos_token_id=kw["vocab"] - 1),
+                     vision_config=dict(hidden_size=kw["v_width"], intermediate_size=4 * kw["v_width"], num_hidden_layers=kw["v_layers"],
+                                        num_attention_heads=kw["v_width"] // 64, image_size=kw["res"], patch_size=kw["patch"], hidden_act="quick_gelu"))
+    hf = CLIPModel(cfg).eval()
+    missing, unexpected = hf.load_state_dict(_openai_to_hf_clip(sd, kw["v_layers"], kw["t_layers"]), strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 3, kw["res"], kw["res"]), generator=g)
+    ids = torch.cat([synthetic_token_ids(s, vocab=kw["vocab"]) for s in (1, 2, 3)])
+    with torch.no_grad():
+        fi, ft = c.encode_image(x), c.encode_text(ids)
+        hi = hf.visual_projection(hf.vision_model(pixel_values=x).pooler_output)
+        ht = hf.text_projection(hf.text_model(input_ids=ids).pooler_output)
+    assert torch.allclose(fi, hi, atol=2e-5), (fi - hi).abs().max()
+    assert torch.allclose(ft, ht, atol=2e-5), (ft - ht).abs().max()
+
+
+def test_clip_vit_l14_shapes():
+    n = ck.count_params(ck.clip_vit_shapes())
+    assert 420e6 < n < 435e6, n  # openai ViT-L/14: 427.6 M parameters
