@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sources", type=int, default=64)
     ap.add_argument("--prompts", type=int, default=2)
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--vae-micro-batch", type=int, default=8)
     ap.add_argument("--num-inference-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -120,6 +120,14 @@ int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, in
                             const void* weight, int ksize, void* out, int ldo, int cout, const saspa_epilogue* ep_host,
                             cudaStream_t stream);
 
+/* The same implicit GEMM with stride in {1,2} and an explicit top/left zero padding `pad` (0 .. ksize/2): x [n,ih,iw,c] -> out
+ * [n,oh,ow,cout], out(y,x) = sum_taps w(ky,kx) . x(y*stride + ky - pad, x*stride + kx - pad); taps outside the input read zeros
+ * (TMA out-of-bounds fill), which also supplies any bottom/right padding -- diffusers' Downsample2D (stride 2, padding 1;
+ * UNet/ControlNet, models/downsampling.py) and the VAE encoder's asymmetric (0,1,0,1) pad + stride-2 conv need no im2col buffer. */
+int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int ih, int iw,
+                                    const void* weight, int ksize, int stride, int pad, int oh, int ow, void* out, int ldo, int cout,
+                                    const saspa_epilogue* ep_host, cudaStream_t stream);
+
 /* Selects the 3x3 implicit-GEMM main loop: 0 = auto (halo tile when the map holds an 8 x 16 pixel tile, else one TMA
  * box per tap), 1 = per-tap boxes only, 2 = halo only (error when not eligible).  Returns the previous setting; a
  * negative argument only queries.  Process-wide; meant for tests and A/B timing. */

@@ -68,6 +68,10 @@ SIGNATURES = {
         c_int,
         [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, POINTER(Epilogue), _P],
     ),
+    "saspa_conv2d_igemm_strided_bf16": (
+        c_int,
+        [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, POINTER(Epilogue), _P],
+    ),
     "saspa_im2col_bf16": (
         c_int,
         [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],

@@ -6,7 +6,10 @@
 // AttnProcessor2_0 (reference call site: pipe(**pipe_args), run_aug/run_aug.py:278).
 //
 // One CTA owns 256 queries of one (batch, head) as two 128-row tiles and sweeps the keys in tiles of
-// BKV (128 for head_dim <= 64, else 64).  Ten warps:
+// BKV (128 for head_dim <= 64, else 64).  3 + 8 * SPLIT warps.  SPLIT = 1 is the product path.  SPLIT = 2 (tuning hook only) shares
+// each query row's score columns between two threads of two warps on the same TMEM lane quadrant (four softmax warps per SM
+// sub-partition instead of two, row max exchanged through shared memory); measured 5 % SLOWER on every shape, i.e. the softmax
+// warps' own latencies are not what bounds the kernel (profiles/r1_attn_ablation.txt):
 //   warp 0     TMA producer: Q once, then K_j / V_j into a STAGES-deep ring of 128B-swizzled smem tiles
 //              (64-column panels straight out of the fused [b, t, 3c] QKV buffer -- nothing is repacked in HBM).
 //   warp 1     owns the 512 TMEM columns; one lane issues every tcgen05.mma:
@@ -14,14 +17,15 @@
 //                O_i += P_i V_j            (TS: P_i read from TMEM, V_j MN-major in smem) -> TMEM
 //              issue order per key tile j:  QK(0,j+1) QK(1,j+1) PV(0,j) PV(1,j), so the next S is ready
 //              before the softmax warps finish the current one.
-//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1: one thread per query row (no shuffles):
+//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (SPLIT = 2: warps 10-17 repeat the pattern for the upper half of the
+//              score columns): one thread per query row and column half (no shuffles):
 //              tcgen05.ld the S row, release S, running max with lazy rescale (O is only rescaled in TMEM
 //              when the max grows by more than 2^8), p = ex2(s*c - m), bf16 P packed two per column back
 //              into TMEM with tcgen05.st; finally O / l -> global.
 //              A quarter of the exponentials are evaluated on the FMA pipe (Cody-Waite split + cubic, rel. error 7.5e-5,
 //              far below the bf16 rounding of P): the d = 40 layers are bound by the 16/clk/SM MUFU unit, not by the
 //              tensor pipe.
-//   warp 10    (head_dim % 16 == 8 only) patches a column of ones into the zero-cost pad of each landed V tile, so
+//   last warp  (head_dim % 16 == 8 only) patches a column of ones into the zero-cost pad of each landed V tile, so
 //              the P V MMA also accumulates the softmax denominator sum_j P_ij in O[:, D] -- no per-element adds.
 // Padding is free: head_dim 40 runs as K = 48 (the Q pad chunk is zeroed in smem; K's pad columns then
 // multiply zeros) and PV as N = 48 (the extra accumulator columns are never stored).
@@ -31,8 +35,8 @@
 namespace {
 using namespace tcx;
 
-constexpr int ATC_THREADS = 352;
 constexpr int QROWS = 128;
+constexpr int atc_threads(int split) { return (3 + 8 * split) * 32; }
 
 template <int D>
 struct ACfg {
@@ -63,8 +67,8 @@ struct AttnParams {
   int debug;  // timing experiments only (tools_attn_bench.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
 };
 
-template <int D>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+template <int D, int SPLIT>
+__global__ void __launch_bounds__(atc_threads(SPLIT), 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnParams p) {
   using C = ACfg<D>;
@@ -88,6 +92,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
   uint64_t* p_full = s_free + 2;
   uint64_t* o_done = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  __shared__ float xch[2][2][SPLIT][QROWS];  // [parity][query tile][column half][row]: partial row max / row sum exchange (SPLIT = 2)
+  constexpr int CW = BKV / SPLIT;            // score columns per softmax thread
+  static_assert(CW % 32 == 0, "column split must keep 32-column TMEM loads");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
@@ -111,8 +118,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_free[i], 4 * SPLIT);
+      mbar_init(&p_full[i], 4 * SPLIT);
       mbar_init(&o_done[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         tc_commit(&v_empty[s]);
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2 + 8 * SPLIT) {
     // ===================== V patcher: ones into pad column D of every landed V tile =====================
     if (C::ONES) {
       constexpr int ch = D / 8, pn = ch / 8, lc = ch % 8;  // 16-byte chunk holding column D
@@ -220,17 +227,20 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..9) =====================
-    const int i = (warp - 2) >> 2;  // query tile of this warpgroup
-    const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+    // ===================== softmax / correction / epilogue (warps 2 .. 1 + 8 * SPLIT) =====================
+    const int i = ((warp - 2) >> 2) & 1;  // query tile of this warpgroup
+    const int hf = (warp - 2) >> 3;       // column half of the score tile this thread owns (0 when SPLIT == 1)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int qi = q0 + i * QROWS + row;
+    const int c0 = hf * CW;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_s = lane_base + i * BKV;
-    const uint32_t t_p = lane_base + C::P_OFF + i * (BKV / 2);
+    const uint32_t t_s = lane_base + i * BKV + c0;
+    const uint32_t t_p = lane_base + C::P_OFF + i * (BKV / 2) + c0 / 2;
     const uint32_t t_o = lane_base + C::O_OFF + i * ON;
+    const int pair_bar = 1 + i * 4 + quad;  // named barrier shared by the two warps that own the same 32 query rows
 
-    if (PAD_Q) {
+    if (PAD_Q && hf == 0) {
       mbar_wait(q_full, 0);
       constexpr int ch = D / 8, pn = ch / 8, lc = ch % 8;
       uint8_t* dst = sQ + (i * NPAN + pn) * C::QPAN_BYTES + row * 128 + ((lc ^ (row & 7)) << 4);
@@ -244,31 +254,39 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      uint32_t su[BKV];
+      uint32_t su[CW];
 #pragma unroll
-      for (int c = 0; c < BKV; c += 32) tc_ld32p(t_s + c, &su[c]);
+      for (int c = 0; c < CW; c += 32) tc_ld32p(t_s + c, &su[c]);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[i]);
 
-      const int kv0 = j * BKV;
-      if (kv0 + BKV > p.tkv) {
+      const int kv0 = j * BKV + c0;
+      if (kv0 + CW > p.tkv) {
 #pragma unroll
-        for (int c = 0; c < BKV; ++c)
+        for (int c = 0; c < CW; ++c)
           if (kv0 + c >= p.tkv) su[c] = 0xff800000u;
       }
-      if (p.causal && kv0 + BKV - 1 > qi) {
+      if (p.causal && kv0 + CW - 1 > qi) {
 #pragma unroll
-        for (int c = 0; c < BKV; ++c)
+        for (int c = 0; c < CW; ++c)
           if (kv0 + c > qi) su[c] = 0xff800000u;
       }
       float mx[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) mx[c] = __uint_as_float(su[c]);
 #pragma unroll
-      for (int c = 8; c < BKV; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(su[c]));
-      const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * p.scale_log2;
+      for (int c = 8; c < CW; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(su[c]));
+      float m_part = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      if constexpr (SPLIT == 2) {
+        // both owners of a row must use the same exponent reference: exchange the partial maxima (parity-double-buffered slot,
+        // so the write of step j + 2 cannot overtake the partner's read of step j)
+        xch[j & 1][i][hf][row] = m_part;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        m_part = fmaxf(m_part, xch[j & 1][i][hf ^ 1][row]);
+      }
+      const float m_tile = m_part * p.scale_log2;
 
       bool p_free = (j == 0);
       if (j == 0) {
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             }
           }
 #pragma unroll 1
-          for (int c = 0; c < ON; c += 16) {
+          for (int c = 16 * hf; c < ON; c += 16 * SPLIT) {  // the 16-column chunks of O alternate between the two owners
             uint32_t o[16];
             tc_ld16(t_o + c, o);
             tc_wait_ld();
@@ -302,14 +320,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       }
 
       const float neg_m = -m_used;
-      uint32_t pk[BKV / 2];
+      uint32_t pk[CW / 2];
       if (p.debug & 1) {  // timing experiment: no exponentials at all
 #pragma unroll
-        for (int c = 0; c < BKV; c += 2)
+        for (int c = 0; c < CW; c += 2)
           pk[c >> 1] = pack_bf16(fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m), fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m));
       } else {
 #pragma unroll
-        for (int c = 0; c < BKV; c += 2) {
+        for (int c = 0; c < CW; c += 2) {
           const float x0 = fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m);
           const float x1 = fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m);
           constexpr int PE = C::POLY_EVERY;
@@ -323,8 +341,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         mbar_wait(&o_done[i], (j - 1) & 1);
         tc_fence_after();
       }
+      if constexpr (CW / 2 >= 32) {
 #pragma unroll
-      for (int c = 0; c < BKV / 2; c += 32) tc_st32(t_p + c, &pk[c]);
+        for (int c = 0; c < CW / 2; c += 32) tc_st32(t_p + c, &pk[c]);
+      } else {
+        tc_st16(t_p, pk);
+      }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -335,6 +357,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     mbar_wait(&o_done[i], (n_tiles - 1) & 1);
     tc_fence_after();
     float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+    if constexpr (SPLIT == 2 && !C::ONES) {  // the row sum is split between the two owners
+      xch[n_tiles & 1][i][hf][row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l += xch[n_tiles & 1][i][hf ^ 1][row];
+    }
     if constexpr (C::ONES) {
       uint32_t lu;
       tc_ld1(t_o + D, lu);  // column D of O = sum_j P_ij (ones column of V)
@@ -345,7 +372,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     __nv_bfloat16* og = p.o + ((long long)b * p.tq + qi) * p.ldo + (long long)h * D;
     const bool valid = qi < p.tq;
 #pragma unroll 1
-    for (int c = 0; c < ON; c += 16) {
+    for (int c = 16 * hf; c < ON; c += 16 * SPLIT) {
       uint32_t o[16];
       tc_ld16(t_o + c, o);
       tc_wait_ld();
@@ -414,13 +441,15 @@ int encode_rows3d(CUtensorMap* tm, const void* base, int cols, int rows, int bat
 
 int g_attn_debug = 0;
 
-template <int D>
-int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+int g_attn_split = 1;  // softmax threads per query row (1 | 2); measured: 2 is 5% slower on every SD shape (profiles/r1_attn_ablation.txt)
+
+template <int D, int SPLIT>
+int launch_tc_split(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
               float scale, int causal, cudaStream_t stream) {
   using C = ACfg<D>;
   static bool configured = false;
   if (!configured) {
-    SASPA_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SASPA_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -438,9 +467,16 @@ int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int
   p.causal = causal;
   p.debug = g_attn_debug;
   dim3 grid(ceil_div(tq, 2 * QROWS), batch * heads);
-  attn_tc_kernel<D><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
+  attn_tc_kernel<D, SPLIT><<<grid, atc_threads(SPLIT), C::SMEM, stream>>>(tmQ, tmK, tmV, p);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
+}
+
+template <int D>
+int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+              float scale, int causal, cudaStream_t stream) {
+  if (g_attn_split == 1) return launch_tc_split<D, 1>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+  return launch_tc_split<D, 2>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
 }
 
 }  // namespace
@@ -463,6 +499,7 @@ int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const voi
 // Timing-experiment hook (see AttnParams::debug); results are WRONG while it is non-zero.  Not part of the product API.
 extern "C" int saspa_attention_debug(int flags) {
   const int prev = g_attn_debug;
-  g_attn_debug = flags;
+  g_attn_debug = flags & 0xff;
+  if (flags & 0x300) g_attn_split = (flags >> 8) & 3;  // tuning hook: 0x100 = one softmax thread per row, 0x200 = two
   return prev;
 }

@@ -58,7 +58,8 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
   int mode;  // 0 = GEMM, 1 = implicit conv (one TMA box per tap), 2 = implicit 3x3 conv from a halo tile
   // conv geometry
-  int n_img, H, W, c0, c1, ksize;
+  int n_img, H, W, c0, c1, ksize;  // H, W: OUTPUT map
+  int stride, pad;                 // per-tap mode: input pixel = output pixel * stride + tap - pad (stride 2: TMA element strides)
   int bw, bh, bn;
   int tiles_x, tiles_y;
   // epilogue
@@ -321,7 +322,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           y0 = ty * p.bh;
           n0 = tn * p.bn;
         }
-        const int pad = p.ksize >> 1;
+        const int pad = p.pad;
+        x0 *= p.stride;
+        y0 *= p.stride;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (is_leader) mbar_expect_tx(&full[stage], C::STAGE_BYTES * CTAS);
@@ -751,8 +754,10 @@ int encode_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
 }
 
 // rank-4 NHWC bf16 activation [n, h, w, c] with pixel stride ld (elements); box = [bn, bh, bw, 64].
+// estride > 1: the box walks the map with that element stride in w and h (a strided conv's A operand), i.e. it still delivers
+// bn x bh x bw pixels but spans bh*estride x bw*estride input pixels.
 int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, long long ld, int bn, int bh, int bw, int box_c = BK,
-                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   if (!enc) {
     saspa_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -760,8 +765,8 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int n, int h, int w, int c, l
   }
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -949,13 +954,17 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   return dispatch(bn, ctas, tmA, tmA, tmB, tmD, tmR, p, stream);
 }
 
-extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int h, int w,
-                                       const void* weight, int ksize, void* out, int ldo, int cout, const saspa_epilogue* ep,
-                                       cudaStream_t stream) {
-  SASPA_CHECK_ARG(n >= 0 && h >= 0 && w >= 0 && cout >= 0, "saspa_conv2d_igemm_bf16: negative dims");
+extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int ih, int iw,
+                                               const void* weight, int ksize, int stride, int pad, int h, int w, void* out, int ldo, int cout,
+                                               const saspa_epilogue* ep, cudaStream_t stream) {
+  SASPA_CHECK_ARG(n >= 0 && h >= 0 && w >= 0 && ih >= 0 && iw >= 0 && cout >= 0, "saspa_conv2d_igemm_bf16: negative dims");
   if (n == 0 || h == 0 || w == 0 || cout == 0) return SASPA_OK;
   SASPA_CHECK_ARG(x0 && weight && out, "saspa_conv2d_igemm_bf16: null pointer");
   SASPA_CHECK_ARG(ksize == 1 || ksize == 3, "saspa_conv2d_igemm_bf16: ksize must be 1 or 3, got %d", ksize);
+  SASPA_CHECK_ARG(stride == 1 || stride == 2, "saspa_conv2d_igemm_bf16: stride must be 1 or 2, got %d", stride);
+  SASPA_CHECK_ARG(pad >= 0 && pad <= ksize / 2, "saspa_conv2d_igemm_bf16: top/left padding must be in [0, ksize/2], got %d", pad);
+  SASPA_CHECK_ARG((long long)(h - 1) * stride + ksize - pad <= ih + ksize / 2 + 1 && (long long)(w - 1) * stride + ksize - pad <= iw + ksize / 2 + 1,
+                  "saspa_conv2d_igemm_bf16: output map %dx%d reaches beyond the zero-padded %dx%d input", h, w, ih, iw);
   if (!x1) c1 = 0;
   SASPA_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0, "saspa_conv2d_igemm_bf16: channel counts must be multiples of 8 (c0=%d c1=%d)", c0, c1);
   SASPA_CHECK_ARG(c1 == 0 || c0 % BK == 0, "saspa_conv2d_igemm_bf16: c0 must be a multiple of 64 when a second source is given (c0=%d)", c0);
@@ -963,6 +972,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   SASPA_CHECK_ARG((reinterpret_cast<uintptr_t>(x0) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
                       (c1 == 0 || (reinterpret_cast<uintptr_t>(x1) & 15) == 0),
                   "saspa_conv2d_igemm_bf16: 16-byte alignment required");
+  const bool same = stride == 1 && pad == ksize / 2 && ih == h && iw == w;
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, cout, out, ldo);
   if (rc) return rc;
@@ -978,6 +988,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
       bi <<= 1;
     }
     if (bw > 1 && bw / 2 >= w) continue;  // a narrower box covers the row just as well
+    if (bw * stride > 256 || bh * stride > 256) continue;  // TMA box extent limit
     long long cost = (long long)ceil_div(w, bw) * bw * ceil_div(h, bh) * bh * ceil_div(n, bi) * bi;
     long long halo = (long long)(bw + 2) * (bh + 2);  // L2 traffic proxy
     long long score = cost * 1024 + halo;
@@ -990,7 +1001,7 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   }
   // 3x3 on maps of at least one 8 x 16 tile: halo mode (the activation is fetched once per 64-channel chunk
   // instead of once per tap; operand traffic out of L2 is what bounds this kernel)
-  const bool halo = ksize == 3 && h >= HALO_BH && w >= HALO_BW && g_conv_impl != 1;
+  const bool halo = same && ksize == 3 && h >= HALO_BH && w >= HALO_BW && g_conv_impl != 1;
   if (g_conv_impl == 2 && !halo) {
     saspa_set_error("saspa_conv2d_igemm_bf16: halo mode forced but the shape is not eligible (ksize=%d h=%d w=%d)", ksize, h, w);
     return SASPA_ERR_UNSUPPORTED;
@@ -1007,6 +1018,8 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   p.c0 = c0;
   p.c1 = c1;
   p.ksize = ksize;
+  p.stride = stride;
+  p.pad = pad;
   p.bw = best_bw;
   p.bh = best_bh;
   p.bn = best_bi;
@@ -1021,9 +1034,9 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
   p.M = n * h * w;
   CUtensorMap tmA0, tmA1, tmB;
   const int abh = halo ? p.bh + 2 : p.bh, abw = halo ? p.bw + 2 : p.bw;  // activation box (with the 1-px halo in mode 2)
-  if ((rc = encode_nhwc(&tmA0, x0, n, h, w, c0, ldx0, p.bn, abh, abw))) return rc;
+  if ((rc = encode_nhwc(&tmA0, x0, n, ih, iw, c0, ldx0, p.bn, abh, abw, BK, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
   if (c1 > 0) {
-    if ((rc = encode_nhwc(&tmA1, x1, n, h, w, c1, ldx1, p.bn, abh, abw))) return rc;
+    if ((rc = encode_nhwc(&tmA1, x1, n, ih, iw, c1, ldx1, p.bn, abh, abw, BK, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
   } else {
     tmA1 = tmA0;
   }
@@ -1036,6 +1049,12 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
       return rc;
   }
   return dispatch(bn_tile, ctas, tmA0, tmA1, tmB, tmD, tmR, p, stream);
+}
+
+extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int h, int w,
+                                       const void* weight, int ksize, void* out, int ldo, int cout, const saspa_epilogue* ep,
+                                       cudaStream_t stream) {
+  return saspa_conv2d_igemm_strided_bf16(x0, ldx0, c0, x1, ldx1, c1, n, h, w, weight, ksize, 1, ksize / 2, h, w, out, ldo, cout, ep, stream);
 }
 
 extern "C" int saspa_conv_impl(int impl) {

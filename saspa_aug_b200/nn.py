@@ -49,8 +49,8 @@ def pix3d(x: torch.Tensor) -> torch.Tensor:
 
 
 class Conv:
-    """Conv2d.  Stride-1 same-padded 1x1/3x3 with Cin % 8 == 0 run as TMA implicit GEMM; everything else
-    (stride 2, Cin in {3,4}, 7x7 stems, asymmetric padding) as im2col + GEMM."""
+    """Conv2d.  1x1/3x3 with Cin % 8 == 0 and stride 1 ("same") or stride 2 (padding 1, or the VAE encoder's bottom/right-only
+    padding) run as TMA implicit GEMM; everything else (Cin in {3,4}, 7x7 / 14x14 stems, strides > 2) as im2col + GEMM."""
 
     def __init__(self, sd: SD, prefix: str, dev, stride: int = 1, padding: Optional[int] = None, weight=None, bias=None):
         w = sd[prefix + ".weight"] if weight is None else weight
@@ -62,7 +62,8 @@ class Conv:
         self.pad = self.k // 2 if padding is None else padding
         self.bias = _f32(b, dev)
         self.direct = stride == 1 and self.pad == self.k // 2 and self.k in (1, 3) and self.cin % 8 == 0
-        if self.direct:
+        self.direct_strided = stride == 2 and self.k == 3 and self.pad in (0, 1) and self.cin % 8 == 0
+        if self.direct or self.direct_strided:
             self.kpad = self.k * self.k * self.cin
             self.w = _bf(conv_weight_kmajor(w), dev)
         else:
@@ -76,6 +77,8 @@ class Conv:
             return ops.conv2d_igemm(x, self.w, self.k, out=out, bias=self.bias, **epi)
         oh = (h + 2 * self.pad + pad_extra_br - self.k) // self.stride + 1
         ow = (w + 2 * self.pad + pad_extra_br - self.k) // self.stride + 1
+        if self.direct_strided:  # taps past the bottom/right edge read TMA zero fill: covers padding 1 and the (0,1,0,1) VAE pad
+            return ops.conv2d_igemm(x, self.w, self.k, out=out, bias=self.bias, stride=self.stride, pad=self.pad, out_hw=(oh, ow), **epi)
         cols = ops.im2col(x, self.k, self.k, self.stride, self.pad, self.pad, oh, ow, self.kpad)
         if out is None:
             out = torch.empty((n, oh, ow, self.cout), dtype=torch.float32 if epi.get("out_fp32") else BF16, device=x.device)

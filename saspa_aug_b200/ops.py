@@ -126,9 +126,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optional[torch.Tensor] = None, *, x1: Optional[torch.Tensor] = None,
-                 bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False) -> torch.Tensor:
-    """Stride-1 same-padded conv on NHWC bf16 views [n,h,w,c] (channel stride 1, dense n/h/w strides);
-    weight bf16 [cout, ksize*ksize*(c0+c1)]."""
+                 bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False,
+                 stride: int = 1, pad: Optional[int] = None, out_hw: Optional[tuple] = None) -> torch.Tensor:
+    """Implicit-GEMM conv on NHWC bf16 views [n,h,w,c] (channel stride 1, dense n/h/w strides); weight bf16 [cout, ksize*ksize*(c0+c1)].
+    Default: stride 1, "same" padding.  stride 2 / explicit top-left ``pad`` / ``out_hw`` = (oh, ow): taps outside the input read zeros."""
     _need_cuda(x, weight)
     n, h, w, c0 = x.shape
     assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
@@ -138,21 +139,24 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
         c1 = x1.shape[3]
     cout = weight.shape[0]
     assert weight.dtype == BF16 and weight.is_contiguous() and weight.shape[1] == ksize * ksize * (c0 + c1)
+    pad = ksize // 2 if pad is None else pad
+    oh, ow = out_hw if out_hw is not None else ((h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1)
     if out is None:
-        out = torch.empty((n, h, w, cout), dtype=torch.float32 if out_fp32 else BF16, device=x.device)
-    assert out.stride(3) == 1 and out.stride(1) == w * out.stride(2) and out.stride(0) == h * out.stride(1)
+        out = torch.empty((n, oh, ow, cout), dtype=torch.float32 if out_fp32 else BF16, device=x.device)
+    assert out.shape[1:3] == (oh, ow) and out.stride(3) == 1 and out.stride(1) == ow * out.stride(2) and out.stride(0) == oh * out.stride(1)
     ld_res = 0
     if residual is not None:
-        assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == w * residual.stride(2)
+        assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == ow * residual.stride(2)
         ld_res = residual.stride(2)
-    ep = make_epilogue(bias, row_bias, h * w, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual)
+    ep = make_epilogue(bias, row_bias, oh * ow, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual)
     ev = _prof_begin()
     check(
-        _lib.load().saspa_conv2d_igemm_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
-                                            _ptr(weight), ksize, _ptr(out), out.stride(2), cout, ctypes.byref(ep), _stream()),
-        "saspa_conv2d_igemm_bf16",
+        _lib.load().saspa_conv2d_igemm_strided_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
+                                                    _ptr(weight), ksize, stride, pad, oh, ow, _ptr(out), out.stride(2), cout, ctypes.byref(ep),
+                                                    _stream()),
+        "saspa_conv2d_igemm_strided_bf16",
     )
-    _prof_end(ev, "conv", 2.0 * n * h * w * cout * ksize * ksize * (c0 + c1), (n, h, w, c0 + c1, cout, ksize))
+    _prof_end(ev, "conv", 2.0 * n * oh * ow * cout * ksize * ksize * (c0 + c1), (n, oh, ow, c0 + c1, cout, ksize) if stride == 1 else (n, oh, ow, c0 + c1, cout, ksize, stride))
     _count()
     return out
 

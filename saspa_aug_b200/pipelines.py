@@ -408,8 +408,7 @@ class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
     The subject embedding is step- and prompt-invariant: it is cached per (reference image bytes, subject ids)."""
 
     def __init__(self, *a, qformer: snn.QFormer = None, qformer_tokenizer=None, ctx_begin_pos: int = 2, **k):
-        k.setdefault("sampler", "pndm")
-        super().__init__(*a, **k)
+        super().__init__(*a, **k)  # from_state_dicts passes sampler "pndm": the checkpoint's scheduler is kept (run_aug.py:217)
         self.qformer = qformer
         self.qformer_tokenizer = qformer_tokenizer or SyntheticBertTokenizer(qformer.cfg.vocab_size, qformer.cfg.max_position_embeddings)
         self.ctx_begin_pos = ctx_begin_pos

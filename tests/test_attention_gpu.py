@@ -23,15 +23,20 @@ def _ref(q, k, v, heads, scale=None, causal=False):
     return (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(b, tq, hd)
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["auto", "mma_sync", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "mma_sync", "tcgen05", "tcgen05_two_threads_per_row"])
 def impl(request):
     """Runs a test once per attention kernel (saspa_attention_impl: 0 = auto, incl. the K/V-resident cross-attention kernel
-    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM)."""
+    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM, one softmax thread per query row (the product path); 3 = the same kernel
+    with two threads per row (tuning hook saspa_attention_debug 0x200 / 0x100))."""
     from saspa_aug_b200 import _lib
 
-    prev = _lib.load().saspa_attention_impl(request.param)
+    lib = _lib.load()
+    prev = lib.saspa_attention_impl(min(request.param, 2))
+    if request.param == 3:
+        lib.saspa_attention_debug(0x200)
     yield request.param
-    _lib.load().saspa_attention_impl(prev)
+    lib.saspa_attention_debug(0x100)
+    lib.saspa_attention_impl(prev)
 
 
 @pytest.mark.parametrize("cfg", [  # b, heads, tq, tkv, d

@@ -109,6 +109,30 @@ def test_conv_igemm(cuda_device, conv_impl, cfg):
     _check(got, ref)
 
 
+@pytest.mark.parametrize("cfg", [  # n, h, w, cin, cout, pad (0 = the VAE encoder's bottom/right-only padding)
+    (2, 64, 64, 320, 320, 1), (4, 32, 32, 640, 640, 1), (4, 16, 16, 1280, 1280, 1), (2, 33, 47, 64, 96, 1), (1, 17, 9, 72, 40, 1),
+    (2, 64, 64, 128, 128, 0), (1, 128, 96, 256, 256, 0), (3, 10, 14, 64, 64, 0), (1, 512, 512, 128, 128, 0)])
+def test_conv_igemm_stride2(cuda_device, cfg):
+    """Stride-2 3x3 implicit GEMM (TMA element strides; no im2col buffer): diffusers Downsample2D (padding 1) and the VAE encoder's
+    F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0); with a per-image row bias and activation in the epilogue."""
+    n, h, w, cin, cout, pad = cfg
+    x = _rand((n, h, w, cin), 20)
+    wt = _rand((cout, cin, 3, 3), 21, 1.0 / math.sqrt(cin * 9))
+    bias = torch.randn(cout, device="cuda")
+    wk = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad == 0:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wt.float(), bias, stride=2).permute(0, 2, 3, 1)
+    else:
+        ref = F.conv2d(xin, wt.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    oh, ow = ref.shape[1:3]
+    got = ops.conv2d_igemm(x, wk, 3, bias=bias, stride=2, pad=pad, out_hw=(oh, ow))
+    _check(got, ref)
+    rb = torch.randn(n, cout, device="cuda")
+    got2 = ops.conv2d_igemm(x, wk, 3, bias=bias, row_bias=rb, act=ops.ACT_SILU, stride=2, pad=pad, out_hw=(oh, ow))
+    _check(got2, F.silu(ref + rb[:, None, None, :]))
+
+
 def test_conv_igemm_two_sources_rowbias_residual(cuda_device, conv_impl):
     n, h, w, c0, c1, cout = 2, 32, 32, 640, 320, 640
     x0, x1 = _rand((n, h, w, c0), 12), _rand((n, h, w, c1), 13)
