@@ -23,20 +23,15 @@ def _ref(q, k, v, heads, scale=None, causal=False):
     return (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(b, tq, hd)
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "mma_sync", "tcgen05", "tcgen05_two_threads_per_row"])
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "mma_sync", "tcgen05"])
 def impl(request):
     """Runs a test once per attention kernel (saspa_attention_impl: 0 = auto, incl. the K/V-resident cross-attention kernel
-    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM, one softmax thread per query row (the product path); 3 = the same kernel
-    with two threads per row (tuning hook saspa_attention_debug 0x200 / 0x100))."""
+    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM)."""
     from saspa_aug_b200 import _lib
 
-    lib = _lib.load()
-    prev = lib.saspa_attention_impl(min(request.param, 2))
-    if request.param == 3:
-        lib.saspa_attention_debug(0x200)
+    prev = _lib.load().saspa_attention_impl(request.param)
     yield request.param
-    lib.saspa_attention_debug(0x100)
-    lib.saspa_attention_impl(prev)
+    _lib.load().saspa_attention_impl(prev)
 
 
 @pytest.mark.parametrize("cfg", [  # b, heads, tq, tkv, d

@@ -21,15 +21,12 @@ def main():
             k, v = kv[..., :c], kv[..., c:]
         out = torch.empty(b, tq, c, dtype=torch.bfloat16, device="cuda")
         res = []
-        for impl, split in ((1, 2), (2, 1), (2, 2), (0, 2)):
+        for impl in (1, 2, 0):
             lib.saspa_attention_impl(impl)
-            lib.saspa_attention_debug(split << 8)
             ms = timeit(lambda: ops.attention(q, k, v, heads, out=out))
             res.append((ms, 4.0 * b * heads * tq * tkv * d / ms / 1e9))
         lib.saspa_attention_impl(0)
-        lib.saspa_attention_debug(0x100)
-        print(f"attn b{b} h{heads} {tq}x{tkv} d{d}: mma.sync {res[0][0]:.3f} ms | tcgen05 1 thread/row {res[1][0]:.3f} ms {res[1][1]:.0f} TF/s | "
-              f"tcgen05 2 threads/row {res[2][0]:.3f} ms {res[2][1]:.0f} TF/s | auto {res[3][0]:.3f} ms {res[3][1]:.0f} TF/s")
+        print(f"attn b{b} h{heads} {tq}x{tkv} d{d}: mma.sync {res[0][0]:.3f} ms | tcgen05 {res[1][0]:.3f} ms {res[1][1]:.0f} TF/s | auto {res[2][0]:.3f} ms {res[2][1]:.0f} TF/s")
 
 
 if __name__ == "__main__":
