@@ -495,7 +495,9 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
     if (d <= 64) return launch_xattn<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 80) return launch_xattn<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 128) return launch_xattn<128>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
-    return launch_xattn<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    // d = 160 (the 16 x 16 level): one resident CTA per SM loses to the tcgen05 kernel (b32 h8 256x77: 45 vs 31 us), which is
+    // tried below; the resident kernel remains the fallback for head dims without a tcgen05 instantiation
+    if (d != 160) return launch_xattn<160>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
   }
   if (g_attention_impl != 1) {
     const int rc = saspa_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, causal, stream);

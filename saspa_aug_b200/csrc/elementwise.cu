@@ -415,9 +415,10 @@ GnRegPlan gn_reg_plan(int hw, int c, int groups) {
   r.pix_per_cta = pix_par * GN_VPT;
   r.parts = (hw + r.pix_per_cta - 1) / r.pix_per_cta;
   // the parts of one (image, slice) wait for each other: keep them well inside one wave.  Measured (profiles/
-  // r1_groupnorm_ab.txt): one 16-warp CTA per SM wins up to ~1K pixels per image (2-3x at 16x16 / 8x8, where the
-  // two-pass kernel runs one CTA per image); at 64x64 the two-pass kernel's four CTAs per SM overlap better.
-  r.ok = r.parts <= 64 && hw <= 1024;
+  // r1_hbm_microbench_i.txt): one 16-warp CTA per SM wins up to 16 x 16 pixels per image (1.2-2x at 16x16 / 8x8, where the
+  // two-pass kernel runs one CTA per image); from 32 x 32 on the two-pass kernel's four CTAs per SM overlap better
+  // (32x1024x640: 43 vs 53 us; 64x1024x640: 67 vs 92 us).  An 8-vector / two-CTA-per-SM variant measured no better.
+  r.ok = r.parts <= 64 && hw <= 512;
   return r;
 }
 
@@ -502,36 +503,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // LayerNorm for the transformer widths of the denoising path (c = 8 * LPR * VPL): LPR lanes per row, 32 / LPR rows
 // per warp, VPL 16-byte vectors per lane (row stays in registers), shuffle reductions over LPR lanes, two-pass variance.
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256) layernorm_sub_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, float eps,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            __nv_bfloat16* __restrict__ y, int ldy) {
+__global__ void __launch_bounds__(256, 3) layernorm_sub_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, float eps,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ y, int ldy) {
   constexpr int RPW = 32 / LPR;  // rows per warp
   constexpr int C = 8 * LPR * VPL;
+  // gamma / beta live in shared memory (not 2 x VPL x 8 registers): the kernel is HBM-bound and needs the occupancy -- three
+  // 256-thread CTAs per SM, each thread with its NEXT row's 16-byte loads already in flight while it reduces the current one.
+  __shared__ __align__(16) float s_ga[C];
+  __shared__ __align__(16) float s_be[C];
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    s_ga[ch] = gamma ? __ldg(gamma + ch) : 1.0f;
+    s_be[ch] = beta ? __ldg(beta + ch) : 0.0f;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  float ga[VPL][8], be[VPL][8];
+  uint4 nxt[VPL];
+  {
+    const long long row = warp_global * RPW + sub;
+    const __nv_bfloat16* xr = x + (size_t)(row < rows ? row : 0) * ldx;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = (l + i * LPR) * 8 + j;
-      ga[i][j] = gamma ? __ldg(gamma + ch) : 1.0f;
-      be[i][j] = beta ? __ldg(beta + ch) : 0.0f;
-    }
+    for (int i = 0; i < VPL; ++i) nxt[i] = __ldg(reinterpret_cast<const uint4*>(xr + (l + i * LPR) * 8));
   }
   for (long long r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
     const long long row = r0 + sub;
     const bool ok = row < rows;
-    const __nv_bfloat16* xr = x + (size_t)(ok ? row : 0) * ldx;
-    float f[VPL][8];
+    uint4 cur[VPL];  // the row stays PACKED in registers (unpacking bf16 is a shift/mask; 8 x VPL floats would spill at this occupancy)
     float sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + (l + i * LPR) * 8));
-      unpack8(u, f[i]);
+      cur[i] = nxt[i];
+      float f[8];
+      unpack8(cur[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += f[i][j];
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+    {
+      const long long rn = row + warps_total * RPW;  // prefetch this lane's next row
+      const __nv_bfloat16* xn = x + (size_t)(rn < rows ? rn : 0) * ldx;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) nxt[i] = __ldg(reinterpret_cast<const uint4*>(xn + (l + i * LPR) * 8));
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -539,9 +552,11 @@ __global__ void __launch_bounds__(256) layernorm_sub_kernel(const __nv_bfloat16*
     float sq = 0.0f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
+      float f[8];
+      unpack8(cur[i], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = f[i][j] - mean;
+        const float d = f[j] - mean;
         sq += d * d;
       }
     }
@@ -552,9 +567,15 @@ __global__ void __launch_bounds__(256) layernorm_sub_kernel(const __nv_bfloat16*
       __nv_bfloat16* yr = y + (size_t)row * ldy;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        float o[8];
+        const int ch = (l + i * LPR) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(s_ga + ch), g1 = *reinterpret_cast<const float4*>(s_ga + ch + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_be + ch), b1 = *reinterpret_cast<const float4*>(s_be + ch + 4);
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float f[8], o[8];
+        unpack8(cur[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * ga[i][j] + be[i][j];
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * ga[j] + be[j];
         *reinterpret_cast<uint4*>(yr + (l + i * LPR) * 8) = pack8(o);
       }
     }
@@ -564,7 +585,7 @@ __global__ void __launch_bounds__(256) layernorm_sub_kernel(const __nv_bfloat16*
 template <int LPR, int VPL>
 void launch_ln_sub(const void* x, int ldx, int rows, float eps, const float* gamma, const float* beta, void* y, int ldy, cudaStream_t stream) {
   constexpr int RPW = 32 / LPR;
-  const int grid = grid_for(ceil_div_ll(rows, RPW), 8, 8);
+  const int grid = grid_for(ceil_div_ll(rows, RPW), 8, 3);
   layernorm_sub_kernel<LPR, VPL><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, rows, eps, gamma, beta,
                                                            static_cast<__nv_bfloat16*>(y), ldy);
 }

@@ -111,7 +111,7 @@ def conv_section(B, only):
 
 def hbm(B):
     print("== HBM-bound ==")
-    for n, hw, c in [(B, 4096, 320), (B, 1024, 640), (B, 256, 1280), (B, 4096, 640), (B, 4096, 960), (B, 1024, 1920), (B, 64, 2560), (8, 262144, 128), (8, 65536, 256)]:
+    for n, hw, c in [(B, 4096, 320), (B, 1024, 640), (B, 256, 1280), (B, 4096, 640), (B, 4096, 960), (B, 1024, 1920), (B, 64, 2560), (2 * B, 1024, 640), (2 * B, 256, 1280), (2 * B, 4096, 320), (8, 262144, 128), (8, 65536, 256)]:
         x = rnd(n, hw, c)
         out = torch.empty_like(x)
         g, bt = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
@@ -124,7 +124,7 @@ def hbm(B):
         _lib.load().saspa_groupnorm_impl(0)
         print(f"groupnorm+silu {n}x{hw}x{c}: two-pass {res[0][0]:.3f} ms {res[0][1]:.0f} GB/s | auto {res[1][0]:.3f} ms {res[1][1]:.0f} GB/s algorithmic "
               f"({res[1][1] / PEAKS['hbm_gbs']:.2f} of HBM peak)")
-    for rows_, c in [(B * 4096, 320), (B * 1024, 640), (B * 256, 1280), (B * 77, 768)]:
+    for rows_, c in [(B * 4096, 320), (2 * B * 4096, 320), (2 * B * 1024, 640), (B * 1024, 640), (B * 256, 1280), (B * 77, 768)]:
         x = rnd(rows_, c)
         out = torch.empty_like(x)
         g, bt = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
