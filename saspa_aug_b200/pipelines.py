@@ -463,6 +463,31 @@ class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
     def encode_subject_prompt(self, prompt_ids: torch.Tensor, query_embeds: torch.Tensor) -> torch.Tensor:
         return self.text_encoder(prompt_ids.to(self.device), ctx_embeddings=query_embeds, ctx_begin_pos=self.ctx_begin_pos)
 
+    def _encode_call(self, prompt, prompt_ids, negative_prompt, negative_prompt_ids, do_cfg: bool, H: int, W: int, *, reference_u8=None,
+                     source_subject=None, target_subject=None, subject_ids=None, prompt_strength: float = 1.0, prompt_reps: int = 20):
+        """get_query_embeddings + encode_prompt (+ the plain negative-prompt encode) of BlipDiffusionControlNetPipeline.__call__
+        -> (text bf16 [B,77,D] with the subject embeddings spliced in, neg or None, None)."""
+        nq = self.qformer.cfg.num_query_tokens
+        if prompt_ids is None:
+            prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+            tgt = [target_subject] * len(prompts) if isinstance(target_subject, str) else list(target_subject)
+            full = build_blip_prompt(prompts, tgt, prompt_strength, prompt_reps)
+            prompt_ids = self.tokenizer(full, max_length=self.tokenizer.model_max_length - nq)  # encode_prompt: max_len = 77 - 16
+        B = prompt_ids.shape[0]
+        if subject_ids is None:
+            src = [source_subject] * B if isinstance(source_subject, str) else list(source_subject)
+            subject_ids = self.qformer_tokenizer(src)
+        elif isinstance(subject_ids, torch.Tensor):
+            subject_ids = list(subject_ids)
+        if reference_u8.shape[0] == 1 and B > 1:
+            reference_u8 = reference_u8.expand(B, -1, -1, -1).contiguous()
+        self._last_query = self.get_query_embeddings(reference_u8, subject_ids)
+        text = self.encode_subject_prompt(prompt_ids, self._last_query)
+        neg = None
+        if do_cfg:
+            neg = self.encode_prompt_ids(negative_prompt_ids) if negative_prompt_ids is not None else self._neg_embeds(negative_prompt, B).contiguous()
+        return text, neg, None
+
     @torch.no_grad()
     def __call__(self, prompt: Union[str, List[str], None] = None, reference_image=None, condtioning_image=None,
                  source_subject_category: Union[str, List[str], None] = None, target_subject_category: Union[str, List[str], None] = None,
@@ -472,30 +497,16 @@ class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
                  neg_ids: Optional[torch.Tensor] = None, subject_ids=None, return_latents_per_step: bool = False, **unused) -> PipelineOutput:
         ref_u8 = self._to_u8_batch(reference_image)
         control_u8 = self._to_u8_batch(condtioning_image)
-        nq = self.qformer.cfg.num_query_tokens
-        if prompt_ids is None:
-            prompts = [prompt] if isinstance(prompt, str) else list(prompt)
-            tgt = [target_subject_category] * len(prompts) if isinstance(target_subject_category, str) else list(target_subject_category)
-            full = build_blip_prompt(prompts, tgt, prompt_strength, prompt_reps)
-            prompt_ids = self.tokenizer(full, max_length=self.tokenizer.model_max_length - nq)  # encode_prompt: max_len = 77 - 16
-        B = prompt_ids.shape[0]
-        if subject_ids is None:
-            src = [source_subject_category] * B if isinstance(source_subject_category, str) else list(source_subject_category)
-            subject_ids = self.qformer_tokenizer(src)
-        elif isinstance(subject_ids, torch.Tensor):
-            subject_ids = list(subject_ids)
-        if ref_u8.shape[0] == 1 and B > 1:
-            ref_u8 = ref_u8.expand(B, -1, -1, -1).contiguous()
+        text, neg, _ = self._encode_call(prompt, prompt_ids, neg_prompt, neg_ids, guidance_scale > 1.0, height, width, reference_u8=ref_u8,
+                                         source_subject=source_subject_category, target_subject=target_subject_category, subject_ids=subject_ids,
+                                         prompt_strength=prompt_strength, prompt_reps=prompt_reps)
+        B = text.shape[0]
+        query = self._last_query
         if control_u8.shape[0] == 1 and B > 1:
             control_u8 = control_u8.expand(B, -1, -1, -1).contiguous()
         if control_u8.shape[1:3] != (height, width):
             raise ValueError(f"condtioning_image is {tuple(control_u8.shape[1:3])}, height/width say {(height, width)}: the reference passes the "
                              "control image's own size (run_aug.py:270-271)")
-        query = self.get_query_embeddings(ref_u8, subject_ids)
-        text = self.encode_subject_prompt(prompt_ids, query)
-        neg = None
-        if guidance_scale > 1.0:
-            neg = self.encode_prompt_ids(neg_ids) if neg_ids is not None else self._neg_embeds(neg_prompt, B).contiguous()
         shape = (B, self.vae_cfg.latent_channels, height // 8, width // 8)
         noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=torch.float32)
         per_step = [] if return_latents_per_step else None

@@ -228,7 +228,10 @@ def sample_prompts(prompts: Sequence[str], n_sources: int, cfg: AugConfig) -> Li
 
 
 def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: str, rank: int = 0, world: int = 1, io_threads: int = 8):
-    """The generation loop (run_aug.py:357-471) for this rank's shard.  Returns the list of (source index, i, path)."""
+    """The generation loop (run_aug.py:357-471) for this rank's shard.  Returns the list of (source index, i, path).
+    Works for the three ControlNet base models: SD v1.5 / SD-XL(-turbo) (text + added conditioning from the pipeline's own
+    ``_encode_call``) and BLIP-Diffusion (reference image = the source, subject categories = ``ds_utils.meta_class``,
+    run_aug.py:444-456; conditioning scale 1.0, no SDEdit)."""
     import torch
     from PIL import Image
 
@@ -259,7 +262,9 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: st
                 sources[index] = img
                 work.append((index, i, prompt, str(out_path)))
         dev = pipe.device
-        neg = pipe._neg_embeds(NEGATIVE_PROMPT, 1)
+        blip = "blip" in cfg.BASE_MODEL
+        assert not (blip and cfg.SDEDIT), "BLIP-Diffusion has no img2img ControlNet pipeline in the reference (run_aug.py:185-187)"
+        do_cfg = cfg.GUIDANCE_SCALE > 1.0
         for b0 in range(0, len(work), cfg.MICRO_BATCH):
             chunk = work[b0 : b0 + cfg.MICRO_BATCH]
             uniq = sorted({w[0] for w in chunk})
@@ -274,9 +279,12 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: st
                     cp = os.path.join(out_dir, f"{Path(paths[u]).stem[:MAX_FILENAME_LENGTH]}_control.png")
                     if not os.path.exists(cp):
                         pool.submit(Image.fromarray(edges[u_i].cpu().numpy()).save, cp)
-            ids = pipe.tokenizer([w[2] for w in chunk])
-            text = pipe.encode_prompt_ids(ids)
             H, W = src_t.shape[1:3]
+            extra = {}
+            if blip:
+                subject = getattr(ds_utils, "meta_class", "object")
+                extra = dict(reference_u8=src_t.index_select(0, sel).contiguous(), source_subject=subject, target_subject=subject)
+            text, neg, added = pipe._encode_call([w[2] for w in chunk], None, NEGATIVE_PROMPT, None, do_cfg, H, W, **extra)
             shape = (1, pipe.vae_cfg.latent_channels, H // 8, W // 8)
             noise, post = [], []
             for (index, i, _, _) in chunk:
@@ -287,10 +295,10 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: st
             noise = torch.cat(noise).to(dev)
             post = torch.cat(post).to(dev) if cfg.SDEDIT else None
             try:
-                imgs = pipe.generate_batch(text, neg.expand(len(chunk), -1, -1).contiguous(), None, src_t.index_select(0, sel) if cfg.SDEDIT else None,
+                imgs = pipe.generate_batch(text, neg, None, src_t.index_select(0, sel) if cfg.SDEDIT else None,
                                            noise=noise, noise_posterior=post, num_inference_steps=cfg.NUM_INFERENCE_STEPS, guidance_scale=cfg.GUIDANCE_SCALE,
-                                           strength=cfg.SDEDIT_STRENGTH, controlnet_conditioning_scale=cfg.CONTROLNET_CONDITIONING_SCALE,
-                                           control_bf16=ctrl.index_select(0, sel))
+                                           strength=cfg.SDEDIT_STRENGTH, controlnet_conditioning_scale=1.0 if blip else cfg.CONTROLNET_CONDITIONING_SCALE,
+                                           control_bf16=ctrl.index_select(0, sel), added=added)
             except RuntimeError as e:  # the reference logs OOM-style errors and leaves the loop (run_aug.py:493-500)
                 logging.exception(e)
                 num_errors += 1

@@ -65,3 +65,35 @@ def test_driver_filter_json_roundtrip(cuda_device, tmp_path):
         # same seeds/prompts/noise; a different micro-batch composition only changes tile mapping and the order of the
         # GroupNorm atomics (fp32 rounding), which a random-init recurrent net amplifies to a few grey levels
         assert np.abs(a - b).mean() < 1.0 and np.abs(a - b).max() <= 16, (index, i, np.abs(a - b).mean(), np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("base_model", ["tiny_xl", "tiny_blip"])
+def test_driver_other_base_models(cuda_device, tmp_path, base_model):
+    """The sharded loop with the SD-XL(-turbo) and BLIP-Diffusion pipelines (added conditioning / subject embeddings come from the
+    pipeline's own _encode_call): files are written under the reference's naming, images are non-degenerate, and a generated image
+    equals the one the reference-style single call (pass_thorugh_pipe with the same per-item generator) produces."""
+    from PIL import Image
+
+    ds = SyntheticUtils(root=str(tmp_path / "ds"), n_images=3, size=(128, 128)).materialize()
+    cfg = run_aug.AugConfig(BASE_MODEL=base_model, RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4)
+    if base_model == "tiny_xl":
+        cfg.GUIDANCE_SCALE = 0.0  # sd_xl-turbo rule (run_aug.py:567-570)
+    pipe = run_aug.init_pipeline(base_model, "canny", 0, sampler="ddim")
+    out_dir = run_aug.output_folder(str(tmp_path / "ds"), cfg)
+    prompts = [f"an airplane parked on wet tarmac {i}." for i in range(8)]
+    written = run_aug.generate(cfg, ds, pipe, prompts, out_dir)
+    assert len(written) == 6 and all(os.path.exists(p) for _, _, p in written)
+    for _, _, p in written:
+        a = np.asarray(Image.open(p))
+        assert a.shape == (128, 128, 3) and a.std() > 1.0
+    # one item through the reference's per-image call path with the same per-item seed
+    index, i, path = written[0]
+    src = Image.open(ds.original_images_paths[index]).convert("RGB")
+    canny = run_aug.generate_canny(src, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, cfg.RESOLUTION)
+    prompt = run_aug.sample_prompts(prompts, len(ds.original_images_paths), cfg)[index][i]
+    g = torch.Generator().manual_seed(run_aug.item_seed(cfg.SEED, index, i))
+    one = run_aug.pass_thorugh_pipe("blip_diffusion" if "blip" in base_model else "sd_xl-turbo", pipe, prompt, src, 0, cfg.SDEDIT_STRENGTH,
+                                    cfg.NUM_INFERENCE_STEPS, g, cfg.GUIDANCE_SCALE, cfg.CONTROLNET_CONDITIONING_SCALE, control_image=canny,
+                                    blip_src_category=ds.meta_class, blip_target_category=ds.meta_class)
+    a, b = np.asarray(one).astype(int), np.asarray(Image.open(path)).astype(int)
+    assert np.abs(a - b).mean() < 1.0 and np.abs(a - b).max() <= 16, (np.abs(a - b).mean(), np.abs(a - b).max())
