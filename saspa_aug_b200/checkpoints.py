@@ -536,6 +536,48 @@ def clip_vit_tiny_kwargs() -> dict:
     return dict(embed_dim=64, v_width=128, v_layers=2, patch=14, res=56, t_width=64, t_layers=2, vocab=1000, ctx=77)
 
 
+def safety_checker_shapes(width=1024, layers=24, patch=14, res=224, proj=768, n_concepts=17, n_special=3) -> Shapes:
+    """State-dict layout of diffusers' StableDiffusionSafetyChecker (pipelines/stable_diffusion/safety_checker.py; loaded by default with
+    runwayml/stable-diffusion-v1-5): transformers CLIPVisionModel (ViT-L/14) + visual_projection + concept / special-care embeddings and
+    their thresholds (the ``*_weights`` buffers)."""
+    v = "vision_model.vision_model."
+    yield v + "embeddings.class_embedding", (width,)
+    yield v + "embeddings.patch_embedding.weight", (width, 3, patch, patch)
+    yield v + "embeddings.position_embedding.weight", ((res // patch) ** 2 + 1, width)
+    yield from _norm(v + "pre_layrnorm", width)  # (sic) transformers' spelling
+    for i in range(layers):
+        q = f"{v}encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield from _lin(q + "self_attn." + nm, width, width)
+        yield from _norm(q + "layer_norm1", width)
+        yield from _lin(q + "mlp.fc1", width, 4 * width)
+        yield from _lin(q + "mlp.fc2", 4 * width, width)
+        yield from _norm(q + "layer_norm2", width)
+    yield from _norm(v + "post_layernorm", width)
+    yield "visual_projection.weight", (proj, width)
+    yield "concept_embeds", (n_concepts, proj)
+    yield "special_care_embeds", (n_special, proj)
+    yield "concept_embeds_weights", (n_concepts,)
+    yield "special_care_embeds_weights", (n_special,)
+
+
+def safety_checker_tiny_kwargs() -> dict:
+    return dict(width=128, layers=2, patch=14, res=56, proj=64)
+
+
+def random_safety_checker_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tensor]:
+    """Seeded init for the safety checker: CLIP-style weights; thresholds drawn around the typical cosine of random embeddings so that
+    both outcomes (flagged / clean) and the special-care adjustment occur on synthetic images."""
+    sd = random_state_dict(shapes, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in ("concept_embeds", "special_care_embeds"):
+        sd[k] = torch.randn(sd[k].shape, generator=g)
+    sigma = sd["concept_embeds"].shape[1] ** -0.5  # std of the cosine between random directions
+    sd["concept_embeds_weights"] = sigma * (2.0 + 0.3 * torch.randn(sd["concept_embeds_weights"].shape, generator=g))
+    sd["special_care_embeds_weights"] = sigma * (1.3 + 0.3 * torch.randn(sd["special_care_embeds_weights"].shape, generator=g))
+    return sd
+
+
 def random_filter_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tensor]:
     """He-normal conv/linear weights (ReLU nets), BatchNorm affine ~ N(1,.1)/N(0,.1) with non-trivial running stats,
     the last BN scale of each residual branch damped (x0.5) so depth does not blow the activations up."""

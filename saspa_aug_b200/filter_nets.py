@@ -209,6 +209,73 @@ class CLIPViT(_CLIPTextTower):
         return ops.gemm(cls, self.proj_t, out_fp32=True)
 
 
+class SafetyChecker:
+    """diffusers StableDiffusionSafetyChecker (pipelines/stable_diffusion/safety_checker.py), loaded by default with the SD v1.5
+    pipelines the reference builds (run_aug.py:200-211): CLIP ViT-L/14 vision tower -> pooled (post-LayerNorm class token) ->
+    visual_projection -> cosine against 3 special-care and 17 concept embeddings; an image is flagged when any
+    round(cos - threshold + adjustment, 3) > 0, adjustment = 0.01 once a special-care concept fired; flagged images are blacked out.
+    Feature extractor = CLIPImageProcessor: shortest side -> 224 (PIL bicubic, bit-exact kernel), center crop, CLIP mean/std."""
+
+    def __init__(self, sd: SD, device="cuda"):
+        dev = torch.device(device)
+        self.dev = dev
+        v = "vision_model.vision_model."
+        width = sd[v + "embeddings.class_embedding"].shape[0]
+        layers = []
+        i = 0
+        while f"{v}encoder.layers.{i}.layer_norm1.weight" in sd:
+            q = f"{v}encoder.layers.{i}.self_attn."
+            wqkv = torch.cat([sd[q + "q_proj.weight"], sd[q + "k_proj.weight"], sd[q + "v_proj.weight"]], 0)
+            bqkv = torch.cat([sd[q + "q_proj.bias"], sd[q + "k_proj.bias"], sd[q + "v_proj.bias"]], 0)
+            p = f"{v}encoder.layers.{i}."
+            layers.append(snn.ViTEncoder._layer(sd, dev, wqkv, bqkv, q + "out_proj", p + "layer_norm1", p + "layer_norm2", p + "mlp.fc1", p + "mlp.fc2"))
+            i += 1
+        self.tower = snn.ViTEncoder(dev, patch_w=sd[v + "embeddings.patch_embedding.weight"], class_emb=sd[v + "embeddings.class_embedding"],
+                                    pos_emb=sd[v + "embeddings.position_embedding.weight"], pre_ln=snn.Norm(sd, v + "pre_layrnorm", dev), layers=layers,
+                                    post_ln=None, heads=max(1, width // 64), act=ACT_QUICKGELU, eps=1e-5)
+        self.post_ln = snn.Norm(sd, v + "post_layernorm", dev)
+        self.proj = snn._bf(sd["visual_projection.weight"], dev)
+        self.resolution = self.tower.patch * int(round((sd[v + "embeddings.position_embedding.weight"].shape[0] - 1) ** 0.5))
+        self.n_special = sd["special_care_embeds"].shape[0]
+        self.embeds = torch.cat([sd["special_care_embeds"], sd["concept_embeds"]], 0).float().contiguous().to(dev)
+        self.thresholds = torch.cat([sd["special_care_embeds_weights"], sd["concept_embeds_weights"]], 0).float().tolist()
+
+    def cosines(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """u8 [n,H,W,3] (device) -> fp32 [n, 3 + 17] cosine of the projected image embedding with (special-care | concept) embeddings."""
+        n, H, W, _ = images_u8.shape
+        R = self.resolution
+        oh, ow = (R, int(R * W / H)) if H <= W else (int(R * H / W), R)
+        r = images_u8 if (oh, ow) == (H, W) else ops.resize_pil(images_u8.contiguous(), oh, ow, "bicubic")
+        x = ops.crop_normalize(r, int(round((oh - R) / 2.0)), int(round((ow - R) / 2.0)), R, R, CLIP_MEAN, CLIP_STD, out_c=3)
+        h = self.tower(x, apply_post_ln=False)
+        pooled = ops.layernorm(h[:, 0].contiguous(), 1e-5, self.post_ln.g, self.post_ln.b)
+        emb = ops.gemm(pooled, self.proj, out_fp32=True)
+        cos, _ = ops.clip_score_argmax(emb, self.embeds, 1.0)
+        return cos
+
+    def decide(self, cos_rows) -> List[bool]:
+        """The reference rule on host floats (exactly safety_checker.py's loop, including the round(., 3))."""
+        out = []
+        for row in cos_rows:
+            adjustment = 0.0
+            for c in range(self.n_special):
+                if round(row[c] - self.thresholds[c] + adjustment, 3) > 0:
+                    adjustment = 0.01
+            bad = any(round(row[c] - self.thresholds[c] + adjustment, 3) > 0 for c in range(self.n_special, len(self.thresholds)))
+            out.append(bad)
+        return out
+
+    @torch.no_grad()
+    def __call__(self, images_u8: torch.Tensor):
+        """-> (images with flagged ones zeroed, has_nsfw_concept list)."""
+        cos = self.cosines(images_u8).cpu().tolist()
+        flags = self.decide(cos)
+        if any(flags):
+            images_u8 = images_u8.clone()
+            images_u8[torch.tensor(flags, device=images_u8.device)] = 0  # placement: black image (np.zeros in the reference)
+        return images_u8, flags
+
+
 class AugmentationFilter:
     """keep = (label in top-k(WSDAN logits)) AND (argmax CLIP(img, [basic prompt, 6 negatives]) == 0)
     (all_utils/utils.py:357-365, :169-177, :401-404), on batches of u8 images resident on the device."""

@@ -78,6 +78,10 @@ class SaspaControlNetPipeline:
         self._graphs = {}
         self.use_cuda_graph = False
         self.vae_micro_batch = 8
+        # diffusers loads StableDiffusionSafetyChecker by default with SD v1.5 (filter_nets.SafetyChecker); None = safety_checker=None.
+        # Random-init runs keep it off (a random checker would blank images at random); assign one built from real weights to match
+        # the reference pipeline bit for bit in behaviour.
+        self.safety_checker = None
 
     # ---- construction -----------------------------------------------------------------------
     @classmethod
@@ -277,6 +281,9 @@ class SaspaControlNetPipeline:
         out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, num_inference_steps=num_inference_steps,
                                   guidance_scale=guidance_scale, strength=strength, controlnet_conditioning_scale=controlnet_conditioning_scale,
                                   step_callback=cb, added=added)
+        nsfw = None
+        if self.safety_checker is not None:  # run_safety_checker of the SD v1.5 pipelines
+            out, nsfw = self.safety_checker(out)
         arr = out.cpu().numpy()
         if output_type == "pil":
             from PIL import Image
@@ -284,7 +291,7 @@ class SaspaControlNetPipeline:
             images = [Image.fromarray(a) for a in arr]
         else:
             images = [a for a in arr]
-        return PipelineOutput(images=images, nsfw_content_detected=None, latents_per_step=per_step)
+        return PipelineOutput(images=images, nsfw_content_detected=nsfw, latents_per_step=per_step)
 
 
 class SaspaSDXLControlNetPipeline(SaspaControlNetPipeline):

@@ -203,3 +203,63 @@ def test_filter_semantic_decisions_identical_vit_l14(cuda_device):
     err = (out["clip_logits"].cpu() - cl).abs().max().item()
     print(f"ViT-L/14 CLIP logits max err {err:.4g}; min top1-top2 gap {(top2[:, 0] - top2[:, 1]).min().item():.4g}; kept {int((cl.argmax(-1) == 0).sum())}/{n}")
     assert torch.equal(out["semantic"].cpu(), (cl.argmax(-1) == 0).to(torch.uint8))
+
+
+@pytest.mark.parametrize("name,n", [("tiny", 24), ("vit_l14", 12)])
+def test_safety_checker_matches_oracle(cuda_device, name, n):
+    """StableDiffusionSafetyChecker (SD v1.5's default-loaded checker): cosines vs the fp32 oracle (transformers CLIPVisionModel tower)
+    and IDENTICAL flag decisions / blacked-out images; a score within 2e-3 of zero (the rule rounds to 3 decimals) would make the
+    comparison ill-posed and is reported instead of silently passing."""
+    from oracle import safety_checker as osc
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200.filter_nets import SafetyChecker
+
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    kw = ck.safety_checker_tiny_kwargs() if name == "tiny" else {}
+    sd = ck.random_safety_checker_state_dict(ck.safety_checker_shapes(**kw), 3)
+    o = osc.SafetyCheckerOracle(**kw).eval()
+    o.load_state_dict(sd, strict=False)
+    imgs = np.stack([synthetic_source(100 + i, 96, 128, kind=("blobs", "noise", "smooth")[i % 3]) for i in range(n)])
+    x = osc.clip_image_processor(imgs, o.res)
+    sp, co = o.cosines(x)
+    want_img, want_flags, res = o(x, imgs)
+    m = SafetyChecker(sd)
+    cos = m.cosines(torch.from_numpy(imgs).cuda()).cpu()
+    ref = torch.cat([sp, co], 1)
+    err = (cos - ref).abs().max().item()
+    margins = [abs(v) for r in res for v in list(r["special_scores"].values()) + list(r["concept_scores"].values())]
+    print(f"safety checker {name}: cosine max err {err:.4g}; smallest |score| {min(margins):.4g}; flagged {sum(want_flags)}/{n}")
+    assert err < 1e-2, err
+    got_img, got_flags = m(torch.from_numpy(imgs).cuda())
+    near = [i for i, r in enumerate(res) if min(abs(v) for v in list(r["special_scores"].values()) + list(r["concept_scores"].values())) < 2 * err + 1e-3]
+    for i in range(n):
+        if i in near:
+            continue  # within the numerical error of the rounding boundary: decision not comparable
+        assert got_flags[i] == want_flags[i], (i, res[i])
+        assert np.array_equal(got_img[i].cpu().numpy(), want_img[i])
+    assert len(near) <= n // 3, near
+
+
+def test_pipeline_safety_checker_hook(cuda_device):
+    """run_safety_checker in the pipeline call: flagged images come back black and nsfw_content_detected is reported."""
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200.filter_nets import SafetyChecker
+    from saspa_aug_b200.pipelines import SaspaControlNetPipeline
+    from saspa_aug_b200.synthetic import synthetic_token_ids
+
+    pipe = SaspaControlNetPipeline.random_init("tiny", seed=7, sampler="ddim", img2img=False)
+    ctrl = np.zeros((4, 128, 128, 3), np.uint8)
+    ctrl[:, 30:90, 64] = 255
+    kw = dict(prompt_ids=synthetic_token_ids(1, batch=4, vocab=1000), negative_prompt_ids=synthetic_token_ids(2, batch=4, vocab=1000), image=ctrl,
+              num_inference_steps=2, guidance_scale=7.5, output_type="np")
+    plain = pipe(generator=torch.Generator().manual_seed(1), **kw)
+    assert plain.nsfw_content_detected is None
+    sd = ck.random_safety_checker_state_dict(ck.safety_checker_shapes(**ck.safety_checker_tiny_kwargs()), 3)
+    sd["concept_embeds_weights"] = sd["concept_embeds_weights"] - 10.0  # every image trips a concept
+    pipe.safety_checker = SafetyChecker(sd)
+    out = pipe(generator=torch.Generator().manual_seed(1), **kw)
+    assert out.nsfw_content_detected == [True] * 4 and all((im == 0).all() for im in out.images)
+    sd["concept_embeds_weights"] = sd["concept_embeds_weights"] + 20.0  # none does
+    pipe.safety_checker = SafetyChecker(sd)
+    out = pipe(generator=torch.Generator().manual_seed(1), **kw)
+    assert out.nsfw_content_detected == [False] * 4 and all(np.array_equal(a, b) for a, b in zip(out.images, plain.images))

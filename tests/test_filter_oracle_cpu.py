@@ -134,3 +134,24 @@ def test_clip_vit_oracle_matches_transformers_clipmodel():
 def test_clip_vit_l14_shapes():
     n = ck.count_params(ck.clip_vit_shapes())
     assert 420e6 < n < 435e6, n  # openai ViT-L/14: 427.6 M parameters
+
+
+def test_safety_checker_oracle_loads_product_layout_and_flags_both_ways():
+    """The product's checkpoint layout == diffusers' StableDiffusionSafetyChecker keys (strict load into the oracle, whose tower is
+    transformers' CLIPVisionModel); with the seeded thresholds both outcomes occur, and flagged images come back black."""
+    from oracle import safety_checker as osc
+
+    kw = ck.safety_checker_tiny_kwargs()
+    sd = ck.random_safety_checker_state_dict(ck.safety_checker_shapes(**kw), 3)
+    m = osc.SafetyCheckerOracle(**kw).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    imgs = np.stack([synthetic_source(100 + i, 96, 128, kind=("blobs", "noise", "smooth")[i % 3]) for i in range(12)])
+    x = osc.clip_image_processor(imgs, kw["res"])
+    assert x.shape == (12, 3, 56, 56)
+    out, flags, res = m(x, imgs)
+    assert 0 < sum(flags) < 12, flags
+    for i, f in enumerate(flags):
+        assert (out[i] == 0).all() if f else np.array_equal(out[i], imgs[i])
+    n = ck.count_params(ck.safety_checker_shapes())
+    assert 300e6 < n < 310e6, n  # CLIP ViT-L/14 vision tower + projection: 304 M
