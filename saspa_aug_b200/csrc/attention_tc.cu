@@ -60,7 +60,7 @@ struct AttnParams {
   int heads, tq, tkv;
   float scale_log2;
   int causal;
-  int debug;  // timing experiments only (tools_attn_bench.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
+  int debug;  // timing experiments only (tools/attn_debug.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
 };
 
 template <int D>

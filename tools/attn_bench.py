@@ -1,9 +1,13 @@
 """A/B timing of the two attention kernels (mma.sync flash vs tcgen05/TMEM) on the SD v1.5 shapes of one UNet step at
 micro-batch 16 (32 CFG rows).  CUDA events, L2 flushed between timed launches.  A tuning aid, not the bench.py contract."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import torch
 
 from saspa_aug_b200 import _lib, ops
-from tools_kernel_bench import rnd, timeit
+from kernel_bench import rnd, timeit
 
 
 def main():

@@ -1,8 +1,12 @@
 """Where does the d = 40 self-attention time go?  Times the tcgen05 kernel with parts disabled (results are wrong on purpose)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import ctypes
 import torch
 from saspa_aug_b200 import _lib, ops
-from tools_kernel_bench import rnd, timeit
+from kernel_bench import rnd, timeit
 
 lib = ctypes.CDLL(_lib.SO_PATH)
 _lib.load().saspa_attention_impl(2)

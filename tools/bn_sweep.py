@@ -1,8 +1,12 @@
 """MMA efficiency by N-tile width: a compute-bound GEMM (148 M-tiles, K = 4096, N = 2560) with BN forced to 64/128/160/256."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import ctypes
 import torch
 from saspa_aug_b200 import _lib, ops
-from tools_kernel_bench import rnd, timeit
+from kernel_bench import rnd, timeit
 
 lib = ctypes.CDLL(_lib.SO_PATH)
 M, N, K = 148 * 128, 2560, 4096

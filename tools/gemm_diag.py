@@ -1,5 +1,9 @@
 """Diagnostic for the tcgen05 GEMM on a real B200: prints the structure of any mismatch on small cases
 (which rows / columns / k-blocks are wrong) so descriptor or swizzle mistakes can be read off one run."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import sys
 
 import torch

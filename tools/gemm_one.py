@@ -1,9 +1,13 @@
 """Launches the tcgen05 GEMM / implicit-conv kernel on the dominant SD v1.5 shapes (for ncu captures).
 Order per round: conv3x3 32x64x64 320->320, GEGLU GEMM 131072x2560x320, in-place residual GEMM 131072x320x320."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import torch
 
 from saspa_aug_b200 import ops
-from tools_kernel_bench import rnd
+from kernel_bench import rnd
 
 B = 32
 x, wk = rnd(B, 64, 64, 320), rnd(320, 9 * 320) * 0.02

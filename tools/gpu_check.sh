@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs each GPU test file in its own process (a trapped kernel poisons the CUDA context) with a timeout,
-# collecting logs under gpurun_out/.  Usage (on the GPU box): bash tools_gpu_check.sh [files...]
+# collecting logs under gpurun_out/.  Usage (on the GPU box): bash tools/gpu_check.sh [files...]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 FILES=${@:-"tests/test_canny_gpu.py tests/test_gemm_gpu.py tests/test_elementwise_gpu.py tests/test_attention_gpu.py tests/test_filter_gpu.py"}

@@ -1,5 +1,9 @@
 """Per-kernel microbenchmarks on a real B200 (CUDA events, L2-flushed between timed launches).
 Prints achieved TFLOP/s or GB/s against MEASURED_PEAKS.json.  Not the bench.py contract; a tuning aid."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import json
 import os
 import sys

@@ -1,8 +1,12 @@
 """One micro-batch generation bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off`.
 Usage (GPU box):
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-      --log-file gpurun_out/launches.csv python tools_profile_step.py [--mb 16] [--steps 2] [--decode]
+      --log-file gpurun_out/launches.csv python tools/profile_step.py [--mb 16] [--steps 2] [--decode]
 Not the bench.py contract: numbers printed under ncu are never bench values; this only produces launch lists."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root (python tools/<name>.py)
 import argparse
 
 import numpy as np
