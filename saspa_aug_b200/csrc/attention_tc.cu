@@ -6,14 +6,14 @@
 // AttnProcessor2_0 (reference call site: pipe(**pipe_args), run_aug/run_aug.py:278).
 //
 // One CTA owns 256 queries of one (batch, head) as two 128-row tiles and sweeps the keys in tiles of
-// BKV (128 for head_dim <= 64, else 64).  Ten warps:
+// BKV (128 for head_dim <= 64, else 64).  Twelve warps:
 //   warp 0     TMA producer: Q once, then K_j / V_j into a STAGES-deep ring of 128B-swizzled smem tiles
 //              (64-column panels straight out of the fused [b, t, 3c] QKV buffer -- nothing is repacked in HBM).
-//   warp 1     owns the 512 TMEM columns; one lane issues every tcgen05.mma:
+//   warp 1, 11 MMA issuers of query tile 0 / 1 (warp 1 also owns the 512 TMEM columns); one elected lane issues every tcgen05.mma:
 //                S_i  = Q_i K_j^T          (SS: both operands K-major in smem)           -> TMEM
 //                O_i += P_i V_j            (TS: P_i read from TMEM, V_j MN-major in smem) -> TMEM
-//              issue order per key tile j:  QK(0,j+1) QK(1,j+1) PV(0,j) PV(1,j), so the next S is ready
-//              before the softmax warps finish the current one.
+//              issue order per tile and key tile j:  QK(i,j+1) then PV(i,j), so the next S is ready before the softmax warps
+//              finish the current one; the two tiles run on independent barriers (see the issuer code).
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1: one thread per query row (no shuffles):
 //              tcgen05.ld the S row, release S, running max with lazy rescale (O is only rescaled in TMEM
 //              when the max grows by more than 2^8), p = ex2(s*c - m), bf16 P packed two per column back
@@ -31,7 +31,7 @@
 namespace {
 using namespace tcx;
 
-constexpr int ATC_THREADS = 352;
+constexpr int ATC_THREADS = 384;
 constexpr int QROWS = 128;
 
 template <int D>
@@ -60,10 +60,11 @@ struct AttnParams {
   int heads, tq, tkv;
   float scale_log2;
   int causal;
+  unsigned long long* trace;  // phase timers of one CTA (tools/attn_debug.py --trace); nullptr in production
   int debug;  // timing experiments only (tools/attn_debug.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
 };
 
-template <int D>
+template <int D, bool TRACE>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnParams p) {
@@ -104,9 +105,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     mbar_init(q_ready, 256);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], 2);  // both MMA issuers
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], 2);
       mbar_init(&v_ready[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -146,9 +147,18 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
           tma_load_3d(&tmV, sV + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES, &v_full[s], col0 + 64 * pn, j * BKV, b);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 11) {
+    // ===================== MMA issuers: warp 1 serves query tile 0, warp 11 query tile 1 =====================
+    // One issuer per tile, each on its own barriers (Q K^T of key tile j+1 as soon as the tile's softmax warps hold S_j in
+    // registers, P V of key tile j as soon as P_j is in TMEM): the two tiles drift into opposite phases -- one on the MUFU, the
+    // other on TMEM / ALU -- instead of contending for the same pipe in lockstep, and a tile's next S is never held back by
+    // the other tile's softmax.  The hardware interleaves the two instruction streams in the tensor pipe; a K / V ring stage
+    // is released when BOTH issuers have committed it (mbarrier count 2).
+    // Each WHOLE warp runs its loop converged and one elected lane issues every tcgen05 instruction: under a divergent
+    // `if (lane == 0)` ptxas wraps each UTCHMMA in an ELECT / R2UR / branch loop (~87 clk per MMA, measured with the phase
+    // timers: issuing the 16 P V MMAs of a key tile took 1400 clk and bounded the d = 40 kernel).
+    {
+      const int it = warp == 1 ? 0 : 1;
       constexpr uint32_t idesc_qk = make_idesc(QROWS, BKV, 0);
       constexpr uint32_t idesc_pv = make_idesc(QROWS, ON, 1);
       auto issue_qk = [&](int i, int s) {
@@ -159,47 +169,60 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
           const int pn = ks >> 2, kk = ks & 3;
           const uint64_t a = make_smem_desc(smem_u32(sQ + (i * NPAN + pn) * C::QPAN_BYTES) + kk * 32);
           const uint64_t bd = make_smem_desc(smem_u32(sK + s * C::KV_STAGE_BYTES + pn * C::KPAN_BYTES) + kk * 32);
-          tc_mma_bf16(d_tmem, a, bd, idesc_qk, ks != 0 ? 1u : 0u);
+          if (elect_one()) tc_mma_bf16(d_tmem, a, bd, idesc_qk, ks != 0 ? 1u : 0u);
         }
-        tc_commit(&s_full[i]);
+        if (elect_one()) tc_commit(&s_full[i]);
       };
+      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 3 && it == 0;
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tt0 = TRACE ? clock64() : 0;
+#define ATC_TRACE(n)                    \
+  if constexpr (TRACE) {                \
+    if (tr) {                           \
+      const long long tt1 = clock64();  \
+      tacc[n] += tt1 - tt0;             \
+      tt0 = tt1;                        \
+    }                                   \
+  }
       mbar_wait(PAD_Q ? q_ready : q_full, 0);
       tc_fence_after();
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      tc_commit(&k_empty[0]);
+      issue_qk(it, 0);
+      if (elect_one()) tc_commit(&k_empty[0]);
+      ATC_TRACE(0)
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % STAGES;
         if (j + 1 < n_tiles) {
           const int s1 = (j + 1) % STAGES;
           mbar_wait(&k_full[s1], ((j + 1) / STAGES) & 1);
-          for (int i = 0; i < 2; ++i) {
-            mbar_wait(&s_free[i], j & 1);  // softmax(i, j) holds its S row in registers
-            tc_fence_after();
-            issue_qk(i, s1);
-          }
-          tc_commit(&k_empty[s1]);
+          ATC_TRACE(1)
+          mbar_wait(&s_free[it], j & 1);  // the tile's softmax warps hold S_j in registers
+          tc_fence_after();
+          ATC_TRACE(2)
+          issue_qk(it, s1);
+          if (elect_one()) tc_commit(&k_empty[s1]);
+          ATC_TRACE(4)
         }
         mbar_wait(C::ONES ? &v_ready[s] : &v_full[s], (j / STAGES) & 1);
+        ATC_TRACE(5)
+        mbar_wait(&p_full[it], j & 1);
         tc_fence_after();
-        // the two query tiles accumulate into independent TMEM regions: interleaving their k-steps hides part of the
-        // per-instruction latency of these small (128 x 48 x 16) MMAs (measured -6% on the d = 40 layers)
-        mbar_wait(&p_full[0], j & 1);
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
+        ATC_TRACE(6)
+        if (!(p.debug & 2)) {
 #pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          if (p.debug & 2) break;
-          const uint64_t bd = make_smem_desc_mn(smem_u32(sV + s * C::KV_STAGE_BYTES) + ks * 2048, C::KPAN_BYTES);
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            tc_mma_bf16_ts(tmem_base + C::O_OFF + i * ON, tmem_base + C::P_OFF + i * (BKV / 2) + ks * 8, bd, idesc_pv, (j > 0 || ks != 0) ? 1u : 0u);
+          for (int ks = 0; ks < BKV / 16; ++ks) {
+            const uint64_t bd = make_smem_desc_mn(smem_u32(sV + s * C::KV_STAGE_BYTES) + ks * 2048, C::KPAN_BYTES);
+            if (elect_one())
+              tc_mma_bf16_ts(tmem_base + C::O_OFF + it * ON, tmem_base + C::P_OFF + it * (BKV / 2) + ks * 8, bd, idesc_pv, (j > 0 || ks != 0) ? 1u : 0u);
+          }
         }
-        tc_commit(&o_done[0]);
-        tc_commit(&o_done[1]);
-        tc_commit(&v_empty[s]);
+        if (elect_one()) tc_commit(&o_done[it]);
+        if (elect_one()) tc_commit(&v_empty[s]);
+        ATC_TRACE(7)
+      }
+      if constexpr (TRACE) {
+        if (tr && lane == 0)
+          for (int n = 0; n < 8; ++n) p.trace[n] = (unsigned long long)tacc[n];
       }
     }
   } else if (warp == 10) {
@@ -239,11 +262,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       mbar_arrive(q_ready);
     }
 
+    const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 3 && lane == 0 && (warp == 2 || warp == 6);
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tt0 = TRACE ? clock64() : 0;
     float m_used = -INFINITY;  // exponent reference (log2 domain); lags the true running max by at most 8
     float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // unused when the P V MMA accumulates the row sum (C::ONES)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
+      ATC_TRACE(0)
       uint32_t su[BKV];
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) tc_ld32p(t_s + c, &su[c]);
@@ -251,6 +277,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[i]);
+      ATC_TRACE(1)
 
       const int kv0 = j * BKV;
       if (kv0 + BKV > p.tkv) {
@@ -301,6 +328,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         }
       }
 
+      // One-time phase offset: tile 1 enters its first exponential phase only when tile 0 has left its own, so the two tiles
+      // start out in opposite phases (one on the MUFU, the other on TMEM / ALU) instead of halving each other's MUFU rate in
+      // lockstep; nothing re-synchronises them afterwards (measured: -14 % on d = 40; a strict per-tile ping-pong was slower).
+      if (j == 0 && i == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
+      ATC_TRACE(2)
       const float neg_m = -m_used;
       uint32_t pk[BKV / 2];
       if (p.debug & 1) {  // timing experiment: no exponentials at all
@@ -319,16 +351,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
           pk[c >> 1] = pack_bf16(p0, p1);
         }
       }
+      if (j == 0 && i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+      ATC_TRACE(3)
       if (!p_free) {  // P V of the previous key tile must have consumed P_i
         mbar_wait(&o_done[i], (j - 1) & 1);
         tc_fence_after();
       }
+      ATC_TRACE(4)
 #pragma unroll
       for (int c = 0; c < BKV / 2; c += 32) tc_st32(t_p + c, &pk[c]);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[i]);
+      ATC_TRACE(5)
+    }
+    if constexpr (TRACE) {
+      if (tr)
+        for (int n = 0; n < 8; ++n) p.trace[8 + 8 * i + n] = (unsigned long long)tacc[n];
     }
 
     // ---- epilogue: O / l -> global ----
@@ -414,13 +454,15 @@ int encode_rows3d(CUtensorMap* tm, const void* base, int cols, int rows, int bat
 
 int g_attn_debug = 0;
 
-template <int D>
-int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+unsigned long long* g_attn_trace = nullptr;
+
+template <int D, bool TRACE>
+int launch_tc_impl(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
               float scale, int causal, cudaStream_t stream) {
   using C = ACfg<D>;
   static bool configured = false;
   if (!configured) {
-    SASPA_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SASPA_CUDA(cudaFuncSetAttribute((attn_tc_kernel<D, TRACE>), cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -437,10 +479,19 @@ int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.debug = g_attn_debug;
+  p.trace = g_attn_trace;
   dim3 grid(ceil_div(tq, 2 * QROWS), batch * heads);
-  attn_tc_kernel<D><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
+  attn_tc_kernel<D, TRACE><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
+}
+
+template <int D>
+int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
+              float scale, int causal, cudaStream_t stream) {
+  if (g_attn_trace != nullptr && (D == 40 || D == 128))  // the phase-timer build exists for the two profiled head dims only
+    return launch_tc_impl<(D == 40 || D == 128) ? D : 40, true>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+  return launch_tc_impl<D, false>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
 }
 
 }  // namespace
@@ -461,6 +512,11 @@ int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const voi
 }
 
 // Timing-experiment hook (see AttnParams::debug); results are WRONG while it is non-zero.  Not part of the product API.
+// Phase-timer hook: a device buffer of 24 u64 receives the clock64 sums of CTA (1, 3): [0..7] MMA issuer (prologue, wait K, wait
+// S-free tile 0 / 1, QK issue, wait V, wait P, PV issue), [8..15] / [16..23] one softmax thread of tile 0 / 1 (wait S, TMEM load,
+// max + rescale, exp + pack, wait P V, TMEM store).  nullptr disables it.  Not part of the product API.
+extern "C" void saspa_attention_trace(void* dev_buf) { g_attn_trace = static_cast<unsigned long long*>(dev_buf); }
+
 extern "C" int saspa_attention_debug(int flags) {
   const int prev = g_attn_debug;
   g_attn_debug = flags;

@@ -355,8 +355,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // The whole warp runs the loops converged and ONE ELECTED lane issues each tcgen05 instruction (elect.sync): under a divergent
+    // `if (lane == 0)` ptxas serialises every UTCHMMA through an ELECT / R2UR / branch loop (~90 clk per MMA -- more than the
+    // 80 clk a 128 x 160 x 16 MMA takes, i.e. the narrower tiles were issue-bound).
     constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
-    if (lane == 0 && is_leader && p.mode == 2) {
+    if (is_leader && p.mode == 2) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -381,22 +384,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const uint64_t a_desc = make_smem_desc_sbo(halo + (ky * (HALO_BW + 2) + kx) * 128, (HALO_BW + 2) * 128);
             const uint64_t b_desc = make_smem_desc(smem_u32(sBh + sb * C::B_BYTES));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
-            op_commit<CTAS>(&empty[sb]);
+            for (int k = 0; k < BK / 16; ++k)
+              if (elect_one()) op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+            if (elect_one()) op_commit<CTAS>(&empty[sb]);
             if (++sb == C::HB_STAGES) {
               sb = 0;
               pb ^= 1;
             }
           }
-          op_commit<CTAS>(&aempty[sa]);
+          if (elect_one()) op_commit<CTAS>(&aempty[sa]);
           if (++sa == HALO_STAGES) {
             sa = 0;
             pa ^= 1;
           }
         }
-        op_commit<CTAS>(&tfull[acc]);
+        if (elect_one()) op_commit<CTAS>(&tfull[acc]);
       }
-    } else if (lane == 0 && is_leader) {
+    } else if (is_leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -414,15 +418,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128B swizzle atom = +2 in the 16-byte start-address field
-            op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (elect_one()) op_mma<CTAS>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          op_commit<CTAS>(&empty[stage]);
+          if (elect_one()) op_commit<CTAS>(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        op_commit<CTAS>(&tfull[acc]);
+        if (elect_one()) op_commit<CTAS>(&tfull[acc]);
       }
     }
   } else {

@@ -32,6 +32,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test (mbarrier.try_wait may SUSPEND the thread for a hardware time limit of several microseconds when the
+// phase is not complete -- fatal for a loop that polls several barriers and must act on whichever completes first).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug must trap (the launch then fails loudly) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -112,6 +125,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int bm, int bn, int b_mn_major
          ((uint32_t)(bm >> 4) << 24);
 }
 
+
+// One lane of a CONVERGED warp (elect.sync): the way to issue single-thread tcgen05 / TMA instructions without ptxas having to
+// serialise a divergent region (which costs an ELECT / R2UR / branch loop around every instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- additions used by the attention kernel ----
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, int c2) {
