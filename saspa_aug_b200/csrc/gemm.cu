@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA fills its own smem; completion lands on the leader's barrier) =====================
+    // (converged warp, one elected lane per instruction -- see the MMA issuer)
     const int b_rows = BN / CTAS;  // this CTA's share of the B tile
-    if (lane == 0 && p.mode == 2) {
+    if (p.mode == 2) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int ctot = p.c0 + p.c1;
@@ -287,21 +288,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int cc = 0; cc < cchunks; ++cc) {
           const int c = cc * BK;
           mbar_wait(&aempty[sa], pa ^ 1);
-          if (is_leader) mbar_expect_tx(&afull[sa], HALO_TX_BYTES * CTAS);
+          if (is_leader && elect_one()) mbar_expect_tx(&afull[sa], HALO_TX_BYTES * CTAS);
           const uint32_t abar = (CTAS == 2) ? mapa_rank(smem_u32(&afull[sa]), 0) : smem_u32(&afull[sa]);
-          if (c < p.c0)
-            op_load_4d<CTAS>(&tmA0, sHalo + sa * HALO_STAGE_BYTES, abar, c, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
-          else
-            op_load_4d<CTAS>(&tmA1, sHalo + sa * HALO_STAGE_BYTES, abar, c - p.c0, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+          if (c < p.c0) {
+            if (elect_one()) op_load_4d<CTAS>(&tmA0, sHalo + sa * HALO_STAGE_BYTES, abar, c, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+          } else {
+            if (elect_one()) op_load_4d<CTAS>(&tmA1, sHalo + sa * HALO_STAGE_BYTES, abar, c - p.c0, tx * HALO_BW - 1, ty * HALO_BH - 1, tn);
+          }
           if (++sa == HALO_STAGES) {
             sa = 0;
             pa ^= 1;
           }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&empty[sb], pb ^ 1);
-            if (is_leader) mbar_expect_tx(&full[sb], C::B_BYTES * CTAS);
+            if (is_leader && elect_one()) mbar_expect_tx(&full[sb], C::B_BYTES * CTAS);
             const uint32_t bbar = (CTAS == 2) ? mapa_rank(smem_u32(&full[sb]), 0) : smem_u32(&full[sb]);
-            op_load_2d<CTAS>(&tmB, sBh + sb * C::B_BYTES, bbar, tap * ctot + c, n_blk * BN + (int)rank * b_rows);
+            if (elect_one()) op_load_2d<CTAS>(&tmB, sBh + sb * C::B_BYTES, bbar, tap * ctot + c, n_blk * BN + (int)rank * b_rows);
             if (++sb == C::HB_STAGES) {
               sb = 0;
               pb ^= 1;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cid; tile < total_tiles; tile += num_clusters) {
@@ -327,25 +329,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         y0 *= p.stride;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (is_leader) mbar_expect_tx(&full[stage], C::STAGE_BYTES * CTAS);
+          if (is_leader && elect_one()) mbar_expect_tx(&full[stage], C::STAGE_BYTES * CTAS);
           const uint32_t fbar = (CTAS == 2) ? mapa_rank(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
           uint8_t* a_dst = sA + stage * A_BYTES;
           uint8_t* b_dst = sB + stage * C::B_BYTES;
           int kB;
           if (p.mode == 0) {
             kB = kb * BK;
-            op_load_2d<CTAS>(&tmA0, a_dst, fbar, kB, m_blk * BM);
+            if (elect_one()) op_load_2d<CTAS>(&tmA0, a_dst, fbar, kB, m_blk * BM);
           } else {
             int tap = kb / cchunks, cc = kb - tap * cchunks;
             int ky = tap / p.ksize, kx = tap - ky * p.ksize;
             int c = cc * BK;
             kB = tap * (p.c0 + p.c1) + c;
-            if (c < p.c0)
-              op_load_4d<CTAS>(&tmA0, a_dst, fbar, c, x0 + kx - pad, y0 + ky - pad, n0);
-            else
-              op_load_4d<CTAS>(&tmA1, a_dst, fbar, c - p.c0, x0 + kx - pad, y0 + ky - pad, n0);
+            if (c < p.c0) {
+              if (elect_one()) op_load_4d<CTAS>(&tmA0, a_dst, fbar, c, x0 + kx - pad, y0 + ky - pad, n0);
+            } else {
+              if (elect_one()) op_load_4d<CTAS>(&tmA1, a_dst, fbar, c - p.c0, x0 + kx - pad, y0 + ky - pad, n0);
+            }
           }
-          op_load_2d<CTAS>(&tmB, b_dst, fbar, kB, n_blk * BN + (int)rank * b_rows);
+          if (elect_one()) op_load_2d<CTAS>(&tmB, b_dst, fbar, kB, n_blk * BN + (int)rank * b_rows);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -814,8 +817,9 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 
 // Tile width along N.
-//  * main-loop-bound problems (convs, K >= 2048): measured per-tile time relative to BN = 256 is 0.72 for BN <= 128 and
-//    0.80 for BN = 160 (profiles/r1_bn_sweep.txt), so cost = waves x per-tile time decides -- the widest tile unless it
+//  * main-loop-bound problems (convs, K >= 2048): measured per-tile time relative to BN = 256 is 0.49 / 0.63 / 0.69 for
+//    BN = 64 / 128 / 160 (profiles/r1_bn_sweep_y.txt, after the elected-issue fix; 0.72 / 0.72 / 0.80 while the narrow tiles were
+//    issue-bound), so cost = waves x per-tile time decides -- the widest tile unless it
 //    pads columns or leaves SMs idle in the last wave of a small-M problem;
 //  * short-K GEMMs are bound by the epilogue / stores, where padded columns cost real time: exact tilings first
 //    (SD channel counts are multiples of 320 -> 160; powers of two -> 256 / 128).
@@ -826,7 +830,7 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound) {
   if (N <= 64) return 64;
   if (mainloop_bound) {
     const int cands[4] = {256, 160, 128, 64};
-    const double t_rel[4] = {1.0, 0.80, 0.72, 0.72};
+    const double t_rel[4] = {1.0, 0.69, 0.63, 0.49};
     const int sms = saspa_num_sms();
     int best = 256;
     double best_cost = 1e30;
@@ -859,12 +863,12 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound) {
 
 int g_force_ctas = 0;  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
 
-// Two-CTA tiles (cta_group::2, 256 x BN): measured +7% at BN = 256 on the plain GEMM main loop, a loss for narrower
-// tiles and for the halo conv (profiles/r1_bn_sweep.txt), so only the widest long-K GEMM tiles pair up.
+// Two-CTA tiles (cta_group::2, 256 x BN): measured +14% at BN = 256 and +9% at BN = 160 on the plain GEMM main loop, a loss
+// for narrower tiles and for the halo conv (profiles/r1_bn_sweep_y.txt), so only the wide long-K GEMM tiles pair up.
 int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K) {
   if (g_force_ctas) return num_m_tiles >= 2 || g_force_ctas == 1 ? g_force_ctas : 1;
   // epilogue-bound launches (GEGLU, short K) lose from coupling two CTAs (measured 325 -> 381 us on the 64x64 GEGLU GEMM)
-  return (bn == 256 && mode == 0 && act != SASPA_ACT_GEGLU && K >= 1024 && num_m_tiles >= 2) ? 2 : 1;
+  return (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= 1024 && num_m_tiles >= 2) ? 2 : 1;
 }
 
 template <int CTAS>
