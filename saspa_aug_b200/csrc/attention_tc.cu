@@ -18,9 +18,8 @@
 //              tcgen05.ld the S row, release S, running max with lazy rescale (O is only rescaled in TMEM
 //              when the max grows by more than 2^8), p = ex2(s*c - m), bf16 P packed two per column back
 //              into TMEM with tcgen05.st; finally O / l -> global.
-//              A quarter of the exponentials are evaluated on the FMA pipe (Cody-Waite split + cubic, rel. error 7.5e-5,
-//              far below the bf16 rounding of P): the d = 40 layers are bound by the 16/clk/SM MUFU unit, not by the
-//              tensor pipe.
+//              (An FMA-pipe exponential -- Cody-Waite split + cubic, rel. error 7.5e-5 -- is kept as a tuning option,
+//              ACfg::POLY_EVERY: once the MMA issue and tile phasing were fixed it measured slower than the MUFU for every share.)
 //   warp 10    (head_dim % 16 == 8 only) patches a column of ones into the zero-cost pad of each landed V tile, so
 //              the P V MMA also accumulates the softmax denominator sum_j P_ij in O[:, D] -- no per-element adds.
 // Padding is free: head_dim 40 runs as K = 48 (the Q pad chunk is zeroed in smem; K's pad columns then
@@ -49,7 +48,10 @@ struct ACfg {
   static constexpr int P_OFF = 2 * BKV;  // TMEM columns: S_i at i*BKV, P_i at P_OFF + i*BKV/2, O_i at O_OFF + i*ON
   static constexpr int O_OFF = 3 * BKV;
   static constexpr bool ONES = (D % 16) != 0;  // a free pad column exists: row sums come out of the P V MMA
-  static constexpr int POLY_EVERY = 4;         // every POLY_EVERY-th exponential runs on the FMA pipe (0 = none)
+  // every POLY_EVERY-th exponential on the FMA pipe (ex2_poly), 0 = all on the MUFU.  Re-measured after the issue / phase fixes
+  // (tools/attn_debug.py, -DSASPA_ATTN_POLY_SWEEP): d = 40 1.43 / 1.50 / 1.53 / 1.78 ms and d = 64 1.57 / 1.74 / 1.76 / 2.08 ms for
+  // 0 / 6 / 4 / 2 -- the softmax warps are issue-bound, not MUFU-bound, so the emulation only adds instructions.
+  static constexpr int POLY_EVERY = 0;
   static_assert(O_OFF + 2 * ON <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "smem budget");
 };
@@ -64,7 +66,7 @@ struct AttnParams {
   int debug;  // timing experiments only (tools/attn_debug.py): 1 = no exponentials, 2 = no P V MMAs, 4 = no Q K^T MMAs
 };
 
-template <int D, bool TRACE>
+template <int D, bool TRACE, int PE = ACfg<D>::POLY_EVERY>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnParams p) {
@@ -344,7 +346,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         for (int c = 0; c < BKV; c += 2) {
           const float x0 = fmaf(__uint_as_float(su[c]), p.scale_log2, neg_m);
           const float x1 = fmaf(__uint_as_float(su[c + 1]), p.scale_log2, neg_m);
-          constexpr int PE = C::POLY_EVERY;
           const float p0 = (PE > 0 && (c % (PE > 0 ? PE : 1)) == PE - 1) ? ex2_poly(x0) : ex2_approx(x0);
           const float p1 = (PE > 0 && ((c + 1) % (PE > 0 ? PE : 1)) == PE - 1) ? ex2_poly(x1) : ex2_approx(x1);
           if constexpr (!C::ONES) lsum[(c >> 1) & 3] += p0 + p1;
@@ -456,13 +457,15 @@ int g_attn_debug = 0;
 
 unsigned long long* g_attn_trace = nullptr;
 
-template <int D, bool TRACE>
+int g_attn_poly = -1;  // tuning hook: -1 = ACfg<D>::POLY_EVERY, else every g_attn_poly-th exponential on the FMA pipe (0 = none)
+
+template <int D, bool TRACE, int PE = ACfg<D>::POLY_EVERY>
 int launch_tc_impl(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq, int tkv,
               float scale, int causal, cudaStream_t stream) {
   using C = ACfg<D>;
   static bool configured = false;
   if (!configured) {
-    SASPA_CUDA(cudaFuncSetAttribute((attn_tc_kernel<D, TRACE>), cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SASPA_CUDA(cudaFuncSetAttribute((attn_tc_kernel<D, TRACE, PE>), cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -481,7 +484,7 @@ int launch_tc_impl(const void* q, int ldq, const void* k, int ldk, const void* v
   p.debug = g_attn_debug;
   p.trace = g_attn_trace;
   dim3 grid(ceil_div(tq, 2 * QROWS), batch * heads);
-  attn_tc_kernel<D, TRACE><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
+  attn_tc_kernel<D, TRACE, PE><<<grid, ATC_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, p);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }
@@ -491,6 +494,19 @@ int launch_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int
               float scale, int causal, cudaStream_t stream) {
   if (g_attn_trace != nullptr && (D == 40 || D == 128))  // the phase-timer build exists for the two profiled head dims only
     return launch_tc_impl<(D == 40 || D == 128) ? D : 40, true>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+#ifdef SASPA_ATTN_POLY_SWEEP  // tuning build only (tools/attn_debug.py --poly): the FMA-pipe share of the exponentials, d = 40 / 64
+  if constexpr (D == 40 || D == 64) {
+    switch (g_attn_poly) {
+      case 0: return launch_tc_impl<D, false, 0>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      case 2: return launch_tc_impl<D, false, 2>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      case 3: return launch_tc_impl<D, false, 3>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      case 4: return launch_tc_impl<D, false, 4>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      case 6: return launch_tc_impl<D, false, 6>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      case 8: return launch_tc_impl<D, false, 8>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
+      default: break;
+    }
+  }
+#endif
   return launch_tc_impl<D, false>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, scale, causal, stream);
 }
 
@@ -515,6 +531,8 @@ int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const voi
 // Phase-timer hook: a device buffer of 24 u64 receives the clock64 sums of CTA (1, 3): [0..7] MMA issuer (prologue, wait K, wait
 // S-free tile 0 / 1, QK issue, wait V, wait P, PV issue), [8..15] / [16..23] one softmax thread of tile 0 / 1 (wait S, TMEM load,
 // max + rescale, exp + pack, wait P V, TMEM store).  nullptr disables it.  Not part of the product API.
+extern "C" void saspa_attention_poly(int every) { g_attn_poly = every; }
+
 extern "C" void saspa_attention_trace(void* dev_buf) { g_attn_trace = static_cast<unsigned long long*>(dev_buf); }
 
 extern "C" int saspa_attention_debug(int flags) {

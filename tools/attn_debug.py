@@ -46,3 +46,16 @@ for (b, heads, t, d) in [(32, 8, 4096, 40), (8, 16, 4096, 128)]:
         for i in (0, 1):
             print(f"  softmax tile {i}: " + ", ".join(f"{n} {x / steps:.0f}" for n, x in zip(["wait S", "TMEM ld", "max/rescale", "exp+pack", "wait PV", "TMEM st"], v[8 + 8 * i: 14 + 8 * i])))
     lib.saspa_attention_debug(0)
+
+# ---- FMA-pipe share of the exponentials (needs a build with -DSASPA_ATTN_POLY_SWEEP; otherwise every row shows the default) ----
+lib.saspa_attention_poly.argtypes = [ctypes.c_int]
+lib.saspa_attention_poly.restype = None
+for (b, heads, t, d) in [(32, 8, 4096, 40), (16, 16, 4096, 64)]:
+    qkv = rnd(b, t, 3 * heads * d)
+    c = heads * d
+    out = torch.empty(b, t, c, dtype=torch.bfloat16, device="cuda")
+    for pe in (0, 8, 6, 4, 3, 2):
+        lib.saspa_attention_poly(pe)
+        ms = timeit(lambda: ops.attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], heads, out=out), iters=5)
+        print(f"d{d} t{t} poly every {pe}: {ms:.3f} ms")
+    lib.saspa_attention_poly(-1)
