@@ -104,10 +104,12 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
                                                         semantic_filtering=False, model_confidence_based_filtering=False, conf_top_k: int = 10,
                                                         filter_confidence_higher_than: int = None, init_log=True, alia_conf_filtering=False, *,
                                                         ds_utils=None, filter_models: Optional[Callable] = None, device="cuda", batch_size: int = 64,
-                                                        return_details: bool = False):
+                                                        return_details: bool = False, decisions: Optional[Dict[str, Tuple[int, int]]] = None):
     """Drop-in for all_utils/utils.py:221-465 (same positional signature).  Keyword-only extras:
       ds_utils       dataset-utils object (default: saspa_aug_b200.datasets.DS_UTILS_DICT[dataset]())
       filter_models  callable(ds_utils, device) -> (WSDANClassifier | None, CLIPRN50 | None, tokenizer) (default: ds_utils.load_filter_models)
+      decisions      {augmentation path: (in_topk, semantic)} computed elsewhere (the sharded driver gathers every rank's filter
+                     records and lets rank 0 write the JSON through this same function: same matching, ordering and file name)
     """
     import torch
 
@@ -138,11 +140,11 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
             raise FileNotFoundError(f"augmented_image_folder_path = {augmented_image_folder_path} doesn't exist or has less than 10 images")
 
     classifier = clip = tokenizer = None
-    if semantic_filtering or model_confidence_based_filtering:
+    if (semantic_filtering or model_confidence_based_filtering) and decisions is None:
         loader = filter_models or ds_utils.load_filter_models
         classifier, clip, tokenizer = loader(ds_utils, device)
     prompt_ids = None
-    if semantic_filtering:
+    if semantic_filtering and decisions is None:
         prompts = [ds_utils.get_basic_prompt()] + SEMANTIC_NEGATIVE_PROMPTS
         logging.info(f"using semantic filtering with prompts = {prompts}")
         prompt_ids = tokenizer(prompts)
@@ -150,8 +152,10 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
         image_path_to_class_id = ds_utils.get_image_path_to_class_id_dict()
         conf_top_k = min(conf_top_k, ds_utils.num_classes)
         logging.info(f"using model_confidence_based_filtering with conf_top_k = {conf_top_k}")
-    flt = AugmentationFilter(classifier if model_confidence_based_filtering else None, clip if semantic_filtering else None, prompt_ids, conf_top_k,
-                             micro_batch=batch_size)
+    flt = None
+    if decisions is None:
+        flt = AugmentationFilter(classifier if model_confidence_based_filtering else None, clip if semantic_filtering else None, prompt_ids, conf_top_k,
+                                 micro_batch=batch_size)
 
     all_file_names = [f for f in os.listdir(augmented_image_folder_path) if not any(s in f for s in SUBSTRINGS_TO_EXCLUDE)]
     matched = match_augmentations(original_images_paths_list, all_file_names, augmented_image_folder_path)
@@ -164,7 +168,12 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
             pairs.append((name, p, label))
     in_topk = np.ones(len(pairs), np.uint8)
     sem = np.ones(len(pairs), np.uint8)
-    if (semantic_filtering or model_confidence_based_filtering) and pairs:
+    if decisions is not None:
+        for k, (_, path, _) in enumerate(pairs):
+            if path not in decisions:
+                raise KeyError(f"no gathered filter record for {path}")
+            in_topk[k], sem[k] = decisions[path]
+    elif (semantic_filtering or model_confidence_based_filtering) and pairs:
         dev = torch.device(device)
         for idx, imgs in _load_batches([p[1] for p in pairs], batch_size):
             labels = torch.tensor([pairs[i][2] for i in idx], dtype=torch.int32, device=dev)

@@ -334,3 +334,79 @@ def gather_records(records: np.ndarray, rank: int, world: int):
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([o[: int(s.item())].cpu().numpy() for o, s in zip(out, sizes)], 0)
+
+
+def filter_shard(cfg: AugConfig, ds_utils, written, device="cuda", batch_size: int = 64, filter_models=None) -> np.ndarray:
+    """Runs the two enabled filters (run_aug.py:551-556) on THIS rank's augmentations -> fixed-size records int32 [n, 4] =
+    (source index, aug index i, in_topk, semantic) for the final gather."""
+    import torch
+
+    from .filter_nets import AugmentationFilter
+    from .filtering import SEMANTIC_NEGATIVE_PROMPTS, _load_batches
+
+    rec = np.ones((len(written), 4), np.int32)
+    for k, (index, i, _) in enumerate(written):
+        rec[k, 0], rec[k, 1] = index, i
+    if not written or not (cfg.SEMANTIC_FILTERING or cfg.MODEL_CONFIDENCE_BASED_FILTERING):
+        return rec
+    classifier, clip, tokenizer = (filter_models or ds_utils.load_filter_models)(ds_utils, device)
+    prompt_ids = tokenizer([ds_utils.get_basic_prompt()] + SEMANTIC_NEGATIVE_PROMPTS) if cfg.SEMANTIC_FILTERING else None
+    flt = AugmentationFilter(classifier if cfg.MODEL_CONFIDENCE_BASED_FILTERING else None, clip if cfg.SEMANTIC_FILTERING else None, prompt_ids,
+                             min(cfg.CONF_TOP_K, ds_utils.num_classes), micro_batch=batch_size)
+    label_of = ds_utils.get_image_path_to_class_id_dict() if cfg.MODEL_CONFIDENCE_BASED_FILTERING else {}
+    paths = ds_utils.original_images_paths
+    dev = torch.device(device)
+    for idx, imgs in _load_batches([w[2] for w in written], batch_size):
+        labels = torch.tensor([int(label_of.get(paths[written[k][0]], 0)) for k in idx], dtype=torch.int32, device=dev)
+        out = flt(torch.from_numpy(imgs).to(dev), labels)
+        rec[idx, 2] = out["in_topk"].cpu().numpy()
+        rec[idx, 3] = out["semantic"].cpu().numpy()
+    return rec
+
+
+def run_sharded(cfg: AugConfig, ds_utils, prompts: Sequence[str], ds_root: str, pipe=None, device=None, filter_models=None):
+    """End to end for one rank of a one-process-per-GPU job (RANK / WORLD_SIZE / LOCAL_RANK from torchrun; single process otherwise):
+    generate this rank's shard (run_aug.py:357-471) -> filter it on this GPU -> ONE collective (all-gather of the per-image filter
+    records, NCCL over NVLink on GPUs) -> rank 0 writes the aug JSON through the reference-compatible writer (run_aug.py:721-733).
+    Returns (json_path | None on ranks > 0, stats)."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import filtering
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if device is None:
+        device = f"cuda:{local}"
+    if torch.cuda.is_available():
+        torch.cuda.set_device(torch.device(device))
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    if pipe is None:
+        pipe = init_pipeline(cfg.BASE_MODEL, cfg.CONTROLNET, cfg.SDEDIT, sampler=cfg.SAMPLER, device=device)
+    out_dir = output_folder(ds_root, cfg)
+    t0 = time.perf_counter()
+    written = generate(cfg, ds_utils, pipe, prompts, out_dir, rank=rank, world=world)
+    t1 = time.perf_counter()
+    rec = filter_shard(cfg, ds_utils, written, device=device, filter_models=filter_models)
+    t2 = time.perf_counter()
+    allrec = gather_records(rec, rank, world)
+    stats = {"rank": rank, "world": world, "generated": len(written), "generate_s": t1 - t0, "filter_s": t2 - t1}
+    json_path = None
+    if rank == 0:
+        paths = ds_utils.original_images_paths
+        by_key = {(int(r[0]), int(r[1])): (int(r[2]), int(r[3])) for r in allrec}
+        # (source index, i) -> file path: every rank used the same rank-independent prompt draw, so rank 0 can rebuild the names
+        sampled = sample_prompts(prompts, len(paths), cfg)
+        decisions = {}
+        for (index, i), d in by_key.items():
+            decisions[str(Path(out_dir) / aug_file_name(Path(paths[index]).stem, sampled[index][i], i))] = d
+        json_path = filtering.create_json_of_image_name_to_augmented_images_paths(
+            cfg.DATASET, out_dir, semantic_filtering=bool(cfg.SEMANTIC_FILTERING), model_confidence_based_filtering=bool(cfg.MODEL_CONFIDENCE_BASED_FILTERING),
+            conf_top_k=cfg.CONF_TOP_K, init_log=False, ds_utils=ds_utils, decisions=decisions)
+        stats.update(records=int(allrec.shape[0]), kept=int(sum(1 for a, b in by_key.values() if a and b)))
+    if world > 1:
+        dist.barrier()
+    return json_path, stats

@@ -100,3 +100,44 @@ def test_world_size_2_gather_gloo():
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                             "--master-port", "29611", w, ROOT], capture_output=True, text=True, timeout=240)
         assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_json_writer_from_gathered_decisions(tmp_path):
+    """Rank 0 of the sharded driver writes the aug JSON from the gathered filter records through the same reference-compatible
+    writer (no networks, no GPU): matching by stem substring, dataset key order, listdir value order, confidence filter before the
+    semantic one, file name from the enabled flags."""
+    import json
+
+    from PIL import Image
+
+    from saspa_aug_b200 import filtering
+    from saspa_aug_b200.datasets import SyntheticUtils
+
+    ds = SyntheticUtils(root=str(tmp_path / "ds"), n_images=4, size=(32, 32)).materialize()
+    cfg = run_aug.AugConfig()
+    out_dir = run_aug.output_folder(str(tmp_path / "ds"), cfg)
+    os.makedirs(out_dir)
+    decisions, expect = {}, {}
+    for index, p in enumerate(ds.original_images_paths):
+        stem = os.path.splitext(os.path.basename(p))[0]
+        Image.new("RGB", (8, 8)).save(os.path.join(out_dir, f"{stem}_source.png"))
+        expect[os.path.basename(p)] = []
+        for i in range(3):
+            path = os.path.join(out_dir, run_aug.aug_file_name(stem, f"an airplane, take {i}", i))
+            Image.new("RGB", (8, 8), (index * 40, i * 60, 0)).save(path)
+            decisions[path] = ((index + i) % 2, int(i != 1))
+    for f in os.listdir(out_dir):  # listdir order is the value order
+        if "_source." in f:
+            continue
+        a, b = decisions[os.path.join(out_dir, f)]
+        if a and b:
+            expect[[k for k in expect if os.path.splitext(k)[0] in f][0]].append(os.path.join(out_dir, f))
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
+                                                                       init_log=False, ds_utils=ds, decisions=decisions)
+    assert os.path.basename(jp) == "semantic_filtering-model_confidence_based_filtering_top_10_classes-aug.json"
+    got = json.load(open(jp))
+    assert list(got) == [os.path.basename(p) for p in ds.original_images_paths] and got == expect
+    missing = dict(list(decisions.items())[1:])
+    with pytest.raises(KeyError):
+        filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
+                                                                   init_log=False, ds_utils=ds, decisions=missing)
