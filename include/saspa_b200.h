@@ -245,6 +245,11 @@ int saspa_fc_f32(const float* x, const float* w, const float* bias, int n, int k
 /* keep[i] = (label[i] in top-k(logits[i, :]))  -- torch.topk tie order: lower index wins */
 int saspa_topk_contains(const float* logits, int n, int classes, const int32_t* label, int k, uint8_t* keep, float* margin,
                         cudaStream_t stream);
+/* prob[i] = softmax(logits[i, :])[idx[i]], max_logit[i] = max_j logits[i, j], argmax[i] = its first index (each output optional): the
+ * confidence tests of the reference's optional filters (all_utils/utils.py:186-191 clip_filtering, :370-376
+ * filter_confidence_higher_than, :411-418 alia_conf_filtering).  idx values must lie in [0, classes). */
+int saspa_softmax_at_f32(const float* logits, int n, int classes, const int32_t* idx, float* prob, float* max_logit, int32_t* argmax,
+                         cudaStream_t stream);
 /* CLIP cosine scoring (all_utils/utils.py:152-166): logits = scale * norm(img) @ norm(txt)^T; argmax over prompts.
  * img fp32 [n, d], txt fp32 [p, d] -> logits fp32 [n, p] (optional), argmax int32 [n]. */
 int saspa_clip_score_argmax(const float* img, const float* txt, int n, int p, int d, float logit_scale, float* logits,

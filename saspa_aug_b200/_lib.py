@@ -103,6 +103,7 @@ SIGNATURES = {
     "saspa_bap_head": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "saspa_fc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "saspa_topk_contains": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "saspa_softmax_at_f32": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "saspa_clip_score_argmax": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P]),
 }
 

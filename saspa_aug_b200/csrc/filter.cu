@@ -173,6 +173,42 @@ __global__ void topk_contains_kernel(const float* __restrict__ logits, int n, in
   }
 }
 
+// softmax(logits[i, :])[idx[i]], max_j logits[i, j] and its (first) argmax: the confidence tests of the reference's optional filters
+// (all_utils/utils.py:186-191 get_clip_filtering, :370-376 filter_confidence_higher_than, :411-418 alia_conf_filtering).
+__global__ void softmax_at_kernel(const float* __restrict__ logits, int n, int classes, const int32_t* __restrict__ idx, float* __restrict__ prob,
+                                  float* __restrict__ max_logit, int32_t* __restrict__ argmax) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float* row = logits + (size_t)i * classes;
+  float m = -INFINITY;
+  int mj = 0x7fffffff;
+  for (int j = lane; j < classes; j += 32) {
+    const float v = row[j];
+    if (v > m) {
+      m = v;
+      mj = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
+    if (om > m || (om == m && oj < mj)) {  // first maximum wins, as torch.argmax / max
+      m = om;
+      mj = oj;
+    }
+  }
+  float s = 0.0f;
+  for (int j = lane; j < classes; j += 32) s += expf(row[j] - m);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (prob) prob[i] = expf(row[idx[i]] - m) / s;
+    if (max_logit) max_logit[i] = m;
+    if (argmax) argmax[i] = mj;
+  }
+}
+
 __global__ void clip_score_kernel(const float* __restrict__ img, const float* __restrict__ txt, int n, int p, int d, float logit_scale,
                                   float* __restrict__ logits, int32_t* __restrict__ argmax) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -324,6 +360,16 @@ extern "C" int saspa_topk_contains(const float* logits, int n, int classes, cons
   if (n == 0) return SASPA_OK;
   SASPA_CHECK_ARG(logits && label && keep, "saspa_topk_contains: null pointer");
   topk_contains_kernel<<<ceil_div(n, 4), 128, 0, stream>>>(logits, n, classes, label, k, keep, margin);
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+
+extern "C" int saspa_softmax_at_f32(const float* logits, int n, int classes, const int32_t* idx, float* prob, float* max_logit, int32_t* argmax,
+                                    cudaStream_t stream) {
+  SASPA_CHECK_ARG(n >= 0 && classes > 0, "saspa_softmax_at_f32: bad shape");
+  if (n == 0) return SASPA_OK;
+  SASPA_CHECK_ARG(logits && (idx || !prob), "saspa_softmax_at_f32: null pointer");
+  softmax_at_kernel<<<ceil_div(n, 4), 128, 0, stream>>>(logits, n, classes, idx, prob, max_logit, argmax);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }

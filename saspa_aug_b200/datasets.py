@@ -34,6 +34,22 @@ class BaseUtils:
     def load_filter_models(self, ds_utils, device):
         raise NotImplementedError
 
+    # ---- used only by the optional filters (all_utils/utils.py:269-300, :323-328) -----------------------------------------
+    clip_filtering_suffix = ""  # e.g. ", a type of aircraft" (planes), ", a type of car" (cars), ", a type of a bird" (cub)
+
+    def get_clip_filtering_prompts(self):
+        """all_utils/utils.py:276-296: one prompt per class name."""
+        return [f"a photo of a {name}{self.clip_filtering_suffix}." for name in self.get_classes()]
+
+    def get_class_index_for_image(self, image_path: str) -> int:
+        """Index of the source image's class in get_classes() (the reference goes through image-stem / image-path -> class-string
+        dicts, :383-388)."""
+        return int(self.get_image_path_to_class_id_dict()[image_path])
+
+    def get_baseline_conf_threshold(self):
+        """{str(class id): logit threshold} of the ALIA confidence filter (dataset_utils get_baseline_conf_threshold)."""
+        raise NotImplementedError
+
 
 class SyntheticUtils(BaseUtils):
     """N synthetic 512x512 sources written under ``root`` as PNGs, label_i = i % num_classes."""
@@ -47,6 +63,7 @@ class SyntheticUtils(BaseUtils):
         self.root = Path(root or os.environ.get("SASPA_SYNTHETIC_ROOT", "/tmp/saspa_synthetic"))
         self.n_images, self.seed_base, self.size = n_images, seed_base, size
         self.wsdan_seed, self.clip_seed, self.net = wsdan_seed, clip_seed, net
+        self.alia_threshold = 1.0  # logit threshold of the synthetic ALIA confidence filter
         self.clip_model = clip_model  # "RN50" (the reference, all_utils/utils.py:253) | "ViT-L/14" (BASELINE config 5)
         self.images_path = self.root / "images"
         self.original_images_paths = [str(self.images_path / f"syn_{seed_base + i:07d}.png") for i in range(n_images)]
@@ -67,6 +84,9 @@ class SyntheticUtils(BaseUtils):
 
     def get_image_path_to_class_id_dict(self):
         return {p: i % self.num_classes for i, p in enumerate(self.original_images_paths)}
+
+    def get_baseline_conf_threshold(self):
+        return {str(c): self.alia_threshold for c in range(self.num_classes)}
 
     def load_filter_models(self, ds_utils, device):
         """Random-init WSDAN_CAL + CLIP (RN50 | ViT-L/14) of the reference architectures (no checkpoints offline)."""

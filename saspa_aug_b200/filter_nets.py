@@ -277,23 +277,38 @@ class SafetyChecker:
 
 
 class AugmentationFilter:
-    """keep = (label in top-k(WSDAN logits)) AND (argmax CLIP(img, [basic prompt, 6 negatives]) == 0)
-    (all_utils/utils.py:357-365, :169-177, :401-404), on batches of u8 images resident on the device."""
+    """The per-image decisions of all_utils/utils.py:357-434 on batches of u8 images resident on the device.
+    Enabled on the reference's hot path (run_aug.py:551-556):
+      in_topk   label in top-k(WSDAN logits)                                          (:357-365)
+      semantic  argmax CLIP(img, [basic prompt, 6 negatives]) == 0                     (:169-177, :401-404)
+    Optional filters (disabled in run_aug.py, used by run_aug_real_guidance.py) need only extra heads:
+      label_conf  softmax(WSDAN logits)[label]      -> filter_confidence_higher_than     (:370-376)
+      max_logit / argmax of the WSDAN logits        -> alia_conf_filtering               (:411-434)
+      class_conf  softmax(CLIP logits over the class prompts)[class]  -> clip_filtering  (:186-191, :377-395)"""
 
-    def __init__(self, classifier: Optional[WSDANClassifier], clip: Optional[CLIPRN50], prompt_ids: Optional[torch.Tensor], conf_top_k: int = 10,
-                 micro_batch: int = 64):
+    def __init__(self, classifier: Optional[WSDANClassifier], clip, prompt_ids: Optional[torch.Tensor], conf_top_k: int = 10,
+                 micro_batch: int = 64, class_prompt_ids: Optional[torch.Tensor] = None):
         self.classifier, self.clip, self.micro_batch = classifier, clip, micro_batch
         self.conf_top_k = min(conf_top_k, classifier.num_classes) if classifier is not None else conf_top_k
         self.text_features = clip.encode_text(prompt_ids.to(clip.dev)) if (clip is not None and prompt_ids is not None) else None
+        self.class_text_features = None
+        if clip is not None and class_prompt_ids is not None:  # the text tower runs once, in chunks (the reference re-runs it per image)
+            ids = class_prompt_ids.to(clip.dev)
+            self.class_text_features = torch.cat([clip.encode_text(ids[i : i + 64]) for i in range(0, ids.shape[0], 64)], 0).contiguous()
 
     @torch.no_grad()
-    def __call__(self, images_u8: torch.Tensor, labels: torch.Tensor):
-        """images u8 [n,H,W,3] (device), labels int32 [n] -> dict(keep, in_topk, semantic, topk_margin, clip_logits)."""
+    def __call__(self, images_u8: torch.Tensor, labels: torch.Tensor, class_idx: Optional[torch.Tensor] = None):
+        """images u8 [n,H,W,3] (device), labels int32 [n] (classifier label), class_idx int32 [n] (index into the class prompts)
+        -> dict(keep, in_topk, semantic, topk_margin, clip_logits, label_conf, max_logit, argmax, class_conf)."""
         n = images_u8.shape[0]
         dev = images_u8.device
         in_topk = torch.ones(n, dtype=torch.uint8, device=dev)
         sem = torch.ones(n, dtype=torch.uint8, device=dev)
         margin = torch.zeros(n, dtype=torch.float32, device=dev)
+        label_conf = torch.zeros(n, dtype=torch.float32, device=dev)
+        max_logit = torch.zeros(n, dtype=torch.float32, device=dev)
+        argmax = torch.zeros(n, dtype=torch.int32, device=dev)
+        class_conf = torch.ones(n, dtype=torch.float32, device=dev)
         clip_logits = None
         H, W = images_u8.shape[1:3]
         for i0 in range(0, n, self.micro_batch):
@@ -303,11 +318,13 @@ class AugmentationFilter:
                 r = ops.resize_pil(img, 256, 256, "bilinear")                       # Resize((256,256)) on PIL
                 x = ops.crop_normalize(r, 16, 16, 224, 224, IMAGENET_MEAN, IMAGENET_STD, out_c=8)  # CenterCrop(224), ToTensor, Normalize
                 logits = self.classifier(x)
-                k, m = ops.topk_contains(logits, labels[i0:i1].contiguous(), self.conf_top_k)
+                lab = labels[i0:i1].contiguous()
+                k, m = ops.topk_contains(logits, lab, self.conf_top_k)
                 in_topk[i0:i1] = k
                 margin[i0:i1] = m
-            if self.clip is not None:
-                # Resize(224): shorter side -> 224 keeping aspect (bicubic), then CenterCrop(224)
+                label_conf[i0:i1], max_logit[i0:i1], argmax[i0:i1] = ops.softmax_at(logits, lab)
+            if self.clip is not None and (self.text_features is not None or self.class_text_features is not None):
+                # Resize(R): shorter side -> R keeping aspect (bicubic), then CenterCrop(R)
                 R = getattr(self.clip, "resolution", 224)
                 if H <= W:
                     oh, ow = R, int(R * W / H)
@@ -317,7 +334,12 @@ class AugmentationFilter:
                 cy, cx = int(round((oh - R) / 2.0)), int(round((ow - R) / 2.0))
                 x = ops.crop_normalize(r, cy, cx, R, R, CLIP_MEAN, CLIP_STD, out_c=getattr(self.clip, "input_channels", 8))
                 feats = self.clip.encode_image(x)
-                lg, arg = ops.clip_score_argmax(feats, self.text_features, self.clip.logit_scale)
-                sem[i0:i1] = (arg == 0).to(torch.uint8)
-                clip_logits = lg if clip_logits is None else torch.cat([clip_logits, lg], 0)
-        return {"keep": in_topk & sem, "in_topk": in_topk, "semantic": sem, "topk_margin": margin, "clip_logits": clip_logits}
+                if self.text_features is not None:
+                    lg, arg = ops.clip_score_argmax(feats, self.text_features, self.clip.logit_scale)
+                    sem[i0:i1] = (arg == 0).to(torch.uint8)
+                    clip_logits = lg if clip_logits is None else torch.cat([clip_logits, lg], 0)
+                if self.class_text_features is not None and class_idx is not None:
+                    cl, _ = ops.clip_score_argmax(feats, self.class_text_features, self.clip.logit_scale)
+                    class_conf[i0:i1], _, _ = ops.softmax_at(cl, class_idx[i0:i1].contiguous())
+        return {"keep": in_topk & sem, "in_topk": in_topk, "semantic": sem, "topk_margin": margin, "clip_logits": clip_logits,
+                "label_conf": label_conf, "max_logit": max_logit, "argmax": argmax, "class_conf": class_conf}

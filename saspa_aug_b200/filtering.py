@@ -116,10 +116,12 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     from .filter_nets import AugmentationFilter
 
     assert not (clip_filtering and model_confidence_based_filtering), "can't use both clip_filtering and model_confidence_based_filtering"
-    for flag, nm in ((lpips_min, "lpips_min"), (lpips_max, "lpips_max"), (clip_filtering, "clip_filtering"), (alia_conf_filtering, "alia_conf_filtering"),
-                     (filter_confidence_higher_than, "filter_confidence_higher_than")):
-        if flag:  # disabled in run_aug.py (LPIPS_*=None, CLIP_FILTERING_TYPE=None, ALIA_CONF_FILTERING=0); SURVEY.md 2.1 row 4b
-            raise NotImplementedError(f"{nm}: this filter is disabled on the reference's hot path and is not built (see DESIGN.md, out of scope)")
+    for flag, nm in ((lpips_min, "lpips_min"), (lpips_max, "lpips_max")):
+        if flag:  # disabled in run_aug.py (LPIPS_*=None); needs the lpips AlexNet weights, which no offline oracle can pin
+            raise NotImplementedError(f"{nm}: the LPIPS filter is disabled on the reference's hot path and is not built (see DESIGN.md, out of scope)")
+    extra = bool(clip_filtering or alia_conf_filtering or filter_confidence_higher_than)
+    if extra and decisions is not None:
+        raise NotImplementedError("gathered decisions carry the two hot-path filters only; run the optional filters in one process")
     if not augmented_image_folder_path.endswith("/images"):
         augmented_image_folder_path = str(Path(augmented_image_folder_path) / "images")
     json_path = get_aug_json_path(augmented_image_folder_path, lpips_min, lpips_max, clip_filtering, clip_filtering_discount, semantic_filtering,
@@ -140,7 +142,7 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
             raise FileNotFoundError(f"augmented_image_folder_path = {augmented_image_folder_path} doesn't exist or has less than 10 images")
 
     classifier = clip = tokenizer = None
-    if (semantic_filtering or model_confidence_based_filtering) and decisions is None:
+    if (semantic_filtering or model_confidence_based_filtering or clip_filtering or alia_conf_filtering) and decisions is None:
         loader = filter_models or ds_utils.load_filter_models
         classifier, clip, tokenizer = loader(ds_utils, device)
     prompt_ids = None
@@ -152,10 +154,24 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
         image_path_to_class_id = ds_utils.get_image_path_to_class_id_dict()
         conf_top_k = min(conf_top_k, ds_utils.num_classes)
         logging.info(f"using model_confidence_based_filtering with conf_top_k = {conf_top_k}")
+    class_prompt_ids = None
+    clip_threshold = None
+    if clip_filtering:  # all_utils/utils.py:269-303
+        class_prompts = ds_utils.get_clip_filtering_prompts()
+        clip_threshold = 1 / len(class_prompts) / clip_filtering_discount
+        logging.info(f"using CLIP filtering, of type {clip_filtering}; total number of classes = {len(class_prompts)}; threhold = {clip_threshold}")
+        class_prompt_ids = tokenizer(class_prompts)
+    class_id_to_conf_threshold = None
+    if alia_conf_filtering:  # :323-328
+        logging.info("using alia_conf_filtering")
+        image_path_to_class_id = ds_utils.get_image_path_to_class_id_dict()
+        class_id_to_conf_threshold = ds_utils.get_baseline_conf_threshold()
     flt = None
     if decisions is None:
-        flt = AugmentationFilter(classifier if model_confidence_based_filtering else None, clip if semantic_filtering else None, prompt_ids, conf_top_k,
-                                 micro_batch=batch_size)
+        need_classifier = model_confidence_based_filtering or alia_conf_filtering
+        need_clip = semantic_filtering or clip_filtering
+        flt = AugmentationFilter(classifier if need_classifier else None, clip if need_clip else None, prompt_ids, conf_top_k, micro_batch=batch_size,
+                                 class_prompt_ids=class_prompt_ids)
 
     all_file_names = [f for f in os.listdir(augmented_image_folder_path) if not any(s in f for s in SUBSTRINGS_TO_EXCLUDE)]
     matched = match_augmentations(original_images_paths_list, all_file_names, augmented_image_folder_path)
@@ -163,32 +179,62 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     pairs: List[Tuple[str, str, int]] = []
     for image_path in original_images_paths_list:
         name = Path(image_path).name
-        label = int(image_path_to_class_id[image_path]) if model_confidence_based_filtering else 0
+        label = int(image_path_to_class_id[image_path]) if (model_confidence_based_filtering or alia_conf_filtering) else 0
         for p in matched[name]:
             pairs.append((name, p, label))
+    pair_class_idx = None
+    if clip_filtering:
+        cls_of = {Path(p).name: ds_utils.get_class_index_for_image(p) for p in original_images_paths_list}
+        pair_class_idx = [cls_of[name] for name, _, _ in pairs]
     in_topk = np.ones(len(pairs), np.uint8)
     sem = np.ones(len(pairs), np.uint8)
+    label_conf = np.zeros(len(pairs), np.float32)
+    max_logit = np.zeros(len(pairs), np.float32)
+    argmax = np.zeros(len(pairs), np.int32)
+    class_conf = np.ones(len(pairs), np.float32)
     if decisions is not None:
         for k, (_, path, _) in enumerate(pairs):
             if path not in decisions:
                 raise KeyError(f"no gathered filter record for {path}")
             in_topk[k], sem[k] = decisions[path]
-    elif (semantic_filtering or model_confidence_based_filtering) and pairs:
+    elif (semantic_filtering or model_confidence_based_filtering or extra) and pairs:
         dev = torch.device(device)
         for idx, imgs in _load_batches([p[1] for p in pairs], batch_size):
             labels = torch.tensor([pairs[i][2] for i in idx], dtype=torch.int32, device=dev)
-            out = flt(torch.from_numpy(imgs).to(dev), labels)
+            cidx = torch.tensor([pair_class_idx[i] for i in idx], dtype=torch.int32, device=dev) if pair_class_idx is not None else None
+            out = flt(torch.from_numpy(imgs).to(dev), labels, cidx)
             in_topk[idx] = out["in_topk"].cpu().numpy()
             sem[idx] = out["semantic"].cpu().numpy()
-    # the reference applies the confidence filter first, then the semantic filter on the survivors (utils.py:357-404)
+            label_conf[idx] = out["label_conf"].cpu().numpy()
+            max_logit[idx] = out["max_logit"].cpu().numpy()
+            argmax[idx] = out["argmax"].cpu().numpy()
+            class_conf[idx] = out["class_conf"].cpu().numpy()
+    # Per source image, in dataset order, the reference applies (utils.py:357-434): top-k / too-high-confidence -> [LPIPS] -> CLIP class
+    # confidence -> semantic -> ALIA confidence, each on the survivors of the previous one.  The ALIA filter spares a random 20 %
+    # (`random.random() > 0.2`, global `random` state, drawn only when the confidence test fired): the draws happen here in the same order.
+    import random
+
     result: Dict[str, List[str]] = {Path(p).name: [] for p in original_images_paths_list}
-    n_topk = n_sem = 0
-    for (name, path, _), a, b in zip(pairs, in_topk, sem):
-        if model_confidence_based_filtering and not a:
-            n_topk += 1
+    n_topk = n_sem = n_high = n_clip = n_alia_ok = n_alia_wrong = 0
+    for k, (name, path, label) in enumerate(pairs):
+        if model_confidence_based_filtering:
+            if not in_topk[k]:
+                n_topk += 1
+                continue
+            if filter_confidence_higher_than and float(label_conf[k]) > filter_confidence_higher_than:
+                n_high += 1
+                continue
+        if clip_filtering and not float(class_conf[k]) >= clip_threshold:
+            n_clip += 1
             continue
-        if semantic_filtering and not b:
+        if semantic_filtering and not sem[k]:
             n_sem += 1
+            continue
+        if alia_conf_filtering and float(max_logit[k]) > class_id_to_conf_threshold[str(label)] and random.random() > 0.2:
+            if int(argmax[k]) == label:
+                n_alia_ok += 1
+            else:
+                n_alia_wrong += 1
             continue
         result[name].append(path)
     Path(json_path).parent.mkdir(parents=True, exist_ok=True)
@@ -199,7 +245,14 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
         logging.info(f"For filter = semantic_filtering, filtered {n_sem} images")
     if model_confidence_based_filtering:
         logging.info(f"For filter = not_in_top_{conf_top_k}, filtered {n_topk} images")
+        if filter_confidence_higher_than:
+            logging.info(f"For filter = confidence higher than {filter_confidence_higher_than}, filtered {n_high} images")
+    if clip_filtering:
+        logging.info(f"For filter = clip_filtering, filtered {n_clip} images")
+    if alia_conf_filtering:
+        logging.info(f"For filter = ALIA (conf higher than threshold), filtered {n_alia_ok} correct + {n_alia_wrong} wrong predictions")
     logging.info(f"dict_num_augmentations_per_image = {get_dict_of_value_counts(result)}")
     if return_details:
-        return json_path, {"pairs": pairs, "in_topk": in_topk, "semantic": sem}
+        return json_path, {"pairs": pairs, "in_topk": in_topk, "semantic": sem, "label_conf": label_conf, "max_logit": max_logit, "argmax": argmax,
+                           "class_conf": class_conf}
     return json_path

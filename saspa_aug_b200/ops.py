@@ -482,6 +482,19 @@ def topk_contains(logits: torch.Tensor, labels: torch.Tensor, k: int):
     return keep, margin
 
 
+def softmax_at(logits: torch.Tensor, idx: torch.Tensor):
+    """logits fp32 [n, C], idx int32 [n] -> (softmax(logits)[i, idx[i]] fp32 [n], max logit fp32 [n], argmax int32 [n])."""
+    _need_cuda(logits, idx)
+    n, classes = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and idx.dtype == torch.int32 and idx.numel() == n
+    prob = torch.empty((n,), dtype=torch.float32, device=logits.device)
+    mx = torch.empty((n,), dtype=torch.float32, device=logits.device)
+    arg = torch.empty((n,), dtype=torch.int32, device=logits.device)
+    check(_lib.load().saspa_softmax_at_f32(_ptr(logits), n, classes, _ptr(idx), _ptr(prob), _ptr(mx), _ptr(arg), _stream()), "saspa_softmax_at_f32")
+    _count()
+    return prob, mx, arg
+
+
 def clip_score_argmax(img: torch.Tensor, txt: torch.Tensor, logit_scale: float):
     _need_cuda(img, txt)
     n, d = img.shape

@@ -263,3 +263,105 @@ def test_pipeline_safety_checker_hook(cuda_device):
     pipe.safety_checker = SafetyChecker(sd)
     out = pipe(generator=torch.Generator().manual_seed(1), **kw)
     assert out.nsfw_content_detected == [False] * 4 and all(np.array_equal(a, b) for a, b in zip(out.images, plain.images))
+
+
+def test_softmax_at_kernel(cuda_device):
+    g = torch.Generator().manual_seed(0)
+    for n, c in [(1, 7), (5, 100), (33, 196), (4, 1000)]:
+        logits = (torch.randn((n, c), generator=g) * 3).cuda()
+        logits[0, min(3, c - 1)] = logits[0].max() + 1.0
+        logits[-1, c - 1] = logits[-1, 0] = logits[-1].max() + 2.0  # tie: the first index wins (torch.argmax)
+        idx = torch.randint(0, c, (n,), generator=g).to(torch.int32).cuda()
+        prob, mx, arg = ops.softmax_at(logits, idx)
+        ref = torch.softmax(logits, dim=1)
+        assert torch.allclose(prob, ref[torch.arange(n), idx.long()], rtol=1e-5, atol=1e-7)
+        assert torch.equal(mx, logits.max(dim=1).values) and torch.equal(arg.long(), logits.argmax(dim=1))
+
+
+def test_optional_filters_match_reference_rule(cuda_device, tmp_path):
+    """The filters run_aug.py leaves disabled: filter_confidence_higher_than, clip_filtering (per-class CLIP softmax
+    threshold 1/C/discount) and alia_conf_filtering (max logit over a per-class threshold, 20 % spared through `random.random()`), applied in
+    the reference's order.  Expected JSONs come from the fp32 oracle nets + a literal restatement of all_utils/utils.py:357-434; thresholds sit
+    midway between oracle values so the comparison is well-posed."""
+    import random
+
+    from PIL import Image
+
+    from oracle import clip_rn50, wsdan
+    from saspa_aug_b200 import checkpoints as ck
+    from saspa_aug_b200 import filtering, run_aug
+    from saspa_aug_b200.datasets import SyntheticUtils
+    from saspa_aug_b200.pipelines import SyntheticTokenizer
+    from tests.test_filter_oracle_cpu import preprocess_baseline, preprocess_clip
+
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    ds = SyntheticUtils(root=str(tmp_path / "ds"), n_images=4, size=(160, 160)).materialize()
+    out_dir = run_aug.output_folder(str(tmp_path / "ds"), run_aug.AugConfig())
+    os.makedirs(out_dir)
+    for index, p in enumerate(ds.original_images_paths):
+        stem = os.path.splitext(os.path.basename(p))[0]
+        for i in range(3):
+            Image.fromarray(synthetic_source(500 + 3 * index + i, 160, 160, kind=("blobs", "noise", "smooth")[i])).save(
+                os.path.join(out_dir, run_aug.aug_file_name(stem, f"an airplane, take {i}", i)))
+    # oracle logits for every augmentation, in the writer's own (dataset, listdir) order
+    names = [f for f in os.listdir(out_dir)]
+    matched = filtering.match_augmentations(ds.original_images_paths, names, out_dir)
+    order = [(p, a) for p in ds.original_images_paths for a in matched[os.path.basename(p)]]
+    imgs = [np.asarray(Image.open(a).convert("RGB")) for _, a in order]
+    labels = [ds.get_image_path_to_class_id_dict()[p] for p, _ in order]
+    om = wsdan.WSDANOracle(ds.num_classes, "resnet50").eval()
+    om.load_state_dict(ck.random_filter_state_dict(ck.wsdan_shapes(ds.num_classes, "resnet50"), ds.wsdan_seed), strict=False)
+    oc = clip_rn50.CLIP().eval()
+    oc.load_state_dict(ck.random_filter_state_dict(ck.clip_rn50_shapes(), ds.clip_seed))
+    tok = SyntheticTokenizer()
+    with torch.no_grad():
+        lo = om(torch.stack([preprocess_baseline(a) for a in imgs]))
+        fi = F.normalize(oc.encode_image(torch.stack([preprocess_clip(a) for a in imgs])), dim=-1)
+        cls_logits = oc.logit_scale.exp() * fi @ F.normalize(oc.encode_text(tok(ds.get_clip_filtering_prompts())), dim=-1).t()
+        sem_logits = oc.logit_scale.exp() * fi @ F.normalize(oc.encode_text(tok([ds.get_basic_prompt()] + filtering.SEMANTIC_NEGATIVE_PROMPTS)), dim=-1).t()
+    conf = torch.softmax(lo, 1)[torch.arange(len(order)), torch.tensor(labels)]
+    cconf = torch.softmax(cls_logits, 1)[torch.arange(len(order)), torch.tensor(labels)]
+    in_topk = wsdan.in_topk(lo, labels, 10)
+
+    def mid(v):
+        s = torch.sort(v).values
+        gaps = s[1:] - s[:-1]
+        k = int(torch.argmax(gaps[len(s) // 4: 3 * len(s) // 4])) + len(s) // 4  # the widest gap in the middle half
+        return float((s[k] + s[k + 1]) / 2)
+
+    def expect(keep_fn):
+        d = {os.path.basename(p): [] for p in ds.original_images_paths}
+        for k, (p, a) in enumerate(order):
+            if keep_fn(k):
+                d[os.path.basename(p)].append(a)
+        return d
+
+    common = dict(init_log=False, ds_utils=ds)
+    # (a) top-k + too-high confidence (utils.py:357-376)
+    thr = mid(conf)
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, model_confidence_based_filtering=True,
+                                                                       filter_confidence_higher_than=thr, **common)
+    assert "filter_confidence_higher_than" in os.path.basename(jp)
+    assert json.load(open(jp)) == expect(lambda k: bool(in_topk[k]) and not float(conf[k]) > thr)
+    # (b) per-class CLIP confidence + semantic (utils.py:186-191, :377-404); threshold 1/C/discount placed in a gap of the oracle values
+    cthr = mid(cconf)
+    discount = 1.0 / (ds.num_classes * cthr)
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, clip_filtering="per_class", clip_filtering_discount=discount,
+                                                                       semantic_filtering=True, **common)
+    assert os.path.basename(jp).startswith("clip_filtering_per_class_discount_")
+    assert json.load(open(jp)) == expect(lambda k: float(cconf[k]) >= 1 / ds.num_classes / discount and int(sem_logits[k].argmax()) == 0)
+    # (c) ALIA confidence filter (utils.py:411-434): same global-`random` draws in the same order
+    ds.alia_threshold = mid(lo.max(dim=1).values)
+    random.seed(123)
+    draws = []
+
+    def alia_keep(k):
+        if float(lo[k].max()) > ds.alia_threshold:
+            draws.append(random.random())
+            return not draws[-1] > 0.2
+        return True
+
+    want = expect(alia_keep)
+    random.seed(123)
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, alia_conf_filtering=True, **common)
+    assert os.path.basename(jp) == "alia_conf_filtering-aug.json" and json.load(open(jp)) == want and len(draws) > 0
