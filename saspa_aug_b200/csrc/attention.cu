@@ -45,6 +45,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 // Stage a [rows x d] bf16 tile (row stride ld elements in gmem) into smem rows of DP*2+16 bytes,
 // zero-filling rows >= valid_rows and columns in [d, DP).
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DP>
 __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long ld, int valid_rows, int d, int tid) {
   constexpr int ROWB = DP * 2 + 16;
@@ -313,31 +319,37 @@ __global__ void __launch_bounds__(ATT_THREADS) xattn_resident_kernel(const __nv_
         mma_bf16_16816(sacc[np * 2 + 1], qf[ks], b2, b3);
       }
     }
+    // The kernel is issue-bound (ncu: 70 % of the issue slots, profiles/r1_ncu_full_xattn.txt), so the softmax is kept to four
+    // instructions per score: row max on the raw accumulators (only the n-tiles that reach past tkv are masked), then one FFMA
+    // (scale, minus the scaled max) and one ex2.approx per element.
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < NK16 * 2; ++nt) {
+      if (nt * 8 + 8 > tkv) {  // warp-uniform: only the last n-tile(s) hold keys >= tkv (zero-filled K rows)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = nt * 8 + (lane & 3) * 2 + (e & 1);
-        const float sv = key < tkv ? sacc[nt][e] * scale_log2 : -INFINITY;
-        sacc[nt][e] = sv;
-        mx[e >> 1] = fmaxf(mx[e >> 1], sv);
+        for (int e = 0; e < 4; ++e) {
+          const int key = nt * 8 + (lane & 3) * 2 + (e & 1);
+          if (key >= tkv) sacc[nt][e] = -INFINITY;
+        }
       }
+      mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
     }
+    float nm[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      if (mx[r] == -INFINITY) mx[r] = 0.0f;
+      nm[r] = (mx[r] == -INFINITY) ? 0.0f : -mx[r] * scale_log2;  // scale_log2 > 0: max commutes with the scaling
     }
     float rs[2] = {0.0f, 0.0f};
     uint32_t pf[NK16][4];
 #pragma unroll
     for (int nt = 0; nt < NK16 * 2; ++nt) {
-      const float p0 = exp2f(sacc[nt][0] - mx[0]);
-      const float p1 = exp2f(sacc[nt][1] - mx[0]);
-      const float p2 = exp2f(sacc[nt][2] - mx[1]);
-      const float p3 = exp2f(sacc[nt][3] - mx[1]);
+      const float p0 = ex2_approx_f(fmaf(sacc[nt][0], scale_log2, nm[0]));
+      const float p1 = ex2_approx_f(fmaf(sacc[nt][1], scale_log2, nm[0]));
+      const float p2 = ex2_approx_f(fmaf(sacc[nt][2], scale_log2, nm[1]));
+      const float p3 = ex2_approx_f(fmaf(sacc[nt][3], scale_log2, nm[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
@@ -490,7 +502,7 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
                   "saspa_attention_bf16: q/k/v must be 16-byte aligned");
   SASPA_CHECK_ARG((long long)batch * heads <= 65535, "saspa_attention_bf16: batch*heads must be <= 65535");
   // short key sequences (cross-attention over the text tokens): K/V-resident streaming kernel
-  if (g_attention_impl == 0 && !causal && tkv <= 128 && tq >= 256 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+  if (g_attention_impl == 0 && !causal && scale > 0.0f && tkv <= 128 && tq >= 256 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
     if (d <= 48) return launch_xattn<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 64) return launch_xattn<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 80) return launch_xattn<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
