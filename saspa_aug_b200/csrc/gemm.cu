@@ -557,10 +557,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           for (int j = 0; j < 32; j += 4) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b = *reinterpret_cast<const float4*>(sb + BN / 2 + c0 + j);
-            f[j] *= gelu_erf_f(__uint_as_float(gt[j]) + b.x);
-            f[j + 1] *= gelu_erf_f(__uint_as_float(gt[j + 1]) + b.y);
-            f[j + 2] *= gelu_erf_f(__uint_as_float(gt[j + 2]) + b.z);
-            f[j + 3] *= gelu_erf_f(__uint_as_float(gt[j + 3]) + b.w);
+            f[j] *= gelu_erf_poly_f(__uint_as_float(gt[j]) + b.x);
+            f[j + 1] *= gelu_erf_poly_f(__uint_as_float(gt[j + 1]) + b.y);
+            f[j + 2] *= gelu_erf_poly_f(__uint_as_float(gt[j + 2]) + b.z);
+            f[j + 3] *= gelu_erf_poly_f(__uint_as_float(gt[j + 3]) + b.w);
           }
         } else {
           if (p.row_bias && row_ok) {
