@@ -222,7 +222,7 @@ def ours(args):
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
             "unet_step_ms": unet_step_ms, "model_build_s": round(build_s, 1),
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -306,95 +306,128 @@ def roofline_leg(pipe, dev_in, args):
 # ----------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference's diffusers path) -- also the `--impl reference` arm
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample(args, threads: int, denoise_steps: int = 1):
-    """Bounded sample of the same workload on the host cores: 1 source, Canny (reference's generate_canny if
-    /root/reference exists, else the pinned port) + text encode + `denoise_steps` UniPC steps of the SD v1.5
-    ControlNet pipeline at 512x512 (CFG pair) + VAE decode, fp32; extrapolated to the 20-step image."""
-    import numpy as np
-    import torch
+class CpuPath:
+    """The reference's CPU implementation of the path, as far as it can exist offline: Canny (oracle C port of cv2.Canny, pinned to the
+    reference's generate_canny) + the fp32 torch restatement of the diffusers SD v1.5 ControlNet graph (UNet + ControlNet CFG step, UniPC,
+    VAE decode) on all host threads.  One `sample()` = a bounded slice of one image of the workload: Canny + `denoise_steps` of the 20
+    steps + VAE decode, extrapolated to the full image (text encode omitted, < 1 %)."""
 
-    from oracle import clib
-    from oracle.diffusers_restated import models as om
-    from oracle.diffusers_restated import schedulers as osched
-    from saspa_aug_b200 import checkpoints as ck
-    from saspa_aug_b200.synthetic import synthetic_source, synthetic_token_ids
+    def __init__(self, args, threads: int):
+        import torch
 
-    torch.set_num_threads(threads)
+        from oracle.diffusers_restated import models as om
+        from saspa_aug_b200 import checkpoints as ck
 
-    def ocfg(c):
-        return om.UNetConfig(**{k: getattr(c, k) for k in om.UNetConfig.__dataclass_fields__})
+        torch.set_num_threads(threads)
+        self.args, self.threads = args, threads
 
-    ucfg = ck.UNetConfig.sd15()
-    with torch.no_grad():
-        with torch.device("meta"):  # skip torch's default init (1.3 B parameters); values do not matter for timing
-            unet, cn = om.UNet2DConditionModel(ocfg(ucfg)), om.ControlNetModel(ocfg(ucfg))
-            vae = om.AutoencoderKL(om.VAEConfig.sd15())
-        g = torch.Generator().manual_seed(0)
-        for m in (unet, cn, vae):
-            m.to_empty(device="cpu").eval()
-            for p in m.parameters():
-                p.normal_(0.0, 0.02, generator=g)
-        src = synthetic_source(0)
-        t0 = time.perf_counter()
-        edge = clib.canny(src, 120, 200)
-        t_canny = time.perf_counter() - t0
-        cond = torch.from_numpy(np.repeat(edge[None, ..., None], 3, 3).astype(np.float32) / 255.0).permute(0, 3, 1, 2)
-        cond = torch.cat([cond] * 2)
-        text = torch.randn((2, 77, 768), generator=g)
-        lat = torch.randn((1, 4, 64, 64), generator=g)
-        sched = osched.UniPCMultistepScheduler()
-        sched.set_timesteps(args.num_inference_steps)
-        t0 = time.perf_counter()
-        for t in sched.timesteps[:denoise_steps]:
-            x2 = torch.cat([lat] * 2)
-            d, m = cn(x2, t, text, cond, 0.75)
-            eps = unet(x2, t, text, d, m)
-            eu, ec = eps.chunk(2)
-            lat = sched.step(eu + 7.5 * (ec - eu), t, lat)
-        t_step = (time.perf_counter() - t0) / denoise_steps
-        t0 = time.perf_counter()
-        vae.decode(lat / 0.18215)
-        t_dec = time.perf_counter() - t0
-    per_image = t_canny + args.num_inference_steps * t_step + t_dec
-    return {"images_per_s": 1.0 / per_image, "t_canny_s": t_canny, "t_step_s": t_step, "t_decode_s": t_dec, "per_image_s": per_image}
+        def ocfg(c):
+            return om.UNetConfig(**{k: getattr(c, k) for k in om.UNetConfig.__dataclass_fields__})
+
+        ucfg = ck.UNetConfig.sd15()
+        with torch.no_grad():
+            with torch.device("meta"):  # skip torch's default init (1.3 B parameters); values do not matter for timing
+                self.unet, self.cn = om.UNet2DConditionModel(ocfg(ucfg)), om.ControlNetModel(ocfg(ucfg))
+                self.vae = om.AutoencoderKL(om.VAEConfig.sd15())
+            self.g = torch.Generator().manual_seed(0)
+            for m in (self.unet, self.cn, self.vae):
+                m.to_empty(device="cpu").eval()
+                for p in m.parameters():
+                    p.normal_(0.0, 0.02, generator=self.g)
+
+    def sample(self, denoise_steps: int = 1):
+        import numpy as np
+        import torch
+
+        from oracle import clib
+        from oracle.diffusers_restated import schedulers as osched
+        from saspa_aug_b200.synthetic import synthetic_source
+
+        args, g = self.args, self.g
+        with torch.no_grad():
+            src = synthetic_source(0)
+            t0 = time.perf_counter()
+            edge = clib.canny(src, 120, 200)
+            t_canny = time.perf_counter() - t0
+            cond = torch.from_numpy(np.repeat(edge[None, ..., None], 3, 3).astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+            cond = torch.cat([cond] * 2)
+            text = torch.randn((2, 77, 768), generator=g)
+            lat = torch.randn((1, 4, 64, 64), generator=g)
+            sched = osched.UniPCMultistepScheduler()
+            sched.set_timesteps(args.num_inference_steps)
+            t0 = time.perf_counter()
+            for t in sched.timesteps[:denoise_steps]:
+                x2 = torch.cat([lat] * 2)
+                d, m = self.cn(x2, t, text, cond, 0.75)
+                eps = self.unet(x2, t, text, d, m)
+                eu, ec = eps.chunk(2)
+                lat = sched.step(eu + 7.5 * (ec - eu), t, lat)
+            t_step = (time.perf_counter() - t0) / denoise_steps
+            t0 = time.perf_counter()
+            self.vae.decode(lat / 0.18215)
+            t_dec = time.perf_counter() - t0
+        per_image = t_canny + args.num_inference_steps * t_step + t_dec
+        return {"images_per_s": 1.0 / per_image, "t_canny_s": t_canny, "t_step_s": t_step, "t_decode_s": t_dec, "per_image_s": per_image}
 
 
 def cpu_baseline_leg(args):
     threads = os.cpu_count() or 1
-    r = cpu_sample(args, threads, 1)
+    r = CpuPath(args, threads).sample(1)
     return {"value": round(r["images_per_s"], 6), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"1 source at 512x512: Canny + 1 of {args.num_inference_steps} UniPC CFG steps (UNet+ControlNet fp32) + VAE decode, torch CPU fp32 oracle; "
                       f"per-image time = canny {r['t_canny_s']:.3f}s + {args.num_inference_steps} x {r['t_step_s']:.2f}s + decode {r['t_decode_s']:.2f}s; text encode omitted (<1%)"}
 
 
 def reference_arm(args):
+    """`--impl reference`: W warm-up + exactly K timed steps, each step one bounded sample (CpuPath.sample) of the same workload on all
+    host threads; rank 0 only (the other ranks of a torchrun launch exit 0 without work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
-    for _ in range(args.warmup_ref):
-        cpu_sample(args, threads, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps_ref):
-        vals.append(cpu_sample(args, threads, 1))
+    path = CpuPath(args, threads)
+    for _ in range(args.warmup):
+        path.sample(1)
+    vals = [path.sample(1) for _ in range(max(1, args.steps))]
     r = vals[-1]
-    v = sum(x["images_per_s"] for x in vals) / len(vals)
+    v = len(vals) / sum(x["per_image_s"] for x in vals)
     per_step_ms = (args.sources * args.prompts) / v * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload(args),
         "cpu_baseline": {"value": round(v, 6), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(vals)} bounded samples (1 source: Canny + 1 of {args.num_inference_steps} CFG steps + VAE decode, fp32 torch CPU), extrapolated to "
-                                   f"{args.num_inference_steps}-step images; the reference's diffusers/cv2 stack cannot be installed offline, so this is the oracle port"},
+                         "sample": f"{len(vals)} timed steps after {args.warmup} warm-up, each a bounded sample of one image (Canny + 1 of {args.num_inference_steps} CFG "
+                                   f"steps + VAE decode, fp32 torch CPU; last: step {r['t_step_s']:.2f}s, decode {r['t_decode_s']:.2f}s), extrapolated to "
+                                   f"{args.num_inference_steps}-step images; the reference's diffusers stack cannot be installed offline, so this is the oracle port"},
         "e2e": {"value": round(v, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+def _claim_stdout() -> int:
+    """stdout must carry exactly ONE JSON line: library chatter written straight to fd 1 (e.g. the "NCCL version ..." banner at
+    communicator creation) is sent to stderr for the rest of the run; the saved descriptor is used for the result line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+_RESULT_FD = None
+
+
+def emit(line: str) -> None:
+    if _RESULT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_RESULT_FD, (line + "\n").encode())
 
 
 def main():
+    global _RESULT_FD
+    _RESULT_FD = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -406,8 +439,6 @@ def main():
     ap.add_argument("--vae-micro-batch", type=int, default=8)
     ap.add_argument("--num-inference-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--steps-ref", type=int, default=2)
-    ap.add_argument("--warmup-ref", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
