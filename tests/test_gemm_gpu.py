@@ -191,3 +191,29 @@ def test_gemm_full_size_linearity(cuda_device):
     idx = torch.randint(0, M, (256,), device="cuda")
     _check(gs[idx], s[idx].float() @ b.float().t(), 2e-3)
     assert ((g1 + g2) - gs).abs().max() / gs.abs().max() < 2e-2
+
+
+def test_empty_inputs_and_argument_errors(cuda_device):
+    """C-ABI error behaviour: zero-sized problems are no-ops that return 0; malformed arguments return a negative code that the
+    binding turns into SaspaError (a RuntimeError, so the reference's `except RuntimeError`, run_aug.py:493, still catches it) with
+    the entry point's message -- never a crash, never a silent fallback."""
+    from saspa_aug_b200.ops import SaspaError
+
+    a0 = torch.empty((0, 64), dtype=torch.bfloat16, device="cuda")
+    b = _rand((32, 64), 1)
+    assert ops.gemm(a0, b).shape == (0, 32)
+    x0 = torch.empty((0, 16, 16, 64), dtype=torch.bfloat16, device="cuda")
+    wk = _rand((64, 9 * 64), 2)
+    assert ops.conv2d_igemm(x0, wk, 3).shape == (0, 16, 16, 64)
+    q0 = torch.empty((0, 128, 64), dtype=torch.bfloat16, device="cuda")
+    assert ops.attention(q0, q0, q0, 1).shape == (0, 128, 64)
+    x = _rand((1, 16, 16, 64), 3)
+    with pytest.raises(SaspaError, match="ksize"):
+        ops.conv2d_igemm(x, _rand((64, 25 * 64), 4), 5)
+    with pytest.raises(SaspaError, match="stride"):
+        ops.conv2d_igemm(x, wk, 3, stride=3, pad=1, out_hw=(6, 6))
+    with pytest.raises((SaspaError, AssertionError)):
+        ops.gemm(_rand((8, 60), 5), _rand((8, 60), 6))  # K = 60: row stride not a multiple of 8 elements
+    assert isinstance(SaspaError("x"), RuntimeError)
+    with pytest.raises((SaspaError, AssertionError)):
+        ops.gemm(torch.zeros((8, 64), dtype=torch.bfloat16), torch.zeros((8, 64), dtype=torch.bfloat16))  # CPU tensors: no CPU fallback
