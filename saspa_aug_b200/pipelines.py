@@ -78,6 +78,7 @@ class SaspaControlNetPipeline:
         self._graphs = {}
         self.use_cuda_graph = False
         self.vae_micro_batch = 8
+        self.noise_dtype = torch.float32  # see .to()
         # diffusers loads StableDiffusionSafetyChecker by default with SD v1.5 (filter_nets.SafetyChecker); None = safety_checker=None.
         # Random-init runs keep it off (a random checker would blank images at random); assign one built from real weights to match
         # the reference pipeline bit for bit in behaviour.
@@ -109,7 +110,14 @@ class SaspaControlNetPipeline:
         return cls.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], unet_cfg=ucfg, vae_cfg=vcfg, text_cfg=tcfg, **kw)
 
     # ---- surface touched by run_aug.py ---------------------------------------------------------
-    def to(self, *a, **k):  # `.to(DEVICE, torch.float16)` at run_aug.py:323; weights already live on the device in bf16
+    def to(self, *a, **k):
+        """`.to(DEVICE, torch.float16)` at run_aug.py:323.  Weights already live on the device in bf16; the dtype is remembered because
+        diffusers draws the latent / VAE-posterior noise from the caller's CPU generator IN THE PIPELINE DTYPE (randn_tensor), and an fp16
+        draw consumes the generator differently from an fp32 one: with the same `generator` the reference's noise is reproduced only if
+        the draw dtype matches.  Default fp32 (a pipeline that was never cast, e.g. BASELINE config 1 / the fp32 oracle)."""
+        for x in list(a) + list(k.values()):
+            if isinstance(x, torch.dtype):
+                self.noise_dtype = x
         return self
 
     def upcast_vae(self):  # run_aug.py:224 (sd_xl-turbo); the VAE path already accumulates in fp32
@@ -273,9 +281,9 @@ class SaspaControlNetPipeline:
         B = text.shape[0]
         shape = (B, self.vae_cfg.latent_channels, H // 8, W // 8)
         # diffusers randn_tensor: CPU generator -> sample on CPU, then move.  img2img draws the VAE posterior noise first.
-        post = torch.randn(shape, generator=generator, dtype=torch.float32).to(self.device) if source_u8 is not None else None
-        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=torch.float32)
-        noise = noise.to(self.device)
+        post = torch.randn(shape, generator=generator, dtype=self.noise_dtype).float().to(self.device) if source_u8 is not None else None
+        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=self.noise_dtype)
+        noise = noise.float().to(self.device)
         per_step = [] if return_latents_per_step else None
         cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
         out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, num_inference_steps=num_inference_steps,
@@ -515,10 +523,10 @@ class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
             raise ValueError(f"condtioning_image is {tuple(control_u8.shape[1:3])}, height/width say {(height, width)}: the reference passes the "
                              "control image's own size (run_aug.py:270-271)")
         shape = (B, self.vae_cfg.latent_channels, height // 8, width // 8)
-        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=torch.float32)
+        noise = latents if latents is not None else torch.randn(shape, generator=generator, dtype=self.noise_dtype)
         per_step = [] if return_latents_per_step else None
         cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
-        out = self.generate_batch(text, neg, control_u8, None, noise=noise.to(self.device), num_inference_steps=num_inference_steps,
+        out = self.generate_batch(text, neg, control_u8, None, noise=noise.float().to(self.device), num_inference_steps=num_inference_steps,
                                   guidance_scale=guidance_scale, controlnet_conditioning_scale=1.0, step_callback=cb)
         arr = out.cpu().numpy()
         if output_type == "pil":

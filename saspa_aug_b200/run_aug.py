@@ -86,13 +86,10 @@ def aug_file_name(image_stem: str, prompt: str, i: int) -> str:
     return f"{image_stem[:MAX_FILENAME_LENGTH]}_prompt_{prompt.replace('/', '-')}_{i}.png"
 
 
-def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
-    """all_utils/utils.py:58-79 (host-side pre-processing; identity for sources already at HxW % 64 == 0, min side = res)."""
-    import cv2
-
+def resized_hw(h: int, w: int, smaller_side_res: int):
+    """Size rule of all_utils/utils.py:58-79: min side -> res, area cap 1.2 MP, both sides rounded to multiples of 64 -> (H, W, k)."""
     MAX_RES_SIZE = 1200000
-    H, W, _ = input_image.shape
-    H, W = float(H), float(W)
+    H, W = float(h), float(w)
     k = float(smaller_side_res) / min(H, W)
     H *= k
     W *= k
@@ -100,8 +97,14 @@ def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
         k = np.sqrt(MAX_RES_SIZE / (H * W))
         H *= k
         W *= k
-    H = int(np.round(H / 64.0)) * 64
-    W = int(np.round(W / 64.0)) * 64
+    return int(np.round(H / 64.0)) * 64, int(np.round(W / 64.0)) * 64, k
+
+
+def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
+    """all_utils/utils.py:58-79 (host-side pre-processing; identity for sources already at HxW % 64 == 0, min side = res)."""
+    import cv2
+
+    H, W, k = resized_hw(input_image.shape[0], input_image.shape[1], smaller_side_res)
     if (H, W) == input_image.shape[:2]:
         return input_image
     return cv2.resize(input_image, (W, H), interpolation=cv2.INTER_LANCZOS4 if k > 1 else cv2.INTER_AREA)
@@ -211,6 +214,32 @@ def item_seed(seed: int, index: int, i: int) -> int:
     return (seed * 1_000_003 + index * 131 + i) % (2 ** 31 - 1)
 
 
+def reference_order_noise(cfg: AugConfig, source_hw: Sequence, sampled: Sequence[Sequence[str]], skip, mine, latent_channels: int = 4,
+                          dtype=None):
+    """RNG_MODE = "reference_order" (SURVEY.md 8e): the reference threads ONE generator -- ``torch.manual_seed(SEED)``, the global CPU
+    generator, run_aug.py:324 -- through every pipeline call in dataset order (:464), and diffusers draws from it on the CPU in the
+    pipeline dtype (fp16 after ``.to(DEVICE, torch.float16)``, :323): per call the VAE-posterior noise first when SDEdit is on, then the
+    latent noise.  This rank-independent pre-pass replays exactly that stream (a private generator with the same seed yields the same
+    values) and keeps the draws of the items in ``mine``; items the reference would skip (existing output, :430-432) draw nothing.
+      source_hw  [(H, W)] of every source AFTER resize_image;  skip(index, i) -> bool;  mine: set of source indices of this rank
+    -> {(index, i): (noise fp32 [1,C,H/8,W/8], posterior noise fp32 | None)}"""
+    import torch
+
+    dtype = dtype or torch.float16
+    g = torch.Generator().manual_seed(cfg.SEED)
+    out = {}
+    for index, (H, W) in enumerate(source_hw):
+        shape = (1, latent_channels, H // 8, W // 8)
+        for i in range(len(sampled[index])):
+            if skip(index, i):
+                continue
+            post = torch.randn(shape, generator=g, dtype=dtype) if cfg.SDEDIT else None
+            noise = torch.randn(shape, generator=g, dtype=dtype)
+            if index in mine:
+                out[(index, i)] = (noise.float(), post.float() if post is not None else None)
+    return out
+
+
 def sample_prompts(prompts: Sequence[str], n_sources: int, cfg: AugConfig) -> List[List[str]]:
     """Rank-independent pre-pass replaying the reference's sequential global draws (run_aug.py:382, :391-394):
     np.random.seed(SEED) then one np.random.choice(prompts, NUM_PER_IMAGE) per source in dataset order."""
@@ -241,6 +270,18 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: st
     paths = ds_utils.original_images_paths
     sampled = sample_prompts(prompts, len(paths), cfg)
     mine = shard_indices(len(paths), rank, world)
+    ref_noise = None
+    if cfg.RNG_MODE == "reference_order":
+        def _hw(p):
+            with Image.open(p) as im:  # header only
+                w, h = im.size
+            return resized_hw(h, w, cfg.RESOLUTION)[:2]
+
+        ref_noise = reference_order_noise(cfg, [_hw(p) for p in paths], sampled,
+                                          lambda index, i: (Path(out_dir) / aug_file_name(Path(paths[index]).stem, sampled[index][i], i)).exists(),
+                                          set(mine), pipe.vae_cfg.latent_channels)
+    elif cfg.RNG_MODE != "per_item":
+        raise ValueError(f"RNG_MODE {cfg.RNG_MODE!r}: per_item | reference_order")
     pool = ThreadPoolExecutor(max_workers=io_threads)
     written = []
     work = []  # (index, i, prompt, output_path)
@@ -288,6 +329,12 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts: Sequence[str], out_dir: st
             shape = (1, pipe.vae_cfg.latent_channels, H // 8, W // 8)
             noise, post = [], []
             for (index, i, _, _) in chunk:
+                if ref_noise is not None:
+                    n_ref, p_ref = ref_noise[(index, i)]
+                    noise.append(n_ref)
+                    if cfg.SDEDIT:
+                        post.append(p_ref)
+                    continue
                 g = torch.Generator().manual_seed(item_seed(cfg.SEED, index, i))
                 if cfg.SDEDIT:
                     post.append(torch.randn(shape, generator=g))

@@ -97,3 +97,37 @@ def test_driver_other_base_models(cuda_device, tmp_path, base_model):
                                     blip_src_category=ds.meta_class, blip_target_category=ds.meta_class)
     a, b = np.asarray(one).astype(int), np.asarray(Image.open(path)).astype(int)
     assert np.abs(a - b).mean() < 1.0 and np.abs(a - b).max() <= 16, (np.abs(a - b).mean(), np.abs(a - b).max())
+
+
+def test_reference_order_rng_matches_sequentially_threaded_generator(cuda_device, tmp_path):
+    """RNG_MODE = "reference_order": the sharded loop (here as rank 1 of 2 and rank 0 of 2) produces the images a reference-style
+    single-process loop produces when ONE generator (torch.manual_seed(SEED), fp16 draws after .to(device, float16)) is threaded through
+    per-image pipeline calls in dataset order (run_aug.py:324, :464)."""
+    from PIL import Image
+
+    ds = SyntheticUtils(root=str(tmp_path / "ds"), n_images=4, size=(128, 128)).materialize()
+    cfg = run_aug.AugConfig(BASE_MODEL="tiny", RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4, RNG_MODE="reference_order")
+    pipe = run_aug.init_pipeline("tiny", "canny", 0, sampler="ddim").to("cuda", torch.float16)
+    prompts = [f"an airplane above the clouds {i}." for i in range(8)]
+    sampled = run_aug.sample_prompts(prompts, 4, cfg)
+    g = torch.manual_seed(cfg.SEED)  # the reference's generator is the global CPU generator
+    want = {}
+    for index, p in enumerate(ds.original_images_paths):
+        src = Image.open(p).convert("RGB")
+        canny = run_aug.generate_canny(src, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, cfg.RESOLUTION)
+        for i, prompt in enumerate(sampled[index]):
+            want[(index, i)] = np.asarray(run_aug.pass_thorugh_pipe("sd_v1.5", pipe, prompt, src, 0, cfg.SDEDIT_STRENGTH, cfg.NUM_INFERENCE_STEPS, g,
+                                                                    cfg.GUIDANCE_SCALE, cfg.CONTROLNET_CONDITIONING_SCALE, control_image=canny)).astype(int)
+    got = {}
+    for rank in (1, 0):
+        for index, i, path in run_aug.generate(cfg, ds, pipe, prompts, str(tmp_path / f"out{rank}" / "images"), rank=rank, world=2):
+            got[(index, i)] = np.asarray(Image.open(path)).astype(int)
+    assert set(got) == set(want)
+    for k in want:
+        d = np.abs(got[k] - want[k])
+        assert d.mean() < 1.0 and d.max() <= 16, (k, d.mean(), d.max())
+    # and it differs from the per-item mode (different noise)
+    cfg2 = run_aug.AugConfig(BASE_MODEL="tiny", RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4)
+    other = run_aug.generate(cfg2, ds, pipe, prompts, str(tmp_path / "per_item" / "images"))
+    a = np.asarray(Image.open(other[0][2])).astype(int)
+    assert np.abs(a - want[(other[0][0], other[0][1])]).mean() > 2.0

@@ -141,3 +141,51 @@ def test_json_writer_from_gathered_decisions(tmp_path):
     with pytest.raises(KeyError):
         filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
                                                                    init_log=False, ds_utils=ds, decisions=missing)
+
+
+def test_reference_order_noise_replays_the_global_generator():
+    """RNG_MODE = "reference_order": every rank replays the ONE generator the reference threads through all pipeline calls
+    (torch.manual_seed(SEED) -> global CPU generator, fp16 draws on the CPU, posterior noise first under SDEdit) and keeps its own
+    items; the union over ranks equals a sequential single-process replay, skipped (already existing) items draw nothing."""
+    import torch
+
+    sizes = [(512, 512), (512, 704), (576, 512), (512, 512), (512, 512)]
+    sampled = [["a", "b"]] * len(sizes)
+    for sdedit in (0, 1):
+        cfg = run_aug.AugConfig(SEED=7, SDEDIT=sdedit)
+        skipped = {(1, 1), (3, 0)}
+        # literal sequential replay, the way run_aug.py + diffusers consume the global generator
+        g = torch.manual_seed(cfg.SEED)
+        want = {}
+        for index, (H, W) in enumerate(sizes):
+            for i in range(2):
+                if (index, i) in skipped:
+                    continue
+                shape = (1, 4, H // 8, W // 8)
+                post = torch.randn(shape, generator=g, dtype=torch.float16) if sdedit else None
+                want[(index, i)] = (torch.randn(shape, generator=g, dtype=torch.float16), post)
+        got = {}
+        for rank in range(3):
+            mine = set(run_aug.shard_indices(len(sizes), rank, 3))
+            part = run_aug.reference_order_noise(cfg, sizes, sampled, lambda a, b: (a, b) in skipped, mine)
+            assert all(k[0] in mine for k in part) and not (set(part) & set(got))
+            got.update(part)
+        assert set(got) == set(want)
+        for k, (n, p) in want.items():
+            assert got[k][0].dtype == torch.float32 and torch.equal(got[k][0], n.float())
+            assert (got[k][1] is None) if p is None else torch.equal(got[k][1], p.float())
+    assert run_aug.resized_hw(300, 400, 512)[:2] == (512, 704) and run_aug.resized_hw(512, 512, 512)[:2] == (512, 512)
+
+
+def test_pipeline_draws_noise_in_the_dtype_given_to_to():
+    """`pipe.to(DEVICE, torch.float16)` (run_aug.py:323) makes diffusers draw latent noise from the caller's generator in fp16; the
+    drop-in remembers the dtype so the same generator state produces the same noise (an fp32 draw consumes the generator differently)."""
+    import torch
+
+    from saspa_aug_b200.pipelines import SaspaControlNetPipeline
+
+    p = SaspaControlNetPipeline.__new__(SaspaControlNetPipeline)
+    p.noise_dtype = torch.float32
+    assert p.to("cuda") is p and p.noise_dtype == torch.float32
+    assert p.to("cuda", torch.float16) is p and p.noise_dtype == torch.float16
+    assert p.to(torch_dtype=torch.bfloat16).noise_dtype == torch.bfloat16
