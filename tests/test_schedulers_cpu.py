@@ -97,3 +97,47 @@ def test_known_timesteps():
     t = psched.make_scheduler("ddim", timestep_spacing="trailing")
     t.set_timesteps(4)
     assert t.timesteps.tolist() == [999, 749, 499, 249]
+
+
+@pytest.mark.parametrize("name,n", [("ddim", 20), ("ddim", 7), ("unipc", 20), ("unipc", 9), ("pndm", 20), ("pndm", 6)])
+def test_exact_on_noise_consistent_trajectories(name, n):
+    """Pins the restated schedulers (diffusers is not installable offline: "parity unpinned" at the reference boundary) to the one
+    property all three solvers must have by construction: if the model returns the TRUE noise of a trajectory x_t = sqrt(a_t) x0 +
+    sqrt(1 - a_t) eps (constant x0 and eps), every step lands exactly on that trajectory at the previous timestep -- DDIM (eta 0) by its
+    closed form, UniPC (data prediction: the predicted x0 is constant, so predictor and corrector are exact at any order), PLMS (its
+    transfer formula is exact for a constant eps).  Checked for the oracle and the product's coefficient tables, in fp64."""
+    from oracle.diffusers_restated.pipelines import make_scheduler as omake
+
+    g = torch.Generator().manual_seed(3)
+    shape = (1, 4, 4, 4)
+    x0 = torch.randn(shape, generator=g, dtype=torch.float64)
+    eps = torch.randn(shape, generator=g, dtype=torch.float64)
+    o, p = omake(name), psched.make_scheduler(name)
+    o.set_timesteps(n)
+    p.set_timesteps(n)
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2  # scaled_linear (SURVEY.md A.4)
+    acp = torch.cumprod(1.0 - betas, 0)
+
+    def on_traj(t):
+        a = acp[int(t)] if t >= 0 else torch.tensor(1.0, dtype=torch.float64)
+        return a.sqrt() * x0 + (1 - a).sqrt() * eps
+
+    ts = [int(t) for t in o.timesteps]
+    x = on_traj(ts[0])
+    bufs = {"x": x.clone()}
+    for nm in p.history_buffers:
+        bufs[nm] = torch.zeros(shape, dtype=torch.float64)
+    p.begin(0)
+    xo = x.clone()
+    for k, t in enumerate(ts):
+        xo = o.step(eps, torch.tensor(t), xo)
+        _apply(p.plan(k), bufs, eps)
+    # where the trajectory ends: DDIM / PLMS step to t_last - 1000/n (alpha of "timestep -1" = final_alpha_cumprod = a_0 with
+    # set_alpha_to_one=False); UniPC's last step goes to sigma = 0, i.e. returns x0 itself
+    if name == "unipc":
+        want = x0
+    else:
+        want = acp[0].sqrt() * x0 + (1 - acp[0]).sqrt() * eps
+    for got, tag in ((xo.double(), "oracle"), (bufs["x"], "product")):
+        err = (got - want).abs().max().item()
+        assert err < 2e-5, (name, n, tag, err)  # measured 0.6e-6 .. 2.6e-6 (fp32 coefficient tables)
