@@ -420,14 +420,14 @@ class SaspaBlipControlNetPipeline(SaspaControlNetPipeline):
         embeddings after ``ctx_begin_pos`` (=2) token embeddings -> text [B,77,768];
       * CFG against ``neg_prompt`` (plain CLIP encode, 77 ids); PNDM with skip_prk_steps (PLMS); ControlNet conditioning scale 1.0
         (the pipeline passes none); latents = randn * init_noise_sigma; VAE decode; postprocess.
-    The subject embedding is step- and prompt-invariant: it is cached per (reference image bytes, subject ids)."""
+    The subject embedding is step- and prompt-invariant: it is computed once per call / micro-batch, outside the step loop (the
+    sharded driver passes each source once per micro-batch; `get_query_embeddings` can be called separately to reuse it across prompts)."""
 
     def __init__(self, *a, qformer: snn.QFormer = None, qformer_tokenizer=None, ctx_begin_pos: int = 2, **k):
         super().__init__(*a, **k)  # from_state_dicts passes sampler "pndm": the checkpoint's scheduler is kept (run_aug.py:217)
         self.qformer = qformer
         self.qformer_tokenizer = qformer_tokenizer or SyntheticBertTokenizer(qformer.cfg.vocab_size, qformer.cfg.max_position_embeddings)
         self.ctx_begin_pos = ctx_begin_pos
-        self._subject_cache = {}
 
     @classmethod
     def from_state_dicts(cls, unet_sd, controlnet_sd, vae_sd, text_sd, qformer_sd, *, unet_cfg=None, vae_cfg=None, text_cfg=None, qformer_cfg=None,
