@@ -75,8 +75,6 @@ class SaspaControlNetPipeline:
         self.vae_cfg = vae_cfg or ck.VAEConfig.sd15()
         self.scheduler: SchedulerBase = make_scheduler(sampler)
         self._neg_cache = {}
-        self._graphs = {}
-        self.use_cuda_graph = False
         self.vae_micro_batch = 8
         self.noise_dtype = torch.float32  # see .to()
         # diffusers loads StableDiffusionSafetyChecker by default with SD v1.5 (filter_nets.SafetyChecker); None = safety_checker=None.

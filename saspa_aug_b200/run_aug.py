@@ -140,9 +140,9 @@ def generate_canny(cond_image_input, low_threshold, high_threshold, image_resolu
 
 
 def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="ddim", state_dicts=None, device="cuda"):
-    """run_aug.py:128-230 for the ControlNet-canny SD v1.5 architecture.  ``use_compile`` is accepted and ignored (the
-    launch list is replayed by CUDA graphs, not traced).  Weights: ``state_dicts`` (diffusers-keyed) or deterministic
-    random init -- no checkpoints exist offline."""
+    """run_aug.py:128-230 for the ControlNet-canny pipelines (SD v1.5, SD-XL(-turbo), BLIP-Diffusion).  ``use_compile`` is accepted
+    and ignored: nothing is traced, the kernels are launched directly (the step is GPU-bound: ~550 launches per 94 ms at micro-batch
+    32).  Weights: ``state_dicts`` (diffusers-keyed) or deterministic random init -- no checkpoints exist offline."""
     from .pipelines import (SaspaBlipControlNetPipeline, SaspaControlNetPipeline, SaspaSDXLControlNetPipeline, blip_configs, random_state_dicts,
                             sdxl_configs)
 

@@ -22,13 +22,10 @@ def main():
     ap.add_argument("--mb", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--decode", action="store_true")
-    ap.add_argument("--graph", action="store_true")
     ap.add_argument("--shapes", action="store_true", help="CUDA-event time every tcgen05 launch and print a per-shape table (no ncu)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     pipe = SaspaControlNetPipeline.random_init("sd15", seed=1234, sampler="unipc", device=dev, img2img=False)
-    if a.graph:
-        pipe.use_cuda_graph = True
     src = torch.from_numpy(np.stack([synthetic_source(s) for s in range(max(1, a.mb // 2))])).to(dev)
     ids = torch.cat([synthetic_token_ids(i) for i in range(a.mb)]).to(dev)
     neg = pipe.encode_prompt_ids(synthetic_token_ids(999_999).to(dev)).expand(a.mb, -1, -1).contiguous()
