@@ -189,3 +189,37 @@ def test_pipeline_draws_noise_in_the_dtype_given_to_to():
     assert p.to("cuda") is p and p.noise_dtype == torch.float32
     assert p.to("cuda", torch.float16) is p and p.noise_dtype == torch.float16
     assert p.to(torch_dtype=torch.bfloat16).noise_dtype == torch.bfloat16
+
+
+from oracle import ref_import  # noqa: E402
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_host_mirrors_against_the_reference_functions_live():
+    """The host-side mirrors of all_utils/utils.py run against the reference's OWN functions (imported from /root/reference, this
+    container only): resize_image (:58-79, LANCZOS4 up / AREA down, x64 rounding, 1.2 MP cap), HWC3 (:39-55, gray / RGBA),
+    get_dict_of_value_counts (:468-482) and get_aug_json_path (:194-218) on a flag sweep."""
+    import itertools
+
+    ru = ref_import.import_reference_utils()
+    rng = np.random.default_rng(5)
+    for h, w in [(300, 400), (512, 512), (1600, 1200), (720, 1280), (100, 333), (2000, 3000)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for res in (512, 768):
+            want, got = ru.resize_image(img, res), run_aug.resize_image(img, res)
+            assert want.shape == got.shape and np.array_equal(want, got), (h, w, res)
+            assert run_aug.resized_hw(h, w, res)[:2] == want.shape[:2]
+    gray = rng.integers(0, 256, (37, 41), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    one = rng.integers(0, 256, (9, 9, 1), dtype=np.uint8)
+    for x in (gray, rgba, one, rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)):
+        assert np.array_equal(ru.HWC3(x), run_aug.HWC3(x))
+    d = {"a": [1, 2], "b": [], "c": [3], "d": [4, 5]}
+    assert dict(ru.get_dict_of_value_counts_image_name_to_num_aug_images(d)) == filtering.get_dict_of_value_counts(d)
+    for lmin, lmax, cf, sem, conf, topk, hi, alia in itertools.product((None, 0.1), (None, 0.7), (False, "per_class"), (False, True), (False, True),
+                                                                       (10, 5), (None, 0.9), (False, True)):
+        if cf and conf:
+            continue
+        kw = dict(lpips_min=lmin, lpips_max=lmax, clip_filtering=cf, clip_filtering_discount=2, semantic_filtering=sem,
+                  model_confidence_based_filtering=conf, conf_top_k=topk, filter_confidence_higher_than=hi, alia_conf_filtering=alia)
+        assert ru.get_aug_json_path("/data/x/aug/images", **kw) == filtering.get_aug_json_path("/data/x/aug/images", **kw), kw
