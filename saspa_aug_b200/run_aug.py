@@ -411,11 +411,13 @@ def filter_shard(cfg: AugConfig, ds_utils, written, device="cuda", batch_size: i
     return rec
 
 
-def run_sharded(cfg: AugConfig, ds_utils, prompts: Sequence[str], ds_root: str, pipe=None, device=None, filter_models=None):
+def run_sharded(cfg: AugConfig, ds_utils, prompts: Sequence[str], ds_root: str, pipe=None, device=None, filter_models=None,
+                generate_fn=None, filter_fn=None):
     """End to end for one rank of a one-process-per-GPU job (RANK / WORLD_SIZE / LOCAL_RANK from torchrun; single process otherwise):
     generate this rank's shard (run_aug.py:357-471) -> filter it on this GPU -> ONE collective (all-gather of the per-image filter
     records, NCCL over NVLink on GPUs) -> rank 0 writes the aug JSON through the reference-compatible writer (run_aug.py:721-733).
-    Returns (json_path | None on ranks > 0, stats)."""
+    Returns (json_path | None on ranks > 0, stats).  ``generate_fn`` / ``filter_fn`` replace the two GPU stages (defaults: ``generate``,
+    ``filter_shard``); the CPU test of the multi-rank host logic (gloo, world size 2) injects stand-ins."""
     import time
 
     import torch
@@ -431,13 +433,13 @@ def run_sharded(cfg: AugConfig, ds_utils, prompts: Sequence[str], ds_root: str, 
         torch.cuda.set_device(torch.device(device))
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
-    if pipe is None:
+    if pipe is None and generate_fn is None:
         pipe = init_pipeline(cfg.BASE_MODEL, cfg.CONTROLNET, cfg.SDEDIT, sampler=cfg.SAMPLER, device=device)
     out_dir = output_folder(ds_root, cfg)
     t0 = time.perf_counter()
-    written = generate(cfg, ds_utils, pipe, prompts, out_dir, rank=rank, world=world)
+    written = (generate_fn or generate)(cfg, ds_utils, pipe, prompts, out_dir, rank=rank, world=world)
     t1 = time.perf_counter()
-    rec = filter_shard(cfg, ds_utils, written, device=device, filter_models=filter_models)
+    rec = (filter_fn or filter_shard)(cfg, ds_utils, written, device=device, filter_models=filter_models)
     t2 = time.perf_counter()
     allrec = gather_records(rec, rank, world)
     stats = {"rank": rank, "world": world, "generated": len(written), "generate_s": t1 - t0, "filter_s": t2 - t1}

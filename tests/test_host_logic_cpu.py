@@ -223,3 +223,74 @@ def test_host_mirrors_against_the_reference_functions_live():
         kw = dict(lpips_min=lmin, lpips_max=lmax, clip_filtering=cf, clip_filtering_discount=2, semantic_filtering=sem,
                   model_confidence_based_filtering=conf, conf_top_k=topk, filter_confidence_higher_than=hi, alia_conf_filtering=alia)
         assert ru.get_aug_json_path("/data/x/aug/images", **kw) == filtering.get_aug_json_path("/data/x/aug/images", **kw), kw
+
+
+_SHARDED_WORKER = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+root = sys.argv[2]
+from PIL import Image
+from saspa_aug_b200 import run_aug
+from saspa_aug_b200.datasets import SyntheticUtils
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ds = SyntheticUtils(root=root, n_images=7, size=(32, 32))
+if rank == 0:
+    ds.materialize()
+import torch.distributed as dist
+dist.init_process_group("gloo")
+dist.barrier()
+cfg = run_aug.AugConfig(NUM_PER_IMAGE=2)
+prompts = [f"an airplane, variation {i}." for i in range(10)]
+
+
+def fake_generate(cfg, ds_utils, pipe, prompts, out_dir, rank=0, world=1):  # stands in for the GPU generation stage: same names, same shard
+    os.makedirs(out_dir, exist_ok=True)
+    sampled = run_aug.sample_prompts(prompts, len(ds_utils.original_images_paths), cfg)
+    written = []
+    for index in run_aug.shard_indices(len(ds_utils.original_images_paths), rank, world):
+        stem = os.path.splitext(os.path.basename(ds_utils.original_images_paths[index]))[0]
+        for i, prompt in enumerate(sampled[index]):
+            path = os.path.join(out_dir, run_aug.aug_file_name(stem, prompt, i))
+            Image.new("RGB", (8, 8), (index * 30, i * 100, rank * 100)).save(path)
+            written.append((index, i, path))
+    return written
+
+
+def fake_filter(cfg, ds_utils, written, device=None, filter_models=None):  # deterministic decisions: (index + i) % 3 != 0 passes top-k, i == 0 is semantic
+    rec = np.zeros((len(written), 4), np.int32)
+    for k, (index, i, _) in enumerate(written):
+        rec[k] = (index, i, int((index + i) % 3 != 0), int(i == 0 or index % 2 == 0))
+    return rec
+
+
+json_path, stats = run_aug.run_sharded(cfg, ds, prompts, root, generate_fn=fake_generate, filter_fn=fake_filter, device="cpu")
+assert stats["generated"] == 2 * len(run_aug.shard_indices(7, rank, world))
+if rank == 0:
+    d = json.load(open(json_path))
+    assert list(d) == [os.path.basename(p) for p in ds.original_images_paths]
+    sampled = run_aug.sample_prompts(prompts, 7, cfg)
+    kept = 0
+    for index, p in enumerate(ds.original_images_paths):
+        stem = os.path.splitext(os.path.basename(p))[0]
+        want = {os.path.join(run_aug.output_folder(root, cfg), run_aug.aug_file_name(stem, sampled[index][i], i)) for i in range(2)
+                if (index + i) % 3 != 0 and (i == 0 or index % 2 == 0)}
+        assert set(d[os.path.basename(p)]) == want, (index, d[os.path.basename(p)], want)
+        kept += len(want)
+    assert stats["records"] == 14 and stats["kept"] == kept and json_path.endswith("semantic_filtering-model_confidence_based_filtering_top_10_classes-aug.json")
+    print("SHARDED_OK", kept)
+else:
+    assert json_path is None
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_run_sharded_host_logic_gloo(tmp_path):
+    """The end-to-end rank entry with the two GPU stages replaced by stand-ins: interleaved sharding, barrier, ONE gather of the
+    fixed-size records, rank 0 rebuilding the file names from the rank-independent prompt draw and writing the reference-layout JSON."""
+    w = tmp_path / "worker.py"
+    w.write_text(_SHARDED_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", str(w), ROOT, str(tmp_path / "ds")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
