@@ -46,24 +46,39 @@ def get_aug_json_path(augmented_image_folder_path, lpips_min=None, lpips_max=Non
     return str(Path(augmented_image_folder_path).parent / name)
 
 
-def check_folder_of_images_with_pil(folder, max_delete=50, substrings_to_exclude=()):
-    """all_utils/utils.py:681-703: PIL-verify every image, delete the corrupt ones (at most ``max_delete``)."""
+def check_folder_of_images_with_pil(folder, max_delete=20, substrings_to_exclude=()):
+    """all_utils/utils.py:681-703: PIL-verify every non-excluded file of the folder, delete the corrupt ones, stop checking once
+    ``max_delete`` files were deleted (the reference breaks out of its loop; it does not raise)."""
     from PIL import Image
 
     deleted = 0
-    for p in sorted(Path(folder).glob("*.*")):
-        if any(s in p.name for s in substrings_to_exclude):
-            continue
+    for name in [f for f in os.listdir(folder) if not any(s in f for s in substrings_to_exclude)]:
+        p = Path(folder) / name
         try:
             with Image.open(p) as im:
                 im.verify()
         except Exception:
-            if deleted >= max_delete:
-                raise RuntimeError(f"more than {max_delete} corrupt images in {folder}")
-            logging.info(f"deleting corrupt image {p}")
-            p.unlink()
+            logging.info(f"image {p} is corrupted, deleting")
+            os.remove(p)
             deleted += 1
+            if deleted >= max_delete:
+                logging.info(f"reached max_delete = {max_delete}, breaking")
+                break
     return deleted
+
+
+def load_filter_models(ds_utils, device):
+    """(classifier, clip, tokenizer) for a dataset-utils object.  Two ways in, tried in this order:
+      * ``ds_utils.load_filter_models(ds_utils, device)`` -- a dataset that builds the B200 nets itself (the synthetic one does);
+      * the REFERENCE's interface (all_utils/dataset_utils.py:78-115): a class that only offers ``load_baseline_model()`` -> a torch
+        ``WSDAN_CAL`` (or its ``state_dict``) + transform registers unchanged -- the weights are re-laid out into the B200 classifier
+        (checkpoint_io.wsdan_from_reference_model); CLIP RN50 comes from ``ds_utils.load_clip(device)`` when offered, else from the
+        openai-clip checkpoint named by $SASPA_CLIP_RN50 (a TorchScript / state-dict file, as clip.load reads it)."""
+    if hasattr(ds_utils, "load_filter_models"):
+        return ds_utils.load_filter_models(ds_utils, device)
+    from . import checkpoint_io
+
+    return checkpoint_io.filter_models_from_reference_interface(ds_utils, device)
 
 
 def match_augmentations(original_images_paths: Sequence[str], all_file_names: Sequence[str], folder: str) -> Dict[str, List[str]]:
@@ -104,12 +119,17 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
                                                         semantic_filtering=False, model_confidence_based_filtering=False, conf_top_k: int = 10,
                                                         filter_confidence_higher_than: int = None, init_log=True, alia_conf_filtering=False, *,
                                                         ds_utils=None, filter_models: Optional[Callable] = None, device="cuda", batch_size: int = 64,
-                                                        return_details: bool = False, decisions: Optional[Dict[str, Tuple[int, int]]] = None):
+                                                        return_details: bool = False, decisions: Optional[Dict[Tuple[str, str], Tuple[int, int]]] = None,
+                                                        missing_decisions: Optional[Callable] = None):
     """Drop-in for all_utils/utils.py:221-465 (same positional signature).  Keyword-only extras:
       ds_utils       dataset-utils object (default: saspa_aug_b200.datasets.DS_UTILS_DICT[dataset]())
       filter_models  callable(ds_utils, device) -> (WSDANClassifier | None, CLIPRN50 | None, tokenizer) (default: ds_utils.load_filter_models)
-      decisions      {augmentation path: (in_topk, semantic)} computed elsewhere (the sharded driver gathers every rank's filter
-                     records and lets rank 0 write the JSON through this same function: same matching, ordering and file name)
+      decisions      {(source file name, augmentation path): (in_topk, semantic)} computed elsewhere (the sharded driver gathers every
+                     rank's filter records and lets rank 0 write the JSON through this same function: same matching, ordering and
+                     file name).  Keyed by the PAIR: the reference matches by substring (utils.py:352-354), so one file can belong to
+                     several sources and is scored against each source's own label.
+      missing_decisions  callable([(source name, path)]) -> {pair: (in_topk, semantic)} for matched pairs without a gathered record
+                     (substring cross-matches, files of earlier runs); without it such pairs are logged and left out.
     """
     import torch
 
@@ -143,8 +163,7 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
 
     classifier = clip = tokenizer = None
     if (semantic_filtering or model_confidence_based_filtering or clip_filtering or alia_conf_filtering) and decisions is None:
-        loader = filter_models or ds_utils.load_filter_models
-        classifier, clip, tokenizer = loader(ds_utils, device)
+        classifier, clip, tokenizer = (filter_models or load_filter_models)(ds_utils, device)
     prompt_ids = None
     if semantic_filtering and decisions is None:
         prompts = [ds_utils.get_basic_prompt()] + SEMANTIC_NEGATIVE_PROMPTS
@@ -192,11 +211,17 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     max_logit = np.zeros(len(pairs), np.float32)
     argmax = np.zeros(len(pairs), np.int32)
     class_conf = np.ones(len(pairs), np.float32)
+    unscored = np.zeros(len(pairs), bool)
     if decisions is not None:
-        for k, (_, path, _) in enumerate(pairs):
-            if path not in decisions:
-                raise KeyError(f"no gathered filter record for {path}")
-            in_topk[k], sem[k] = decisions[path]
+        miss = [(name, path) for name, path, _ in pairs if (name, path) not in decisions]
+        more = missing_decisions(miss) if (miss and missing_decisions is not None) else {}
+        for k, (name, path, _) in enumerate(pairs):
+            d = decisions.get((name, path), more.get((name, path)))
+            if d is None:  # a file nobody scored (left by an earlier run) and no way to score it here: logged and left out, not fatal
+                logging.info(f"no filter record for {path} (source {name}); left out of the JSON")
+                unscored[k] = True
+                continue
+            in_topk[k], sem[k] = d
     elif (semantic_filtering or model_confidence_based_filtering or extra) and pairs:
         dev = torch.device(device)
         for idx, imgs in _load_batches([p[1] for p in pairs], batch_size):
@@ -217,6 +242,8 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     result: Dict[str, List[str]] = {Path(p).name: [] for p in original_images_paths_list}
     n_topk = n_sem = n_high = n_clip = n_alia_ok = n_alia_wrong = 0
     for k, (name, path, label) in enumerate(pairs):
+        if unscored[k]:
+            continue
         if model_confidence_based_filtering:
             if not in_topk[k]:
                 n_topk += 1

@@ -62,9 +62,9 @@ def test_driver_filter_json_roundtrip(cuda_device, tmp_path):
     for index, i, p in w2:
         ref = [q for a, b, q in written if (a, b) == (index, i)][0]
         a, b = np.asarray(Image.open(p)).astype(int), np.asarray(Image.open(ref)).astype(int)
-        # same seeds/prompts/noise; a different micro-batch composition only changes tile mapping and the order of the
-        # GroupNorm atomics (fp32 rounding), which a random-init recurrent net amplifies to a few grey levels
-        assert np.abs(a - b).mean() < 1.0 and np.abs(a - b).max() <= 16, (index, i, np.abs(a - b).mean(), np.abs(a - b).max())
+        # same seeds/prompts/noise => bit-identical pixels: every kernel's per-item arithmetic is independent of what else shares the
+        # micro-batch (tile shapes follow per-image geometry, reductions run in a fixed order), SURVEY.md 8e "results independent of W"
+        assert np.array_equal(a, b), (index, i, np.abs(a - b).mean(), np.abs(a - b).max())
 
 
 @pytest.mark.parametrize("base_model", ["tiny_xl", "tiny_blip"])
@@ -96,7 +96,7 @@ def test_driver_other_base_models(cuda_device, tmp_path, base_model):
                                     cfg.NUM_INFERENCE_STEPS, g, cfg.GUIDANCE_SCALE, cfg.CONTROLNET_CONDITIONING_SCALE, control_image=canny,
                                     blip_src_category=ds.meta_class, blip_target_category=ds.meta_class)
     a, b = np.asarray(one).astype(int), np.asarray(Image.open(path)).astype(int)
-    assert np.abs(a - b).mean() < 1.0 and np.abs(a - b).max() <= 16, (np.abs(a - b).mean(), np.abs(a - b).max())
+    assert np.array_equal(a, b), (np.abs(a - b).mean(), np.abs(a - b).max())  # batch-1 call == the item inside a micro-batch of 4
 
 
 def test_reference_order_rng_matches_sequentially_threaded_generator(cuda_device, tmp_path):
@@ -125,7 +125,7 @@ def test_reference_order_rng_matches_sequentially_threaded_generator(cuda_device
     assert set(got) == set(want)
     for k in want:
         d = np.abs(got[k] - want[k])
-        assert d.mean() < 1.0 and d.max() <= 16, (k, d.mean(), d.max())
+        assert d.max() == 0, (k, d.mean(), d.max())
     # and it differs from the per-item mode (different noise)
     cfg2 = run_aug.AugConfig(BASE_MODEL="tiny", RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4)
     other = run_aug.generate(cfg2, ds, pipe, prompts, str(tmp_path / "per_item" / "images"))

@@ -45,6 +45,12 @@ def test_file_and_folder_naming():
     cfg = run_aug.AugConfig(USE_ARTISTIC_PROMPTS=True, PROMPT_WITH_SUB_CLASS=True)
     assert run_aug.output_folder("/data/planes", cfg) == \
         "/data/planes/aug_data/controlnet/sd_v1.5/canny/gpt-meta_class_prompt_w_sub_class_artistic_prompts_p_0.5_seed_1/images"
+    blip = run_aug.AugConfig(BASE_MODEL="blip_diffusion", USE_CAMERA_VARIATIONS_PROMPTS=True, PROMPT_WITH_SUB_CLASS=False)
+    assert run_aug.output_folder("/d", blip) == \
+        "/d/aug_data/controlnet/blip_diffusion/canny/gpt-meta_class_camera_variations_p_0.5_style_img_from_diff_img_seed_1/images"
+    cub = run_aug.AugConfig(DATASET="cub").apply_dataset_rules()  # run_aug.py:564-571
+    assert (cub.BASE_MODEL, cub.GUIDANCE_SCALE, cub.NUM_INFERENCE_STEPS, cub.NEGATIVE_PROMPT) == ("sd_xl-turbo", 0.0, 2, None)
+    assert run_aug.AugConfig(DATASET="compcars-parts").apply_dataset_rules().NUM_INFERENCE_STEPS == 50  # "cars" in DATASET.lower()
     cfg2 = run_aug.AugConfig(SDEDIT=1, SDEDIT_STRENGTH=0.5, CONTROLNET=None)
     assert "/aug_data/regular/sd_v1.5-SDEdit_strength_0.5/None/" in run_aug.output_folder("/d", cfg2)
     assert run_aug.aug_file_name("x" * 60, "a/b photo", 1) == "x" * 40 + "_prompt_a-b photo_1.png"
@@ -65,12 +71,21 @@ def test_resize_image_and_hwc3_match_reference_semantics():
 
 
 def test_prompt_sampling_is_partition_independent():
-    cfg = run_aug.AugConfig(USE_ARTISTIC_PROMPTS=True)
+    from saspa_aug_b200.datasets import SyntheticUtils
+
+    cfg = run_aug.AugConfig()  # reference defaults: artistic suffix on even i (sd_v1.5), sub-class inserted before the meta class
+    assert cfg.USE_ARTISTIC_PROMPTS and cfg.PROMPT_WITH_SUB_CLASS
+    ds = SyntheticUtils(root="/nonexistent", n_images=12)
     prompts = [f"an airplane number {i}." for i in range(50)]
-    a = run_aug.sample_prompts(prompts, 12, cfg)
-    b = run_aug.sample_prompts(prompts, 12, cfg)
+    a = run_aug.sample_prompts(prompts, ds.original_images_paths, cfg, ds)
+    b = run_aug.sample_prompts(prompts, ds.original_images_paths, cfg, ds)
     assert a == b and len(a) == 12 and all(len(x) == 2 for x in a)
-    assert all(not p.endswith(".") for x in a for p in x) and all("," in x[0] and "," not in x[1] for x in a)
+    assert all(not p.endswith(".") for x in a for p in x) and all(", a painting of" in x[0] and "," not in x[1] for x in a)
+    assert all(f"an class_{k % 100} airplane number" in p for k, x in enumerate(a) for p in x)
+    plain = run_aug.sample_prompts(prompts, 12, run_aug.AugConfig(PROMPT_WITH_SUB_CLASS=False))  # anonymous sources: only without per-source rewriting
+    assert [[p.replace(f"class_{k % 100} ", "") for p in x] for k, x in enumerate(a)] == plain
+    with pytest.raises(ValueError):
+        run_aug.sample_prompts(prompts, 12, cfg)
     parts = [run_aug.shard_indices(12, r, 4) for r in range(4)]
     assert sorted(i for p in parts for i in p) == list(range(12)) and parts[1] == [1, 5, 9]
     assert run_aug.item_seed(1, 5, 0) != run_aug.item_seed(1, 5, 1)
@@ -125,22 +140,36 @@ def test_json_writer_from_gathered_decisions(tmp_path):
         for i in range(3):
             path = os.path.join(out_dir, run_aug.aug_file_name(stem, f"an airplane, take {i}", i))
             Image.new("RGB", (8, 8), (index * 40, i * 60, 0)).save(path)
-            decisions[path] = ((index + i) % 2, int(i != 1))
+            decisions[(os.path.basename(p), path)] = ((index + i) % 2, int(i != 1))
     for f in os.listdir(out_dir):  # listdir order is the value order
-        if "_source." in f:
+        if "_source." in f or "_control." in f:
             continue
-        a, b = decisions[os.path.join(out_dir, f)]
+        name = [k for k in expect if os.path.splitext(k)[0] in f][0]
+        a, b = decisions[(name, os.path.join(out_dir, f))]
         if a and b:
-            expect[[k for k in expect if os.path.splitext(k)[0] in f][0]].append(os.path.join(out_dir, f))
+            expect[name].append(os.path.join(out_dir, f))
     jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
                                                                        init_log=False, ds_utils=ds, decisions=decisions)
     assert os.path.basename(jp) == "semantic_filtering-model_confidence_based_filtering_top_10_classes-aug.json"
     got = json.load(open(jp))
     assert list(got) == [os.path.basename(p) for p in ds.original_images_paths] and got == expect
-    missing = dict(list(decisions.items())[1:])
-    with pytest.raises(KeyError):
-        filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
-                                                                   init_log=False, ds_utils=ds, decisions=missing)
+    # a matched pair nobody scored (a file left by an earlier run, a substring cross-match): handed to `missing_decisions`; without
+    # one it is logged and left out -- never a KeyError that would abort the JSON on rank 0
+    dropped = [k for k, v in decisions.items() if v == (1, 1)][0]
+    missing = {k: v for k, v in decisions.items() if k != dropped}
+    asked = []
+
+    def score(pairs):
+        asked.extend(pairs)
+        return {pr: (1, 1) for pr in pairs}
+
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
+                                                                       init_log=False, ds_utils=ds, decisions=missing, missing_decisions=score)
+    assert asked == [dropped] and json.load(open(jp)) == expect
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
+                                                                       init_log=False, ds_utils=ds, decisions=missing)
+    got = json.load(open(jp))
+    assert dropped[1] not in got[dropped[0]] and sum(len(v) for v in got.values()) == sum(len(v) for v in expect.values()) - 1
 
 
 def test_reference_order_noise_replays_the_global_generator():
@@ -150,10 +179,10 @@ def test_reference_order_noise_replays_the_global_generator():
     import torch
 
     sizes = [(512, 512), (512, 704), (576, 512), (512, 512), (512, 512)]
-    sampled = [["a", "b"]] * len(sizes)
     for sdedit in (0, 1):
         cfg = run_aug.AugConfig(SEED=7, SDEDIT=sdedit)
         skipped = {(1, 1), (3, 0)}
+        draws = [[run_aug.PromptDraw(p, None, (k, i) in skipped) for i, p in enumerate("ab")] for k in range(len(sizes))]
         # literal sequential replay, the way run_aug.py + diffusers consume the global generator
         g = torch.manual_seed(cfg.SEED)
         want = {}
@@ -167,7 +196,7 @@ def test_reference_order_noise_replays_the_global_generator():
         got = {}
         for rank in range(3):
             mine = set(run_aug.shard_indices(len(sizes), rank, 3))
-            part = run_aug.reference_order_noise(cfg, sizes, sampled, lambda a, b: (a, b) in skipped, mine)
+            part = run_aug.reference_order_noise(cfg, sizes, draws, mine)
             assert all(k[0] in mine for k in part) and not (set(part) & set(got))
             got.update(part)
         assert set(got) == set(want)
@@ -247,7 +276,7 @@ prompts = [f"an airplane, variation {i}." for i in range(10)]
 
 def fake_generate(cfg, ds_utils, pipe, prompts, out_dir, rank=0, world=1):  # stands in for the GPU generation stage: same names, same shard
     os.makedirs(out_dir, exist_ok=True)
-    sampled = run_aug.sample_prompts(prompts, len(ds_utils.original_images_paths), cfg)
+    sampled = run_aug.sample_prompts(prompts, ds_utils.original_images_paths, cfg, ds_utils)
     written = []
     for index in run_aug.shard_indices(len(ds_utils.original_images_paths), rank, world):
         stem = os.path.splitext(os.path.basename(ds_utils.original_images_paths[index]))[0]
@@ -270,7 +299,7 @@ assert stats["generated"] == 2 * len(run_aug.shard_indices(7, rank, world))
 if rank == 0:
     d = json.load(open(json_path))
     assert list(d) == [os.path.basename(p) for p in ds.original_images_paths]
-    sampled = run_aug.sample_prompts(prompts, 7, cfg)
+    sampled = run_aug.sample_prompts(prompts, ds.original_images_paths, cfg, ds)
     kept = 0
     for index, p in enumerate(ds.original_images_paths):
         stem = os.path.splitext(os.path.basename(p))[0]
