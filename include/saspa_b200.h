@@ -81,12 +81,16 @@ int saspa_crop_normalize_bf16(const uint8_t* img, int n, int h, int w, int crop_
  * (all_utils/utils.py:361, :152-164).
  *
  * Epilogue (applied in this order, per output element (row r, col j)):
+ *     folded LayerNorm (ln_stats): acc = rstd_r * (acc - mean_r * ln_colsum[j]) -- A holds the UN-normalised rows, B = W * gamma,
+ *                      bias = b + W . beta; (mean_r, rstd_r) come from the partial row sums a producer GEMM wrote (row_stats_out)
  *     v = acc + bias[j] + row_bias[r / rows_per_group, j]
  *     v = act(v)                       (SASPA_ACT_*; skipped here when act_after_residual)
  *     GEGLU: out col j pairs value col j with gate col j + BN/2 of the same tile: v = val * gelu(gate)
  *     v = alpha * v + beta * residual[r, j]
  *     v = act(v)                       (only when act_after_residual)
  *     out[r, j] = (bf16 | fp32) v
+ *     row_stats_out[r, 2 * n_tile + g] = (sum_j out[r, j], sum_j out[r, j]^2) over the columns epilogue group g of N tile n_tile
+ *                      stored, taken on the bf16-ROUNDED values (what the next GEMM reads)
  * ------------------------------------------------------------------------------------------ */
 enum { SASPA_ACT_NONE = 0, SASPA_ACT_SILU = 1, SASPA_ACT_GELU = 2, SASPA_ACT_RELU = 3, SASPA_ACT_QUICKGELU = 4, SASPA_ACT_GEGLU = 5 };
 
@@ -103,6 +107,15 @@ typedef struct saspa_epilogue {
   float beta;              /* scale on the residual */
   int out_fp32;            /* 0: bf16 output, 1: fp32 output */
   int act_after_residual;  /* 0: act before the residual add (diffusers blocks); 1: after it (ResNet bottleneck ReLU) */
+  /* LayerNorm folded into the GEMMs around it (diffusers BasicTransformerBlock norm1/2/3 -> to_q|k|v / to_q / ff.net.0.proj,
+   * models/attention.py): the producer of the residual stream emits per-row partial sums, the consumer applies the statistics
+   * to its accumulator -- the normalised tensor never exists in HBM.  GEMM entry point only. */
+  void* row_stats_out;     /* float2 [M, row_stats_slots] or NULL */
+  int row_stats_slots;     /* = saspa_gemm_row_stats_slots(N) */
+  const void* ln_stats;    /* float2 [M, ln_slots] (a producer's row_stats_out for this GEMM's A rows) or NULL */
+  int ln_slots;
+  const float* ln_colsum;  /* fp32 [N]: sum_k B[j, k] of the bf16 weights */
+  float ln_eps;
 } saspa_epilogue;
 
 /* D[M,N] = epilogue(A[M,K] . B[N,K]^T).  A, B bf16 row-major (K contiguous); lda/ldb/ldd in elements,
@@ -110,6 +123,10 @@ typedef struct saspa_epilogue {
  * saspa_geglu_interleave_rows semantics and D is [M, N/2]. */
 int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
                     const saspa_epilogue* ep_host, cudaStream_t stream);
+
+/* Slots per row of the partial statistics a GEMM with N output columns writes to row_stats_out (a function of N only, so that a
+ * row's statistics do not depend on how many rows share the launch). */
+int saspa_gemm_row_stats_slots(int N);
 
 /* Implicit-GEMM convolution, stride 1, "same" zero padding, ksize in {1,3}, NHWC:
  *   x0 [n,h,w,c0] (pixel stride ldx0) and optionally x1 [n,h,w,c1] (pixel stride ldx1) are read as the

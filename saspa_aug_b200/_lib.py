@@ -32,6 +32,12 @@ class Epilogue(Structure):
         ("beta", c_float),
         ("out_fp32", c_int),
         ("act_after_residual", c_int),
+        ("row_stats_out", c_void_p),
+        ("row_stats_slots", c_int),
+        ("ln_stats", c_void_p),
+        ("ln_slots", c_int),
+        ("ln_colsum", c_void_p),
+        ("ln_eps", c_float),
     ]
 
 
@@ -64,6 +70,7 @@ SIGNATURES = {
         [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, _P, c_int, _P],
     ),
     "saspa_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, POINTER(Epilogue), _P]),
+    "saspa_gemm_row_stats_slots": (c_int, [c_int]),
     "saspa_conv2d_igemm_bf16": (
         c_int,
         [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, POINTER(Epilogue), _P],

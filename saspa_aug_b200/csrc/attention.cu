@@ -483,10 +483,12 @@ int g_attention_impl = 0;  // 0 = auto (K/V-resident kernel for tkv <= 128, else
 
 int saspa_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq,
                        int tkv, int d, float scale, int causal, cudaStream_t stream);
+int saspa_xattention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch, int heads, int tq,
+                        int tkv, int d, float scale, cudaStream_t stream);
 
 extern "C" int saspa_attention_impl(int impl) {
   const int prev = g_attention_impl;
-  if (impl >= 0 && impl <= 2) g_attention_impl = impl;
+  if (impl >= 0 && impl <= 3) g_attention_impl = impl;
   return prev;
 }
 
@@ -501,8 +503,13 @@ extern "C" int saspa_attention_bf16(const void* q, int ldq, const void* k, int l
                       (reinterpret_cast<uintptr_t>(o) & 3) == 0,
                   "saspa_attention_bf16: q/k/v must be 16-byte aligned");
   SASPA_CHECK_ARG((long long)batch * heads <= 65535, "saspa_attention_bf16: batch*heads must be <= 65535");
-  // short key sequences (cross-attention over the text tokens): K/V-resident streaming kernel
-  if (g_attention_impl == 0 && !causal && scale > 0.0f && tkv <= 128 && tq >= 256 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+  // short key sequences (cross-attention over the text tokens): persistent tcgen05 kernel with K / V resident (xattention_tc.cu);
+  // impl 3 forces the older mma.sync K/V-resident kernel for A/B timing
+  if ((g_attention_impl == 0 || g_attention_impl == 2) && !causal && tkv <= 128 && tq >= 256) {
+    const int rc = saspa_xattention_tc(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
+    if (rc != SASPA_ERR_UNSUPPORTED) return rc;
+  }
+  if ((g_attention_impl == 0 || g_attention_impl == 3) && !causal && scale > 0.0f && tkv <= 128 && tq >= 256 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
     if (d <= 48) return launch_xattn<48>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 64) return launch_xattn<64>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);
     if (d <= 80) return launch_xattn<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, heads, tq, tkv, d, scale, stream);

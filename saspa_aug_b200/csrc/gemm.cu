@@ -79,6 +79,14 @@ struct GemmParams {
   int n_out;      // valid output columns (N, or N/2 for GEGLU)
   int vec_ok;     // 16-byte vector path allowed for residual loads / stores (direct path)
   int tma_store;  // bf16 output (and residual) move through smem staging panels + TMA
+  // LayerNorm folded into this GEMM (mode 0): acc = x . W'^T with W' = W * gamma; v = rstd_r * (acc - mean_r * colsum_j) + bias'_j
+  const float2* ln_stats;  // [M, ln_slots] partial (sum, sum of squares) of each A row, written by the producer's epilogue
+  int ln_slots;
+  const float* ln_colsum;  // [N] sum_k W'[j, k] (fp32 sum of the bf16 weights the MMA multiplies)
+  float ln_eps, ln_inv_k;
+  // per-row partial statistics of THIS GEMM's bf16 output (the next LayerNorm's input): slot = 2 * n_tile + epilogue group
+  float2* stats_out;
+  int stats_slots;
 };
 
 using namespace tcx;
@@ -91,12 +99,12 @@ struct Cfg {
   static constexpr int NBUF = (BN > 160 && CTAS == 1) ? 2 : 4;
   static constexpr int PD = NBUF / 2;
   static constexpr int STAGING_BYTES = 2 * NBUF * PANEL_BYTES;
-  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/ - 2048 /*bias*/;
+  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 512 /*barriers*/ - 4096 /*bias + LayerNorm column sums*/;
   static constexpr int RING_BYTES = RING_BUDGET / 1024 * 1024;
   static constexpr int STAGES = (RING_BYTES / STAGE_BYTES) > 8 ? 8 : (RING_BYTES / STAGE_BYTES);
   // halo mode (3x3 conv): 2 halo stages of the activation + a ring of weight k-blocks
   static constexpr int HB_STAGES = ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES) > 8 ? 8 : ((RING_BYTES - HALO_STAGES * HALO_STAGE_BYTES) / B_BYTES);
-  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512 + 2048;
+  static constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 + 512 + 4096;
   static_assert(STAGES >= 3 && HB_STAGES >= 4, "operand ring too shallow");
   static_assert(BN % PANEL == 0, "BN must be a multiple of the staging panel width");
   static_assert((BN / CTAS) % 8 == 0, "each CTA's B share must be whole 8-row core matrices");
@@ -110,6 +118,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case SASPA_ACT_QUICKGELU: return quick_gelu_f(v);
     default: return v;
   }
+}
+
+// (sum, sum of squares) of eight bf16 values exactly as they were stored
+__device__ __forceinline__ void row_stats_add(const uint4& u, float& s, float& q) {
+  const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
+  const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
+  s += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  q += ((a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3)) + ((a4 * a4 + a5 * a5) + (a6 * a6 + a7 * a7));
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
@@ -223,6 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* rfull = bars + 24;   // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
   float* sBias = reinterpret_cast<float*>(bars) + 128;  // [2][256]: the tile's bias slice, staged once per tile (512 B past the barriers)
+  float* sColsum = sBias + 512;                         // [2][256]: the tile's slice of the LayerNorm column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank = 0;
@@ -524,11 +541,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       // the bias slice of this tile goes through shared memory: its global-load latency is paid once per tile, off the
       // accumulator-drain path (it used to stall every panel).  Two buffers: nobody runs more than a tile ahead.
       float* sb = sBias + (it & 1) * 256;
-      if (p.bias) {
+      float* sc = sColsum + (it & 1) * 256;
+      if (p.bias || p.ln_colsum) {
         const int t = (int)threadIdx.x - 64;
-        if (t < BN) sb[t] = (col_base_in + t < p.N) ? __ldg(p.bias + col_base_in + t) : 0.0f;
+        if (t < BN) {
+          if (p.bias) sb[t] = (col_base_in + t < p.N) ? __ldg(p.bias + col_base_in + t) : 0.0f;
+          if (p.ln_colsum) sc[t] = (col_base_in + t < p.N) ? __ldg(p.ln_colsum + col_base_in + t) : 0.0f;
+        }
         asm volatile("bar.sync 3, 256;" ::: "memory");
       }
+      // folded LayerNorm: this row's mean / rstd from the producer's partials, summed in slot order (fixed => batch invariant);
+      // the loads are in flight while the accumulator is still being produced
+      float ln_mean = 0.0f, ln_rstd = 1.0f;
+      if (p.ln_stats && row_ok) {
+        const float2* sp = p.ln_stats + (size_t)pix * p.ln_slots;
+        float a = 0.0f, b = 0.0f;
+        for (int s2 = 0; s2 < p.ln_slots; ++s2) {
+          const float2 v2 = __ldg(sp + s2);
+          a += v2.x;
+          b += v2.y;
+        }
+        ln_mean = a * p.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(b * p.ln_inv_k - ln_mean * ln_mean, 0.0f) + p.ln_eps);
+      }
+      float st_sum = 0.0f, st_sq = 0.0f;  // row statistics of this tile's bf16 output (p.stats_out)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
@@ -545,6 +581,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.ln_stats) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cs = *reinterpret_cast<const float4*>(sc + c0 + j);
+            f[j] = ln_rstd * fmaf(-ln_mean, cs.x, f[j]); f[j + 1] = ln_rstd * fmaf(-ln_mean, cs.y, f[j + 1]);
+            f[j + 2] = ln_rstd * fmaf(-ln_mean, cs.z, f[j + 2]); f[j + 3] = ln_rstd * fmaf(-ln_mean, cs.w, f[j + 3]);
+          }
+          if (geglu) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 cs = *reinterpret_cast<const float4*>(sc + BN / 2 + c0 + j);
+              gt[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.x, __uint_as_float(gt[j])));
+              gt[j + 1] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.y, __uint_as_float(gt[j + 1])));
+              gt[j + 2] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.z, __uint_as_float(gt[j + 2])));
+              gt[j + 3] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.w, __uint_as_float(gt[j + 3])));
+            }
+          }
+        }
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -624,6 +678,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             u.z = pack_bf16(f[j + 4], f[j + 5]);
             u.w = pack_bf16(f[j + 6], f[j + 7]);
             *reinterpret_cast<uint4*>(pbuf + ((c ^ row_swz) << 4)) = u;
+            if (p.stats_out) row_stats_add(u, st_sum, st_sq);
           }
           fence_proxy_async_smem();
           // after this barrier every thread knows stores <= n_seq - NBUF + 1 have drained their panel
@@ -685,6 +740,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 u.z = pack_bf16(f[j + 4], f[j + 5]);
                 u.w = pack_bf16(f[j + 6], f[j + 7]);
                 *reinterpret_cast<uint4*>(op + j) = u;
+                if (p.stats_out) row_stats_add(u, st_sum, st_sq);
               }
             } else {
               for (int j = 0; j < 32; ++j)
@@ -693,6 +749,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         }  // row_ok
       }
+      if (p.stats_out && row_ok) p.stats_out[(size_t)pix * p.stats_slots + 2 * n_blk + grp] = make_float2(st_sum, st_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -823,9 +880,12 @@ int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 //    pads columns or leaves SMs idle in the last wave of a small-M problem;
 //  * short-K GEMMs are bound by the epilogue / stores, where padded columns cost real time: exact tilings first
 //    (SD channel counts are multiples of 320 -> 160; powers of two -> 256 / 128).
-int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound) {
+int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_n = false) {
   if (act == SASPA_ACT_GEGLU) return 256;  // value | gate halves in one tile
   if (g_force_bn) return g_force_bn;
+  // a GEMM that emits row statistics partitions each row's sums by N tile: the tile width must then be a function of N alone,
+  // or a row's LayerNorm statistics would depend on how many other rows share the launch
+  if (fixed_by_n) mainloop_bound = false;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   if (mainloop_bound) {
@@ -893,7 +953,7 @@ int dispatch(int bn, int ctas, const CUtensorMap& a0, const CUtensorMap& a1, con
 int g_conv_impl = 0;  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
 
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
-  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0};
+  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f};
   if (!ep) ep = &kDefault;
   p.bias = ep->bias;
   p.row_bias = ep->row_bias;
@@ -909,6 +969,17 @@ int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int l
   p.D = D;
   p.ldd = ldd;
   p.n_out = (ep->act == SASPA_ACT_GEGLU) ? N / 2 : N;
+  p.stats_out = static_cast<float2*>(ep->row_stats_out);
+  p.stats_slots = ep->row_stats_slots;
+  p.ln_stats = static_cast<const float2*>(ep->ln_stats);
+  p.ln_slots = ep->ln_slots;
+  p.ln_colsum = ep->ln_colsum;
+  p.ln_eps = ep->ln_eps;
+  SASPA_CHECK_ARG(!ep->row_stats_out || (!ep->out_fp32 && ep->act != SASPA_ACT_GEGLU && N % 32 == 0 && (reinterpret_cast<uintptr_t>(ep->row_stats_out) & 7) == 0),
+                  "epilogue: row_stats_out needs a bf16, non-GEGLU output with N %% 32 == 0 (N=%d)", N);
+  SASPA_CHECK_ARG(!ep->ln_stats || (ep->ln_colsum && ep->ln_slots > 0 && ep->ln_slots <= 64 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
+                                    (reinterpret_cast<uintptr_t>(ep->ln_stats) & 7) == 0),
+                  "epilogue: ln_stats needs ln_colsum (16-byte aligned) and 1 <= ln_slots <= 64 (got %d)", ep->ln_slots);
   SASPA_CHECK_ARG(ep->act >= SASPA_ACT_NONE && ep->act <= SASPA_ACT_GEGLU, "epilogue: unknown activation %d", ep->act);
   SASPA_CHECK_ARG(!(ep->act == SASPA_ACT_GEGLU && (N % 256 != 0)), "GEGLU epilogue needs N %% 256 == 0 (tile-interleaved weights), got %d", N);
   SASPA_CHECK_ARG(!(ep->act == SASPA_ACT_GEGLU && ep->row_bias), "GEGLU epilogue does not take a row_bias");
@@ -948,8 +1019,11 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   p.K = K;
   p.mode = 0;
   p.num_m_tiles = ceil_div(M, BM);
-  const int bn = pick_bn(N, p.act, p.num_m_tiles, K >= 2048);
+  const int bn = pick_bn(N, p.act, p.num_m_tiles, K >= 2048, p.stats_out != nullptr);
   p.num_n_tiles = ceil_div(N, bn);
+  p.ln_inv_k = 1.0f / (float)K;
+  SASPA_CHECK_ARG(!p.stats_out || p.stats_slots == 2 * p.num_n_tiles, "saspa_gemm_bf16: row_stats_slots must be saspa_gemm_row_stats_slots(N) = %d, got %d",
+                  2 * p.num_n_tiles, p.stats_slots);
   CUtensorMap tmA, tmB;
   if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
   const int ctas = pick_ctas(p.num_m_tiles, bn, 0, p.act, K);
@@ -960,6 +1034,13 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
     if (p.residual && (rc = encode_2d(&tmR, p.residual, M, p.n_out, p.ld_res, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   return dispatch(bn, ctas, tmA, tmA, tmB, tmD, tmR, p, stream);
+}
+
+// Slots per row of the partial row statistics a GEMM with N output columns writes (2 epilogue groups x N tiles; the tile width is
+// then a function of N alone, see pick_bn).
+extern "C" int saspa_gemm_row_stats_slots(int N) {
+  if (N <= 0) return 0;
+  return 2 * ceil_div(N, pick_bn(N, SASPA_ACT_NONE, 1, false, true));
 }
 
 extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0, const void* x1, int ldx1, int c1, int n, int ih, int iw,
@@ -984,6 +1065,7 @@ extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0,
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, cout, out, ldo);
   if (rc) return rc;
+  SASPA_CHECK_ARG(!p.stats_out && !p.ln_stats, "saspa_conv2d_igemm_bf16: row statistics / folded LayerNorm are GEMM-only epilogue options");
   // M tile = bw x bh x bnimg = 128 output pixels; minimise padded work, tie-break towards square tiles.
   int best_bw = 0, best_bh = 0, best_bi = 0;
   long long best_cost = -1;

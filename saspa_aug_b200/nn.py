@@ -18,6 +18,7 @@ B200-first choices (vs. the diffusers graph):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -133,20 +134,44 @@ class ResnetBlock:
         return self.conv2(a2, out=out, residual=res, beta=1.0)
 
 
+FOLD_LAYERNORM = os.environ.get("SASPA_FOLD_LN", "1") != "0"  # A/B switch for tools and tests; the product default is the folded path
+
+
 class TransformerBlock:
-    """diffusers BasicTransformerBlock (self-attn, cross-attn, GEGLU feed-forward; pre-LayerNorm)."""
+    """diffusers BasicTransformerBlock (self-attn, cross-attn, GEGLU feed-forward; pre-LayerNorm).
+
+    The three LayerNorms never run as kernels: each is folded into the GEMM that consumes it.  With W' = W * gamma (bf16),
+    LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (b + W beta): the GEMM multiplies the UN-normalised residual stream and its
+    epilogue applies the row statistics, which the GEMM that PRODUCED the stream (proj_in / to_out / ff.net.2, all with the residual
+    add in their epilogue) emitted as per-row partial sums of its bf16 output.  The normalised tensor never exists in HBM."""
 
     def __init__(self, sd: SD, p: str, dev, heads: int):
         self.heads = heads
+        self.fold = FOLD_LAYERNORM
         self.ln1, self.ln2, self.ln3 = Norm(sd, p + ".norm1", dev), Norm(sd, p + ".norm2", dev), Norm(sd, p + ".norm3", dev)
-        self.wqkv = _bf(torch.cat([sd[p + ".attn1.to_q.weight"], sd[p + ".attn1.to_k.weight"], sd[p + ".attn1.to_v.weight"]], 0), dev)
+        wqkv = torch.cat([sd[p + ".attn1.to_q.weight"], sd[p + ".attn1.to_k.weight"], sd[p + ".attn1.to_v.weight"]], 0)
         self.o1 = Linear(sd, p + ".attn1.to_out.0", dev)
-        self.q2 = Linear(sd, p + ".attn2.to_q", dev)
+        wq2 = sd[p + ".attn2.to_q.weight"]
         self.wkv2 = _bf(torch.cat([sd[p + ".attn2.to_k.weight"], sd[p + ".attn2.to_v.weight"]], 0), dev)
         self.o2 = Linear(sd, p + ".attn2.to_out.0", dev)
         wi, bi = geglu_interleave(sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"])
-        self.ff1 = Linear(sd, "", dev, weight=wi, bias=bi)
         self.ff2 = Linear(sd, p + ".ff.net.2", dev)
+        if self.fold:
+            self.qkv = self._folded(wqkv, None, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], dev)
+            self.q2 = self._folded(wq2, sd.get(p + ".attn2.to_q.bias"), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], dev)
+            self.ff1 = self._folded(wi, bi, sd[p + ".norm3.weight"], sd[p + ".norm3.bias"], dev)
+        else:
+            self.wqkv = _bf(wqkv, dev)
+            self.q2 = Linear(sd, p + ".attn2.to_q", dev)
+            self.ff1 = Linear(sd, "", dev, weight=wi, bias=bi)
+
+    @staticmethod
+    def _folded(w, b, gamma, beta, dev):
+        """(W' = bf16(W * gamma), fp32 colsum of W' as the MMA sees it, fp32 bias b + W beta)."""
+        w32, g32, be32 = w.detach().float(), gamma.detach().float(), beta.detach().float()
+        wp = _bf(w32 * g32[None, :], dev)
+        bias = w32 @ be32 + (b.detach().float() if b is not None else 0.0)
+        return wp, wp.float().sum(dim=1).contiguous(), _f32(bias, dev)
 
     def text_kv(self, text2d: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Step-invariant K/V projections of the text states [n*77, cross] -> two [n,77,c] views."""
@@ -156,21 +181,39 @@ class TransformerBlock:
         kv3 = kv.view(n, t, 2 * c)
         return kv3[..., :c], kv3[..., c:]
 
-    def __call__(self, h: torch.Tensor, n: int, kv: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
+    def __call__(self, h: torch.Tensor, n: int, kv: Tuple[torch.Tensor, torch.Tensor], stats: Optional[torch.Tensor] = None, want_stats: bool = False):
+        """h [rows, c] is updated in place.  Folded path: ``stats`` = row statistics of h from its producer; returns (h, stats of the
+        new h when ``want_stats``)."""
         rows, c = h.shape
         t = rows // n
-        y = ops.layernorm(h, 1e-5, self.ln1.g, self.ln1.b)
-        qkv = ops.gemm(y, self.wqkv).view(n, t, 3 * c)
+        if not self.fold:
+            y = ops.layernorm(h, 1e-5, self.ln1.g, self.ln1.b)
+            qkv = ops.gemm(y, self.wqkv).view(n, t, 3 * c)
+            a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads)
+            self.o1(a.view(rows, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, 1e-5, self.ln2.g, self.ln2.b)
+            q = self.q2(y).view(n, t, c)
+            a = ops.attention(q, kv[0], kv[1], self.heads)
+            self.o2(a.view(rows, c), out=h, residual=h, beta=1.0)
+            y = ops.layernorm(h, 1e-5, self.ln3.g, self.ln3.b)
+            f = self.ff1(y, act=ACT_GEGLU)
+            self.ff2(f, out=h, residual=h, beta=1.0)
+            return h, None
+        w, cs, b = self.qkv
+        qkv = ops.gemm(h, w, bias=b, ln_stats=stats, ln_colsum=cs, ln_eps=1e-5).view(n, t, 3 * c)
         a = ops.attention(qkv[..., :c], qkv[..., c : 2 * c], qkv[..., 2 * c :], self.heads)
-        self.o1(a.view(rows, c), out=h, residual=h, beta=1.0)
-        y = ops.layernorm(h, 1e-5, self.ln2.g, self.ln2.b)
-        q = self.q2(y).view(n, t, c)
+        _, st = self.o1(a.view(rows, c), out=h, residual=h, beta=1.0, row_stats=True)
+        w, cs, b = self.q2
+        q = ops.gemm(h, w, bias=b, ln_stats=st, ln_colsum=cs, ln_eps=1e-5).view(n, t, c)
         a = ops.attention(q, kv[0], kv[1], self.heads)
-        self.o2(a.view(rows, c), out=h, residual=h, beta=1.0)
-        y = ops.layernorm(h, 1e-5, self.ln3.g, self.ln3.b)
-        f = self.ff1(y, act=ACT_GEGLU)
+        _, st = self.o2(a.view(rows, c), out=h, residual=h, beta=1.0, row_stats=True)
+        w, cs, b = self.ff1
+        f = ops.gemm(h, w, bias=b, act=ACT_GEGLU, ln_stats=st, ln_colsum=cs, ln_eps=1e-5)
+        if want_stats:
+            _, st = self.ff2(f, out=h, residual=h, beta=1.0, row_stats=True)
+            return h, st
         self.ff2(f, out=h, residual=h, beta=1.0)
-        return h
+        return h, None
 
 
 class Transformer2D:
@@ -190,9 +233,10 @@ class Transformer2D:
     def __call__(self, x: torch.Tensor, kvs, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, hh, ww, c = x.shape
         g = ops.groupnorm(pix3d(x), self.groups, 1e-6, self.norm.g, self.norm.b, ACT_NONE)
-        h = self.proj_in(g.view(n * hh * ww, c))
-        for blk, kv in zip(self.blocks, kvs):
-            h = blk(h, n, kv)
+        fold = bool(self.blocks) and self.blocks[0].fold
+        h, st = self.proj_in(g.view(n * hh * ww, c), row_stats=True) if fold else (self.proj_in(g.view(n * hh * ww, c)), None)
+        for bi, (blk, kv) in enumerate(zip(self.blocks, kvs)):
+            h, st = blk(h, n, kv, st, want_stats=bi + 1 < len(self.blocks))
         if out is None:
             out = torch.empty((n, hh, ww, c), dtype=BF16, device=x.device)
         self.proj_out(h, out=pix2d(out), residual=pix2d(x), beta=1.0)

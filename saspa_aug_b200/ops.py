@@ -82,8 +82,14 @@ def canny(img: torch.Tensor, low: int, high: int, out_channels: int = 1, want_ct
 # GEMM / conv
 # ------------------------------------------------------------------------------------------------
 def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alpha=1.0, residual=None, ld_res=0, beta=1.0, out_fp32=False,
-                  act_after_residual=False):
+                  act_after_residual=False, row_stats_out=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5):
     ep = Epilogue()
+    ep.row_stats_out = _ptr(row_stats_out)
+    ep.row_stats_slots = int(row_stats_out.shape[1]) if row_stats_out is not None else 0
+    ep.ln_stats = _ptr(ln_stats)
+    ep.ln_slots = int(ln_stats.shape[1]) if ln_stats is not None else 0
+    ep.ln_colsum = _ptr(ln_colsum)
+    ep.ln_eps = float(ln_eps)
     ep.bias = _ptr(bias)
     ep.row_bias = _ptr(row_bias)
     ep.rows_per_group = int(rows_per_group)
@@ -98,9 +104,18 @@ def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alph
     return ep
 
 
+def row_stats_slots(n: int) -> int:
+    """Partial-statistics slots per row a GEMM with ``n`` output columns writes (see ``gemm(row_stats=...)``)."""
+    return int(_lib.load().saspa_gemm_row_stats_slots(int(n)))
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, row_bias=None, rows_per_group=1,
-         act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False) -> torch.Tensor:
-    """out[M,N'] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 2-D views with unit inner stride."""
+         act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False, row_stats: bool = False,
+         ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5):
+    """out[M,N'] = epilogue(a[M,K] @ b[N,K]^T); a, b bf16 2-D views with unit inner stride.
+    row_stats=True additionally returns fp32 [M, slots, 2] partial (sum, sum of squares) of every OUTPUT row -> (out, stats);
+    ln_stats (such a tensor for the rows of ``a``) + ln_colsum fold a LayerNorm of ``a`` into this GEMM (b = W * gamma,
+    bias = b + W . beta, ln_colsum = b.float().sum(1))."""
     _need_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.dim() == 2 and b.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1
@@ -113,8 +128,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     assert out.stride(1) == 1 and out.shape == (M, n_out)
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(1) == 1 and residual.shape == (M, n_out)
+    stats = torch.empty((M, row_stats_slots(n_out), 2), dtype=torch.float32, device=a.device) if row_stats else None
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape[0] == M and ln_stats.shape[2] == 2
+        assert ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
     ep = make_epilogue(bias, row_bias, rows_per_group, act, alpha, residual, residual.stride(0) if residual is not None else 0, beta,
-                       out.dtype == torch.float32, act_after_residual)
+                       out.dtype == torch.float32, act_after_residual, stats, ln_stats, ln_colsum, ln_eps)
     ev = _prof_begin()
     check(
         _lib.load().saspa_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, ctypes.byref(ep), _stream()),
@@ -122,7 +141,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     )
     _prof_end(ev, "gemm", 2.0 * M * N * K, (M, N, K, int(act), residual is not None))
     _count()
-    return out
+    return (out, stats) if row_stats else out
 
 
 def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optional[torch.Tensor] = None, *, x1: Optional[torch.Tensor] = None,

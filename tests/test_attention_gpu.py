@@ -23,10 +23,10 @@ def _ref(q, k, v, heads, scale=None, causal=False):
     return (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(b, tq, hd)
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["auto", "mma_sync", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "mma_sync", "tcgen05", "resident_mma_sync"])
 def impl(request):
-    """Runs a test once per attention kernel (saspa_attention_impl: 0 = auto, incl. the K/V-resident cross-attention kernel
-    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM)."""
+    """Runs a test once per attention kernel (saspa_attention_impl: 0 = auto, incl. the persistent tcgen05 cross-attention kernel
+    for tkv <= 128; 1 = mma.sync flash; 2 = tcgen05/TMEM only; 3 = the older mma.sync K/V-resident cross-attention kernel)."""
     from saspa_aug_b200 import _lib
 
     prev = _lib.load().saspa_attention_impl(request.param)
@@ -37,7 +37,10 @@ def impl(request):
 @pytest.mark.parametrize("cfg", [  # b, heads, tq, tkv, d
     (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (4, 8, 256, 256, 160), (4, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80),
     (3, 8, 256, 77, 160), (2, 8, 64, 77, 160), (2, 12, 77, 77, 64), (1, 8, 5632, 5632, 40), (2, 5, 100, 131, 64), (2, 16, 257, 257, 64),
-    (7, 8, 50, 50, 64), (2, 4, 200, 200, 128), (1, 8, 1000, 77, 40), (2, 5, 300, 128, 64), (1, 8, 5632, 77, 40), (2, 8, 320, 1, 80)])
+    (7, 8, 50, 50, 64), (2, 4, 200, 200, 128), (1, 8, 1000, 77, 40), (2, 5, 300, 128, 64), (1, 8, 5632, 77, 40), (2, 8, 320, 1, 80),
+    # cross-attention, persistent kernel: many head switches per CTA, SDXL head dims, 81..128 keys, one-deep K/V ring (d 128, 128 keys)
+    (40, 8, 256, 77, 40), (4, 20, 1024, 77, 64), (3, 10, 4096, 77, 64), (2, 8, 256, 77, 128), (9, 8, 384, 100, 80), (5, 4, 640, 128, 128),
+    (64, 8, 4096, 77, 40)])
 def test_attention(cuda_device, cfg, impl):
     b, heads, tq, tkv, d = cfg
     q, k, v = _rand((b, tq, heads * d), 1), _rand((b, tkv, heads * d), 2), _rand((b, tkv, heads * d), 3)

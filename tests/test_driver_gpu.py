@@ -90,7 +90,7 @@ def test_driver_other_base_models(cuda_device, tmp_path, base_model):
     index, i, path = written[0]
     src = Image.open(ds.original_images_paths[index]).convert("RGB")
     canny = run_aug.generate_canny(src, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, cfg.RESOLUTION)
-    prompt = run_aug.sample_prompts(prompts, len(ds.original_images_paths), cfg)[index][i]
+    prompt = run_aug.sample_prompts(prompts, ds.original_images_paths, cfg, ds)[index][i]
     g = torch.Generator().manual_seed(run_aug.item_seed(cfg.SEED, index, i))
     one = run_aug.pass_thorugh_pipe("blip_diffusion" if "blip" in base_model else "sd_xl-turbo", pipe, prompt, src, 0, cfg.SDEDIT_STRENGTH,
                                     cfg.NUM_INFERENCE_STEPS, g, cfg.GUIDANCE_SCALE, cfg.CONTROLNET_CONDITIONING_SCALE, control_image=canny,
@@ -109,7 +109,7 @@ def test_reference_order_rng_matches_sequentially_threaded_generator(cuda_device
     cfg = run_aug.AugConfig(BASE_MODEL="tiny", RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4, RNG_MODE="reference_order")
     pipe = run_aug.init_pipeline("tiny", "canny", 0, sampler="ddim").to("cuda", torch.float16)
     prompts = [f"an airplane above the clouds {i}." for i in range(8)]
-    sampled = run_aug.sample_prompts(prompts, 4, cfg)
+    sampled = run_aug.sample_prompts(prompts, ds.original_images_paths, cfg, ds)
     g = torch.manual_seed(cfg.SEED)  # the reference's generator is the global CPU generator
     want = {}
     for index, p in enumerate(ds.original_images_paths):
@@ -131,3 +131,61 @@ def test_reference_order_rng_matches_sequentially_threaded_generator(cuda_device
     other = run_aug.generate(cfg2, ds, pipe, prompts, str(tmp_path / "per_item" / "images"))
     a = np.asarray(Image.open(other[0][2])).astype(int)
     assert np.abs(a - want[(other[0][0], other[0][1])]).mean() > 2.0
+
+
+_RANK_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, sys.argv[1])
+root = sys.argv[2]
+import torch
+from saspa_aug_b200 import run_aug
+from saspa_aug_b200.datasets import SyntheticUtils
+
+sizes = [(128, 128), (96, 128), (128, 96), (128, 128)]  # mixed aspect ratios: 128x128, 128x192 and 192x128 after resize_image(., 128)
+ds = SyntheticUtils(root=root, n_images=10, sizes=sizes, n_classes=12, clip_seed=813)
+if int(os.environ.get("RANK", "0")) == 0:
+    ds.materialize()
+cfg = run_aug.AugConfig(BASE_MODEL="tiny", RESOLUTION=128, NUM_INFERENCE_STEPS=3, MICRO_BATCH=4)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    dist.barrier()
+prompts = [f"an airplane over terrain {i}." for i in range(12)]
+json_path, stats = run_aug.run_sharded(cfg, ds, prompts, root, device="cuda:0")
+print("STATS", json.dumps(stats))
+if json_path:
+    print("JSON", json_path)
+'''
+
+
+def test_one_rank_and_two_rank_runs_write_the_same_json_and_pixels(cuda_device, tmp_path):
+    """SURVEY.md 8e: results are independent of the world size.  The same job (10 mixed-aspect sources x 2, generate -> verify -> filter ->
+    gather -> rank-0 JSON) runs once as a single process and once as two ranks (one process per rank, gloo for the one collective so
+    both can share this GPU; NCCL needs a device per rank): every PNG is byte-identical and the aug JSON equal up to the root folder."""
+    import json
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    w = tmp_path / "worker.py"
+    w.write_text(_RANK_WORKER)
+    env = dict(os.environ, SASPA_DIST_BACKEND="gloo")
+    r1 = subprocess.run([sys.executable, str(w), repo, str(tmp_path / "one")], capture_output=True, text=True, timeout=600, env=env)
+    assert r1.returncode == 0, r1.stdout[-3000:] + r1.stderr[-3000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29621",
+                         str(w), repo, str(tmp_path / "two")], capture_output=True, text=True, timeout=900, env=env)
+    assert r2.returncode == 0, r2.stdout[-3000:] + r2.stderr[-3000:]
+    j1 = [ln.split(" ", 1)[1] for ln in r1.stdout.splitlines() if ln.startswith("JSON ")]
+    j2 = [ln.split(" ", 1)[1] for ln in r2.stdout.splitlines() if ln.startswith("JSON ")]
+    assert len(j1) == 1 and len(j2) == 1  # rank 0 only
+    d1 = json.loads(open(j1[0]).read().replace(str(tmp_path / "one"), "{ROOT}"))
+    d2 = json.loads(open(j2[0]).read().replace(str(tmp_path / "two"), "{ROOT}"))
+    assert list(d1) == list(d2) and len(d1) == 10
+    assert {k: sorted(v) for k, v in d1.items()} == {k: sorted(v) for k, v in d2.items()}  # value order = os.listdir order of each folder
+    kept = sum(len(v) for v in d1.values())
+    print(f"kept {kept} of 20; stats one-rank: {[ln for ln in r1.stdout.splitlines() if ln.startswith('STATS')]}")
+    f1, f2 = os.path.dirname(j1[0]) + "/images", os.path.dirname(j2[0]) + "/images"
+    names = sorted(os.listdir(f1))
+    assert names == sorted(os.listdir(f2)) and sum("_prompt_" in n for n in names) == 20
+    for n in names:
+        assert open(os.path.join(f1, n), "rb").read() == open(os.path.join(f2, n), "rb").read(), n

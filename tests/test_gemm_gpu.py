@@ -217,3 +217,46 @@ def test_empty_inputs_and_argument_errors(cuda_device):
     assert isinstance(SaspaError("x"), RuntimeError)
     with pytest.raises((SaspaError, AssertionError)):
         ops.gemm(torch.zeros((8, 64), dtype=torch.bfloat16), torch.zeros((8, 64), dtype=torch.bfloat16))  # CPU tensors: no CPU fallback
+
+
+@pytest.mark.parametrize("M,C,N,act", [(300, 320, 960, 0), (4096 + 77, 640, 640, 0), (1000, 1280, 2560, 5), (257, 320, 2560, 5), (129, 1280, 3840, 0)])
+def test_layernorm_folded_into_gemm(cuda_device, M, C, N, act):
+    """LN(x) W^T + b computed as rstd * (x W'^T - mean * colsum(W')) + (b + W beta) in the consumer's epilogue, with the row
+    statistics emitted by the PRODUCER GEMM's epilogue (diffusers BasicTransformerBlock norm -> projection, models/attention.py).
+    Reference: torch fp32 LayerNorm + matmul on the same bf16 inputs."""
+    import torch.nn.functional as F
+
+    from saspa_aug_b200.layout import geglu_interleave
+    from saspa_aug_b200.ops import ACT_GEGLU
+
+    g = torch.Generator().manual_seed(M + N)
+    # producer: h = a @ wp^T + residual, bf16, with row statistics of the stored values
+    a = torch.randn((M, 256), generator=g).to(torch.bfloat16).cuda()
+    wp = (torch.randn((C, 256), generator=g) / 16).to(torch.bfloat16).cuda()
+    res = (torch.randn((M, C), generator=g) * 2 + 0.7).to(torch.bfloat16).cuda()  # non-zero mean: exercises the mean * colsum term
+    h, st = ops.gemm(a, wp, residual=res, beta=1.0, row_stats=True)
+    assert st.shape == (M, ops.row_stats_slots(C), 2) and st.dtype == torch.float32
+    hf = h.float()
+    assert torch.allclose(st[..., 0].sum(1), hf.sum(1), rtol=1e-5, atol=1e-3) and torch.allclose(st[..., 1].sum(1), (hf * hf).sum(1), rtol=1e-5, atol=1e-2)
+    # a row's statistics do not depend on how many rows share the launch
+    h2, st2 = ops.gemm(a[:130], wp, residual=res[:130], beta=1.0, row_stats=True)
+    assert torch.equal(h2, h[:130]) and torch.equal(st2, st[:130])
+    # consumer
+    gamma = 1.0 + 0.2 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    w = torch.randn((N, C), generator=g) / C ** 0.5
+    b = 0.1 * torch.randn(N, generator=g)
+    want = F.linear(F.layer_norm(hf.cpu(), (C,), gamma, beta, 1e-5), w, b)
+    if act == ACT_GEGLU:
+        val, gate = want.chunk(2, dim=-1)
+        want = val * F.gelu(gate)
+        w, b = geglu_interleave(w, b)
+    wf = (w * gamma[None, :]).to(torch.bfloat16).cuda()
+    bias = (w @ beta + b).float().cuda()
+    got = ops.gemm(h, wf, bias=bias, act=act, ln_stats=st, ln_colsum=wf.float().sum(1).contiguous(), ln_eps=1e-5).float().cpu()
+    # the unfused kernels on the same inputs (LayerNorm rounds its output to bf16 first): the folded path must be at least as close
+    y = ops.layernorm(h, 1e-5, gamma.cuda(), beta.cuda())
+    unfused = ops.gemm(y, w.to(torch.bfloat16).cuda(), bias=b.float().cuda(), act=act).float().cpu()
+    e_fold, e_unf = (got - want).abs().max().item(), (unfused - want).abs().max().item()
+    print(f"LN fold M={M} C={C} N={N} act={act}: max err folded {e_fold:.4g}, unfused {e_unf:.4g}, max|ref| {want.abs().max().item():.3g}")
+    assert e_fold <= max(1.5 * e_unf, 2e-2 * want.abs().max().item())
