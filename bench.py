@@ -34,7 +34,8 @@ GFLOP_ONE_TIME = 23.3
 def workload(args):
     return {
         "workload": f"BASELINE config 2: {args.sources} synthetic 512x512 sources x {args.prompts} prompts, Canny 120/200 + SD v1.5 ControlNet-canny "
-                    f"text2img, {args.num_inference_steps} UniPC steps, CFG 7.5, cond-scale 0.75, VAE decode to u8; random-init weights",
+                    f"text2img, {args.num_inference_steps} UniPC steps, CFG 7.5, cond-scale 0.75, VAE decode to u8, then the post-generation filter "
+                    f"(WSDAN_CAL-R50 top-10 confidence + CLIP RN50 semantic argmax) to keep flags; random-init weights",
         "images_per_step": args.sources * args.prompts,
         "micro_batch": args.micro_batch,
         "num_inference_steps": args.num_inference_steps,
@@ -104,8 +105,22 @@ def make_inputs(args, rank: int):
     return {"src": torch.from_numpy(src).pin_memory(), "ids": ids.pin_memory(), "noise": noise.pin_memory(), "neg_ids": neg_ids}
 
 
-def run_step(pipe, dev_in, args, out_host=None):
-    """One pass of the hot path over one step's batch with inputs resident on the device.  Returns u8 images (device)."""
+def build_filter(dev):
+    """The post-generation filter of the path (all_utils/utils.py:357-365, :169-177): WSDAN_CAL-R50 top-10 confidence + CLIP RN50
+    semantic argmax, random-init weights of the reference architectures."""
+    from saspa_aug_b200.datasets import SyntheticUtils
+    from saspa_aug_b200.filter_nets import AugmentationFilter
+    from saspa_aug_b200.filtering import SEMANTIC_NEGATIVE_PROMPTS
+
+    ds = SyntheticUtils(n_images=1)
+    classifier, clip, tok = ds.load_filter_models(ds, dev)
+    return AugmentationFilter(classifier, clip, tok([ds.get_basic_prompt()] + SEMANTIC_NEGATIVE_PROMPTS), 10, micro_batch=64)
+
+
+def run_step(pipe, dev_in, args, flt=None):
+    """One pass of the hot path over one step's batch with inputs resident on the device: Canny -> text encode -> denoise loop -> VAE
+    decode -> u8 images -> filter keep flags (an image counts once it is a u8 tensor WITH its filter flags).
+    Returns (u8 images, keep flags | None) on the device."""
     import torch
 
     from saspa_aug_b200 import ops
@@ -126,7 +141,9 @@ def run_step(pipe, dev_in, args, out_host=None):
         img = pipe.generate_batch(text, neg.expand(i1 - i0, -1, -1).contiguous(), None, None, noise=noise[i0:i1], num_inference_steps=args.num_inference_steps,
                                   guidance_scale=7.5, controlnet_conditioning_scale=0.75, control_bf16=c)
         outs.append(img)
-    return torch.cat(outs, 0)
+    imgs = torch.cat(outs, 0)
+    keep = flt(imgs, dev_in["labels"])["keep"] if flt is not None else None
+    return imgs, keep
 
 
 def ours(args):
@@ -153,6 +170,8 @@ def ours(args):
     dev_in = {k: v.to(dev) for k, v in host.items()}
     dev_in["neg"] = pipe.encode_prompt_ids(dev_in["neg_ids"])
     n_img = args.sources * args.prompts
+    flt = build_filter(dev)
+    dev_in["labels"] = (torch.arange(n_img, dtype=torch.int32, device=dev) // args.prompts) % 100
 
     def barrier():
         if world > 1:
@@ -161,14 +180,14 @@ def ours(args):
 
     # ---- device-resident throughput ("value") ----
     for _ in range(args.warmup):
-        run_step(pipe, dev_in, args)
+        run_step(pipe, dev_in, args, flt)
     barrier()
     launches0 = ops.LAUNCHES
     with ClockSampler(local) as clocks:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(args.steps):
-            run_step(pipe, dev_in, args)
+            run_step(pipe, dev_in, args, flt)
         e.record()
         barrier()
     ms = s.elapsed_time(e)
@@ -181,33 +200,60 @@ def ours(args):
 
     # ---- end to end through the public API with HOST buffers ("e2e") ----
     out_host = torch.empty((n_img, 512, 512, 3), dtype=torch.uint8).pin_memory()
+    keep_host = torch.empty((n_img,), dtype=torch.uint8).pin_memory()
+    labels_host = dev_in["labels"].cpu().pin_memory()
 
     def e2e_step():
         d = {"src": host["src"].to(dev, non_blocking=True), "ids": host["ids"].to(dev, non_blocking=True), "noise": host["noise"].to(dev, non_blocking=True),
-             "neg": dev_in["neg"]}
-        img = run_step(pipe, d, args)
+             "labels": labels_host.to(dev, non_blocking=True), "neg": dev_in["neg"]}
+        img, keep = run_step(pipe, d, args, flt)
         out_host.copy_(img, non_blocking=True)
+        keep_host.copy_(keep, non_blocking=True)
 
-    e2e_step()
-    barrier()
+    def timed_e2e(step_fn, k):
+        step_fn()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(k):
+            step_fn()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t1], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * n_img * k / float(te.item())
+
     k2 = max(1, min(args.steps, 2))
-    t1 = time.perf_counter()
-    for _ in range(k2):
+    e2e_value = timed_e2e(e2e_step, k2)
+    h2d = host["src"].numel() + host["ids"].numel() * 8 + host["noise"].numel() * 4 + labels_host.numel() * 4
+    d2h = out_host.numel() + keep_host.numel()
+
+    # ---- the same, plus PNG encoding + file write of every image (what run_aug.py:470 does per image), thread pool ----
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+
+    from PIL import Image
+
+    png_dir = tempfile.mkdtemp(prefix=f"saspa_bench_png_r{rank}_")
+    pool = ThreadPoolExecutor(max_workers=args.io_threads)
+
+    def e2e_png_step():
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t1
-    te = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_img * k2 / float(te.item())
-    h2d = host["src"].numel() + host["ids"].numel() * 8 + host["noise"].numel() * 4
-    d2h = out_host.numel()
+        torch.cuda.current_stream().synchronize()
+        arr = out_host.numpy()
+        list(pool.map(lambda j: Image.fromarray(arr[j]).save(os.path.join(png_dir, f"{j}.png")), range(n_img)))
+
+    e2e_png_value = timed_e2e(e2e_png_step, 1)
+    pool.shutdown()
+    shutil.rmtree(png_dir, ignore_errors=True)
 
     # ---- roofline leg: CUDA events around every tcgen05 launch of one micro-batch pass ----
     roof = None
     unet_step_ms = None
+    pipe_call = None
     if rank == 0:
         roof, unet_step_ms = roofline_leg(pipe, dev_in, args)
+        pipe_call = pipe_call_leg(pipe, args)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -219,8 +265,10 @@ def ours(args):
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload(args),
             "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e_png": {"value": round(e2e_png_value, 4), "unit": UNIT, "io_threads": args.io_threads, "host_cores": os.cpu_count(),
+                        "note": "e2e + PNG encode and file write of every image (PIL, thread pool), 1 timed pass"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "unet_step_ms": unet_step_ms, "model_build_s": round(build_s, 1),
+            "unet_step_ms": unet_step_ms, "pipe_call": pipe_call, "model_build_s": round(build_s, 1),
         }
         emit(json.dumps(line))
     if world > 1:
@@ -260,21 +308,29 @@ def roofline_leg(pipe, dev_in, args):
     e.record()
     torch.cuda.synchronize()
     loop_ms = s.elapsed_time(e)
-    ops.PROFILE = []
-    pipe.generate_batch(text, neg, None, None, noise=dev_in["noise"][:mb], num_inference_steps=steps, guidance_scale=7.5,
-                        controlnet_conditioning_scale=0.75, control_bf16=c, decode=True)
-    torch.cuda.synchronize()
-    prof, ops.PROFILE = ops.PROFILE, None
-    agg = {}
-    for kind, flops, a, b, _shape in prof:
-        d = agg.setdefault(kind, [0.0, 0.0, 0])
-        d[0] += flops
-        d[1] += a.elapsed_time(b)
-        d[2] += 1
+    def profiled(decode):
+        ops.PROFILE = []
+        pipe.generate_batch(text, neg, None, None, noise=dev_in["noise"][:mb], num_inference_steps=steps, guidance_scale=7.5,
+                            controlnet_conditioning_scale=0.75, control_bf16=c, decode=decode)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, flops, a, b, _shape in prof:
+            d = agg.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops
+            d[1] += a.elapsed_time(b)
+            d[2] += 1
+        return agg
+
+    agg_step = profiled(False)  # denoise steps only
+    agg = profiled(True)        # the steps + the VAE decode of the micro-batch (what one micro-batch generation launches)
     tc_flops = sum(agg[k][0] for k in ("gemm", "conv") if k in agg)
     tc_ms = sum(agg[k][1] for k in ("gemm", "conv") if k in agg)
     tc_n = sum(agg[k][2] for k in ("gemm", "conv") if k in agg)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    so_flops = sum(agg_step[k][0] for k in ("gemm", "conv") if k in agg_step)
+    so_ms = sum(agg_step[k][1] for k in ("gemm", "conv") if k in agg_step)
+    achieved_step_only = so_flops / (so_ms * 1e-3) / 1e12 if so_ms > 0 else 0.0
     per_kind = {k: {"launches": v[2], "ms": round(v[1], 3), "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else None} for k, v in agg.items()}
     unet_step_ms = loop_ms / loop_steps
     # DRAM traffic per launch of the same kernel from the committed ncu capture of one step (never measured under bench.py)
@@ -294,13 +350,45 @@ def roofline_leg(pipe, dev_in, args):
         pass
     roof = {
         "bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05 GEMM + implicit-GEMM conv), all launches of one micro-batch generation",
-        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's gemm_tc_kernel launches)",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "frac_step_only": round(achieved_step_only / peak, 4), "achieved_step_only": round(achieved_step_only, 1), "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's gemm_tc_kernel launches)",
         "traffic_source": traffic_src, "algorithmic_flop_per_launch": round(tc_flops / max(tc_n, 1)),
         "peak_source": which, "launches_timed": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "per_kind": per_kind,
         "step_tensor_frac": round(GFLOP_PER_IMAGE_STEP * mb / (unet_step_ms * 1e-3) / 1e3 / peak, 4),
-        "note": "step_tensor_frac = 2135 GFLOP x micro_batch / UNet-step time / peak (whole denoise step incl. attention + memory-bound glue)",
+        "note": "frac = gemm_tc_kernel launches of 3 denoise steps + the VAE decode; frac_step_only = the denoise steps alone; step_tensor_frac = "
+                "2135 GFLOP x micro_batch / UNet-step time / peak (whole denoise step incl. attention + memory-bound glue)",
     }
     return roof, {"micro_batch": mb, "ms": round(unet_step_ms, 3), "ms_per_image": round(unet_step_ms / mb, 4)}
+
+
+def pipe_call_leg(pipe, args):
+    """Latency of ONE reference-shaped call: pass_thorugh_pipe(...) -> pipe(prompt, image=<PIL canny>, num_inference_steps, generator,
+    guidance_scale, negative_prompt, controlnet_conditioning_scale) -> PIL image (run_aug.py:233-279), batch 1, strings in, PIL out,
+    host-side launch overhead included (about 560 kernel launches per step through ctypes, no CUDA graph)."""
+    import statistics
+
+    import torch
+    from PIL import Image
+
+    from saspa_aug_b200 import ops, run_aug
+    from saspa_aug_b200.synthetic import synthetic_source
+
+    src = Image.fromarray(synthetic_source(7))
+    canny = run_aug.generate_canny(src, 120, 200, 512)
+    times, launches = [], 0
+    for rep in range(4):
+        torch.cuda.synchronize()
+        l0, t0 = ops.LAUNCHES, time.perf_counter()
+        img = run_aug.pass_thorugh_pipe("sd_v1.5", pipe, "an airplane flying over a snowy mountain range at sunset", src, 0, 0.85, args.num_inference_steps,
+                                        torch.Generator().manual_seed(rep), 7.5, 0.75, control_image=canny)
+        torch.cuda.synchronize()
+        if rep:  # the first call builds the negative-prompt cache
+            times.append(time.perf_counter() - t0)
+            launches = ops.LAUNCHES - l0
+    assert img.size == (512, 512)
+    med = statistics.median(times)
+    return {"latency_ms": round(med * 1e3, 1), "images_per_s": round(1.0 / med, 3), "batch": 1, "kernel_launches": int(launches),
+            "what": "one pass_thorugh_pipe call (string prompt, PIL control image in, PIL image out), median of 3 after 1 warm-up"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -379,8 +467,10 @@ def cpu_baseline_leg(args):
 
 
 def reference_arm(args):
-    """`--impl reference`: W warm-up + exactly K timed steps, each step one bounded sample (CpuPath.sample) of the same workload on all
-    host threads; rank 0 only (the other ranks of a torchrun launch exit 0 without work)."""
+    """`--impl reference`: W warm-up + exactly K timed steps on all host threads; rank 0 only (the other ranks of a torchrun launch exit 0
+    without work).  The FIRST timed step generates one whole image -- Canny + all 20 UniPC CFG steps + VAE decode, measured end to end;
+    the remaining K - 1 steps are bounded samples (Canny + 1 of the 20 steps + decode) extrapolated to a full image, so that the run ends
+    within minutes.  `consistency` reports the measured full image next to the extrapolation of the samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -388,18 +478,26 @@ def reference_arm(args):
     path = CpuPath(args, threads)
     for _ in range(args.warmup):
         path.sample(1)
-    vals = [path.sample(1) for _ in range(max(1, args.steps))]
-    r = vals[-1]
-    v = len(vals) / sum(x["per_image_s"] for x in vals)
+    t0 = time.perf_counter()
+    full = path.sample(args.num_inference_steps)
+    full_wall = time.perf_counter() - t0
+    vals = [path.sample(1) for _ in range(max(0, args.steps - 1))]
+    per_image = [full_wall] + [x["per_image_s"] for x in vals]
+    r = vals[-1] if vals else full
+    v = len(per_image) / sum(per_image)
     per_step_ms = (args.sources * args.prompts) / v * 1e3
+    extrap = (sum(x["per_image_s"] for x in vals) / len(vals)) if vals else None
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(per_step_ms, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload(args),
         "cpu_baseline": {"value": round(v, 6), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(vals)} timed steps after {args.warmup} warm-up, each a bounded sample of one image (Canny + 1 of {args.num_inference_steps} CFG "
-                                   f"steps + VAE decode, fp32 torch CPU; last: step {r['t_step_s']:.2f}s, decode {r['t_decode_s']:.2f}s), extrapolated to "
-                                   f"{args.num_inference_steps}-step images; the reference's diffusers stack cannot be installed offline, so this is the oracle port"},
+                         "sample": f"{len(per_image)} timed steps after {args.warmup} warm-up: step 1 = ONE WHOLE IMAGE measured (Canny + {args.num_inference_steps} CFG "
+                                   f"steps + VAE decode: {full_wall:.1f}s), the others bounded samples of one image (Canny + 1 of {args.num_inference_steps} steps + "
+                                   f"decode, fp32 torch CPU; last: step {r['t_step_s']:.2f}s, decode {r['t_decode_s']:.2f}s) extrapolated to full images; the "
+                                   f"reference's diffusers stack cannot be installed offline, so this is the oracle port"},
+        "consistency": {"measured_full_image_s": round(full_wall, 2), "extrapolated_per_image_s": round(extrap, 2) if extrap else None,
+                        "extrapolated_over_measured": round(extrap / full_wall, 3) if extrap else None},
         "e2e": {"value": round(v, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -438,6 +536,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--vae-micro-batch", type=int, default=8)
     ap.add_argument("--num-inference-steps", type=int, default=20)
+    ap.add_argument("--io-threads", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

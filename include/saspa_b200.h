@@ -16,6 +16,9 @@
  *   - bf16 tensors are passed as void*; activations are NHWC ("token major"): a 2-D view
  *     [pixels, channels] with a row stride in elements.  GEMM/conv weights are K-major
  *     [Cout, K] with K = kh*kw*Cin ordered (kh, kw, cin).
+ *   - No mutable global state: every entry point is a function of its arguments (a per-device once-initialised cache of function
+ *     attributes aside), re-entrant across streams and threads, CUDA-graph capturable.  The kernel-selection overrides used by tests and
+ *     A/B timing are NOT part of this ABI; they live in saspa_aug_b200/csrc/tuning_hooks.h.
  *   - No CPU fallback exists: on a machine without an sm_100 device every compute entry point
  *     returns a CUDA error.
  */
@@ -69,6 +72,14 @@ int saspa_pil_ksize(int in_size, int out_size, int filter);
 int saspa_resize_pil_u8(const uint8_t* img, int n, int h, int w, int c, uint8_t* tmp /* [n,h,out_w,c] */, uint8_t* out, int out_h,
                         int out_w, const int32_t* bounds_x, const int32_t* coeffs_x, int ksize_x, const int32_t* bounds_y,
                         const int32_t* coeffs_y, int ksize_y, cudaStream_t stream);
+/* LPIPS distance of the optional lpips_min / lpips_max filter (all_utils/utils.py:269-270, :377-381, calc_lpips_distance :576-590;
+ * arithmetic of the un-vendored `lpips` package, net='alex').
+ *   saspa_rgb_to_luma3_u8: PIL Image.convert("L").convert("RGB") (ITU-R 601-2 luma in 16-bit fixed point, replicated), u8 [pixels,3].
+ *   saspa_lpips_layer_accum: accum[i] += mean_pixels sum_c w[c] * (f0[i,p,c] / |f0[i,p,:]| - f1[i,p,c] / |f1[i,p,:]|)^2 for one AlexNet
+ *   layer's NHWC bf16 feature maps [n, hw, c] (c % 8 == 0, c <= 512); the five layers are accumulated by five stream-ordered calls. */
+int saspa_rgb_to_luma3_u8(const uint8_t* img, long long pixels, uint8_t* out, cudaStream_t stream);
+int saspa_lpips_layer_accum(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* accum, cudaStream_t stream);
+
 /* u8 [n,h,w,3] -> crop -> (x/255 - mean[c]) / std[c] -> bf16 NHWC [n,crop_h,crop_w,out_c] (channels >= 3 zero padded) */
 int saspa_crop_normalize_bf16(const uint8_t* img, int n, int h, int w, int crop_y, int crop_x, int crop_h, int crop_w, float mean0,
                               float mean1, float mean2, float std0, float std1, float std2, void* out, int out_c,
@@ -145,15 +156,7 @@ int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0, const void
                                     const void* weight, int ksize, int stride, int pad, int oh, int ow, void* out, int ldo, int cout,
                                     const saspa_epilogue* ep_host, cudaStream_t stream);
 
-/* Selects the 3x3 implicit-GEMM main loop: 0 = auto (halo tile when the map holds an 8 x 16 pixel tile, else one TMA
- * box per tap), 1 = per-tap boxes only, 2 = halo only (error when not eligible).  Returns the previous setting; a
- * negative argument only queries.  Process-wide; meant for tests and A/B timing. */
-int saspa_conv_impl(int impl);
 
-/* CTAs per output tile of the tcgen05 GEMM / conv kernel: 0 = auto (two-CTA 256-row tiles, tcgen05.mma.cta_group::2,
- * whenever the problem has two or more 128-row tiles), 1 = single-CTA tiles only, 2 = two-CTA tiles only.  Returns the
- * previous setting; a negative argument only queries.  Process-wide; meant for tests and A/B timing. */
-int saspa_gemm_force_ctas(int ctas);
 
 /* General im2col for the few strided / odd-channel convolutions (conv_in Cin=4, ControlNet cond embedding,
  * stride-2 downsamplers, ResNet stems): x bf16 NHWC [n,h,w,c] (pixel stride ldx) ->
@@ -171,9 +174,6 @@ int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, int c, int kh
 size_t saspa_groupnorm_workspace_bytes(int n, int hw, int groups);
 int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma,
                               const float* beta, int act, void* y, int ldy, void* stats_ws, size_t ws_bytes, cudaStream_t stream);
-/* 0 = auto (register-resident single-read kernel where an image slice fits one wave, else the two-pass kernel),
- * 1 = two-pass kernel only.  Returns the previous setting; negative only queries.  For tests and A/B timing. */
-int saspa_groupnorm_impl(int impl);
 /* LayerNorm over the last dim: x [rows, c] (row stride ldx) -> y bf16 [rows, c] (row stride ldy). */
 int saspa_layernorm_bf16(const void* x, int ldx, int rows, int c, float eps, const float* gamma, const float* beta, void* y,
                          int ldy, cudaStream_t stream);
@@ -198,10 +198,6 @@ int saspa_pool2d_nhwc_bf16(const void* x, int n, int h, int w, int c, int k, int
  * ------------------------------------------------------------------------------------------ */
 int saspa_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int batch,
                          int heads, int tq, int tkv, int d, float scale, int causal /* CLIP text tower */, cudaStream_t stream);
-/* Selects the attention kernel: 0 = auto (K/V-resident streaming kernel for non-causal tkv <= 128; tcgen05/TMEM kernel for
- * head_dim 40/64/80/128/160; else mma.sync), 1 = mma.sync flash kernel only, 2 = tcgen05 only (error when the shape has
- * no instantiation).  Returns the previous setting; a negative argument only queries.  Process-wide; for tests and A/B timing. */
-int saspa_attention_impl(int impl);
 
 /* Row softmax y = softmax(x * scale) (bf16, fp32 math) and batched 2-D transpose: the d = 512 single-head VAE
  * mid-block attention (diffusers models/autoencoders/vae.py UNetMidBlock2D) runs GEMM -> softmax -> GEMM. */

@@ -96,10 +96,6 @@ SIGNATURES = {
         c_int,
         [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P],
     ),
-    "saspa_attention_impl": (c_int, [c_int]),
-    "saspa_conv_impl": (c_int, [c_int]),
-    "saspa_groupnorm_impl": (c_int, [c_int]),
-    "saspa_gemm_force_ctas": (c_int, [c_int]),
     "saspa_softmax_rows_bf16": (c_int, [_P, c_int, _P, c_int, ctypes.c_longlong, c_int, c_float, _P]),
     "saspa_transpose_bf16": (c_int, [_P, c_int, ctypes.c_longlong, _P, c_int, ctypes.c_longlong, c_int, c_int, c_int, _P]),
     "saspa_timestep_sinusoid_bf16": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P]),
@@ -112,7 +108,13 @@ SIGNATURES = {
     "saspa_topk_contains": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "saspa_softmax_at_f32": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "saspa_clip_score_argmax": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "saspa_rgb_to_luma3_u8": (c_int, [_P, ctypes.c_longlong, _P, _P]),
+    "saspa_lpips_layer_accum": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }
+
+# kernel-selection overrides for tests / A-B timing (saspa_aug_b200/csrc/tuning_hooks.h): not part of the product ABI
+TUNING_HOOKS = {name: (c_int, [c_int]) for name in ("saspa_attention_impl", "saspa_conv_impl", "saspa_groupnorm_impl", "saspa_gemm_force_ctas",
+                                                    "saspa_gemm_force_bn")}
 
 _lib = None
 
@@ -126,7 +128,7 @@ def load() -> ctypes.CDLL:
                 "(there is no CPU or PyTorch fallback for the hot path)"
             )
         lib = ctypes.CDLL(SO_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(TUNING_HOOKS.items()):
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args

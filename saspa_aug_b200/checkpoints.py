@@ -615,3 +615,27 @@ def random_filter_state_dict(shapes: Shapes, seed: int) -> Dict[str, torch.Tenso
             t = 0.05 * torch.randn(shape, generator=g)
         sd[name] = t.float()
     return sd
+
+
+def lpips_alex_shapes() -> Shapes:
+    """lpips 0.1.4 ``LPIPS(net='alex')`` state dict, the entries the distance reads: torchvision AlexNet features sliced at the five
+    ReLUs (``net.slice{k}.{idx}``) and the non-negative 1x1 heads (``lin{k}.model.1.weight``)."""
+    for k, (idx, shape) in enumerate(zip((0, 3, 6, 8, 10), ((64, 3, 11, 11), (192, 64, 5, 5), (384, 192, 3, 3), (256, 384, 3, 3), (256, 256, 3, 3)))):
+        yield f"net.slice{k + 1}.{idx}.weight", shape
+        yield f"net.slice{k + 1}.{idx}.bias", (shape[0],)
+    for k, c in enumerate((64, 192, 384, 256, 256)):
+        yield f"lin{k}.model.1.weight", (1, c, 1, 1)
+
+
+def random_lpips_state_dict(seed: int) -> Dict[str, torch.Tensor]:
+    """He-normal convolutions (ReLU net), small biases, uniform non-negative ``lin`` weights (the learned heads are clamped >= 0)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in lpips_alex_shapes():
+        if name.startswith("lin"):
+            sd[name] = torch.rand(shape, generator=g) / shape[1]
+        elif name.endswith("bias"):
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = torch.randn(shape, generator=g) * (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+    return sd

@@ -12,7 +12,10 @@
 // Also here: row softmax + 2-D transpose used by the d = 512 single-head VAE mid-block attention,
 // which runs as GEMM -> softmax -> GEMM on the tcgen05 GEMM kernel.
 #include "common.cuh"
+#include <atomic>
+
 #include "../../include/saspa_b200.h"
+#include "tuning_hooks.h"
 
 namespace {
 
@@ -477,7 +480,7 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-int g_attention_impl = 0;  // 0 = auto (K/V-resident kernel for tkv <= 128, else tcgen05 when the shape has an instantiation), 1 = mma.sync flash kernel, 2 = tcgen05 only
+std::atomic<int> g_attention_impl{0};  // 0 = auto (K/V-resident kernel for tkv <= 128, else tcgen05 when the shape has an instantiation), 1 = mma.sync flash kernel, 2 = tcgen05 only
 
 }  // namespace
 
@@ -487,7 +490,7 @@ int saspa_xattention_tc(const void* q, int ldq, const void* k, int ldk, const vo
                         int tkv, int d, float scale, cudaStream_t stream);
 
 extern "C" int saspa_attention_impl(int impl) {
-  const int prev = g_attention_impl;
+  const int prev = g_attention_impl.load();
   if (impl >= 0 && impl <= 3) g_attention_impl = impl;
   return prev;
 }

@@ -292,12 +292,16 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         for (int c = 0; c < BKV; ++c)
           if (kv0 + c > qi) su[c] = 0xff800000u;
       }
+      // row maximum: eight independent chains of three-input maxima (FMNMX3), 16 columns per round
       float mx[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mx[c] = __uint_as_float(su[c]);
+      for (int c = 0; c < 8; ++c) mx[c] = fmaxf(__uint_as_float(su[c]), __uint_as_float(su[c + 8]));
 #pragma unroll
-      for (int c = 8; c < BKV; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(su[c]));
-      const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * p.scale_log2;
+      for (int c = 16; c < BKV; c += 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmax3(mx[e], __uint_as_float(su[c + e]), __uint_as_float(su[c + 8 + e]));
+      }
+      const float m_tile = fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * p.scale_log2;
 
       bool p_free = (j == 0);
       if (j == 0) {

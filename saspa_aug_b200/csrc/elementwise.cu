@@ -9,7 +9,10 @@
 // embeddings.py (Timesteps), schedulers/scheduling_{ddim,unipc_multistep,pndm}.py step(),
 // image_processor.py postprocess.
 #include "common.cuh"
+#include <atomic>
+
 #include "../../include/saspa_b200.h"
+#include "tuning_hooks.h"
 
 namespace {
 
@@ -812,9 +815,9 @@ extern "C" int saspa_im2col_bf16(const void* x, int ldx, int n, int h, int w, in
   return SASPA_OK;
 }
 
-int g_gn_impl = 0;  // 0 auto, 1 two-pass kernel only (tests / A-B timing)
+std::atomic<int> g_gn_impl{0};  // 0 auto, 1 two-pass kernel only (tests / A-B timing)
 extern "C" int saspa_groupnorm_impl(int impl) {
-  const int prev = g_gn_impl;
+  const int prev = g_gn_impl.load();
   if (impl == 0 || impl == 1) g_gn_impl = impl;
   return prev;
 }

@@ -32,7 +32,10 @@
 // TMA loads of both CTAs complete on the leader's "full" barrier; tcgen05.commit multicasts "empty" / "accumulator
 // ready" to both CTAs; the peer's epilogue warps release the accumulator with a remote mbarrier arrive.
 #include "tc_ptx.cuh"
+#include <atomic>
+
 #include "../../include/saspa_b200.h"
+#include "tuning_hooks.h"
 
 namespace {
 
@@ -120,12 +123,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-// (sum, sum of squares) of eight bf16 values exactly as they were stored
-__device__ __forceinline__ void row_stats_add(const uint4& u, float& s, float& q) {
-  const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
-  const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
-  s += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  q += ((a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3)) + ((a4 * a4 + a5 * a5) + (a6 * a6 + a7 * a7));
+// (sum, sum of squares) of the 32 fp32 values of a panel row, taken BEFORE the bf16 rounding of the store (two instructions per
+// element instead of four; the rounding noise averages out over a 320..1280-wide row: |mean error| ~ 2^-9 |x| / sqrt(C)), in four
+// independent chains
+__device__ __forceinline__ void row_stats_add(const float (&f)[32], float& s, float& q) {
+  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    s4[j & 3] += f[j];
+    q4[j & 3] = fmaf(f[j], f[j], q4[j & 3]);
+  }
+  s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  q += (q4[0] + q4[1]) + (q4[2] + q4[3]);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
@@ -582,24 +591,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (p.ln_stats) {
+          // v = rstd * (acc - mean * colsum) + bias = fma(rstd, acc, fma(-rstd * mean, colsum, bias)): two FFMA per element, the
+          // second one takes the place of the plain bias add
+          const float nm = -ln_rstd * ln_mean;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 cs = *reinterpret_cast<const float4*>(sc + c0 + j);
-            f[j] = ln_rstd * fmaf(-ln_mean, cs.x, f[j]); f[j + 1] = ln_rstd * fmaf(-ln_mean, cs.y, f[j + 1]);
-            f[j + 2] = ln_rstd * fmaf(-ln_mean, cs.z, f[j + 2]); f[j + 3] = ln_rstd * fmaf(-ln_mean, cs.w, f[j + 3]);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = *reinterpret_cast<const float4*>(sb + c0 + j);
+            f[j] = fmaf(ln_rstd, f[j], fmaf(nm, cs.x, b.x)); f[j + 1] = fmaf(ln_rstd, f[j + 1], fmaf(nm, cs.y, b.y));
+            f[j + 2] = fmaf(ln_rstd, f[j + 2], fmaf(nm, cs.z, b.z)); f[j + 3] = fmaf(ln_rstd, f[j + 3], fmaf(nm, cs.w, b.w));
           }
-          if (geglu) {
+          if (geglu) {  // gate columns: statistics applied here, their bias is added with the GELU below
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 cs = *reinterpret_cast<const float4*>(sc + BN / 2 + c0 + j);
-              gt[j] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.x, __uint_as_float(gt[j])));
-              gt[j + 1] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.y, __uint_as_float(gt[j + 1])));
-              gt[j + 2] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.z, __uint_as_float(gt[j + 2])));
-              gt[j + 3] = __float_as_uint(ln_rstd * fmaf(-ln_mean, cs.w, __uint_as_float(gt[j + 3])));
+              gt[j] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(gt[j]), nm * cs.x));
+              gt[j + 1] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(gt[j + 1]), nm * cs.y));
+              gt[j + 2] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(gt[j + 2]), nm * cs.z));
+              gt[j + 3] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(gt[j + 3]), nm * cs.w));
             }
           }
-        }
-        if (p.bias) {
+        } else if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb + c0 + j);
@@ -678,8 +691,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             u.z = pack_bf16(f[j + 4], f[j + 5]);
             u.w = pack_bf16(f[j + 6], f[j + 7]);
             *reinterpret_cast<uint4*>(pbuf + ((c ^ row_swz) << 4)) = u;
-            if (p.stats_out) row_stats_add(u, st_sum, st_sq);
           }
+          if (p.stats_out) row_stats_add(f, st_sum, st_sq);
           fence_proxy_async_smem();
           // after this barrier every thread knows stores <= n_seq - NBUF + 1 have drained their panel
           if (leader && !tma_res) bulk_wait_read<(NBUF >= 2 ? NBUF - 2 : 0)>();
@@ -740,8 +753,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 u.z = pack_bf16(f[j + 4], f[j + 5]);
                 u.w = pack_bf16(f[j + 6], f[j + 7]);
                 *reinterpret_cast<uint4*>(op + j) = u;
-                if (p.stats_out) row_stats_add(u, st_sum, st_sq);
               }
+              if (p.stats_out) row_stats_add(f, st_sum, st_sq);
             } else {
               for (int j = 0; j < 32; ++j)
                 if (n0 + j < p.n_out) op[j] = __float2bfloat16(f[j]);
@@ -871,7 +884,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 
 // Tile width along N.  SD channel counts are multiples of 320 -> 160 tiles them exactly; the VAE /
 // ResNets are powers of two; GEGLU needs value|gate halves in one tile (256 = 128 + 128).
-int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
+std::atomic<int> g_force_bn{0};  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 
 // Tile width along N.
 //  * main-loop-bound problems (convs, K >= 2048): measured per-tile time relative to BN = 256 is 0.49 / 0.63 / 0.69 for
@@ -882,7 +895,7 @@ int g_force_bn = 0;  // tuning hook (saspa_gemm_force_bn): 0 = heuristic
 //    (SD channel counts are multiples of 320 -> 160; powers of two -> 256 / 128).
 int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_n = false) {
   if (act == SASPA_ACT_GEGLU) return 256;  // value | gate halves in one tile
-  if (g_force_bn) return g_force_bn;
+  if (const int forced = g_force_bn.load()) return forced;
   // a GEMM that emits row statistics partitions each row's sums by N tile: the tile width must then be a function of N alone,
   // or a row's LayerNorm statistics would depend on how many other rows share the launch
   if (fixed_by_n) mainloop_bound = false;
@@ -921,12 +934,12 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_
   return best;
 }
 
-int g_force_ctas = 0;  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
+std::atomic<int> g_force_ctas{0};  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
 
 // Two-CTA tiles (cta_group::2, 256 x BN): measured +14% at BN = 256 and +9% at BN = 160 on the plain GEMM main loop, a loss
 // for narrower tiles and for the halo conv (profiles/r1_bn_sweep_y.txt), so only the wide long-K GEMM tiles pair up.
 int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K) {
-  if (g_force_ctas) return num_m_tiles >= 2 || g_force_ctas == 1 ? g_force_ctas : 1;
+  if (const int forced = g_force_ctas.load()) return num_m_tiles >= 2 || forced == 1 ? forced : 1;
   // epilogue-bound launches (GEGLU, short K) lose from coupling two CTAs (measured 325 -> 381 us on the 64x64 GEGLU GEMM)
   return (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= 1024 && num_m_tiles >= 2) ? 2 : 1;
 }
@@ -950,7 +963,7 @@ int dispatch(int bn, int ctas, const CUtensorMap& a0, const CUtensorMap& a1, con
   return ctas == 2 ? dispatch_bn<2>(bn, a0, a1, b, d, r, p, stream) : dispatch_bn<1>(bn, a0, a1, b, d, r, p, stream);
 }
 
-int g_conv_impl = 0;  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
+std::atomic<int> g_conv_impl{0};  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
 
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
   static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f};
@@ -1148,21 +1161,21 @@ extern "C" int saspa_conv2d_igemm_bf16(const void* x0, int ldx0, int c0, const v
 }
 
 extern "C" int saspa_conv_impl(int impl) {
-  const int prev = g_conv_impl;
+  const int prev = g_conv_impl.load();
   if (impl >= 0 && impl <= 2) g_conv_impl = impl;
   return prev;
 }
 
 // Tuning hook: force the N tile width of the non-GEGLU kernels (0 restores the heuristic).  Not part of the product API.
 extern "C" int saspa_gemm_force_bn(int bn) {
-  const int prev = g_force_bn;
+  const int prev = g_force_bn.load();
   if (bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256) g_force_bn = bn;
   return prev;
 }
 
 // Tuning hook: force one- or two-CTA tiles (0 restores the heuristic).  Not part of the product API.
 extern "C" int saspa_gemm_force_ctas(int ctas) {
-  const int prev = g_force_ctas;
+  const int prev = g_force_ctas.load();
   if (ctas >= 0 && ctas <= 2) g_force_ctas = ctas;
   return prev;
 }

@@ -217,6 +217,12 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, r, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// three-input maximum: one FMNMX3 on sm_100 (halves the instruction count of a row-maximum chain)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -10,9 +10,12 @@
 //     64-column panels straight out of the projection outputs -- nothing is repacked);
 //   * warp 1 issues S = Q K^T (SS, N = keys rounded up to 16) and O = P V (TS: P read from TMEM, V MN-major in smem) for two tiles in
 //     flight: S / P / O of tile parity i live in their own TMEM columns, P aliases the columns of the S it was computed from;
-//   * two softmax warpgroups (one thread per query row) alternate tiles: tcgen05.ld S -> mask -> max -> ex2 -> bf16 P back to TMEM,
-//     then, once P V has landed, O / l -> bf16 -> a dense shared-memory tile -> ONE TMA store per tile (full 32-byte sectors; a
-//     thread-per-row store would write half-used sectors of an HBM-bound kernel's larger stream);
+//   * one softmax warpgroup (warps 2-5, one thread per query row) does EVERY tile: tcgen05.ld S -> mask -> max -> ex2 -> bf16 P back
+//     to TMEM; the 80 exponentials per row make it the busiest role (640 MUFU clocks per tile and SM), so nothing else runs in it;
+//   * one epilogue warpgroup (warps 6-9) drains O once P V has landed: O / l -> bf16 -> a dense shared-memory tile -> ONE TMA store per
+//     tile (full 32-byte sectors; a thread-per-row store would write half-used sectors of an HBM-bound kernel's larger stream); the row
+//     sums l travel through shared memory.  S_i recycles as soon as P V has consumed P_i, O_i as soon as the epilogue has read it, so the
+//     softmax of tile k + 1 overlaps the P V and the epilogue of tile k;
 //   * head_dim 40 runs as K = 48: the pad chunk [40, 48) is zeroed in the resident K tile (warp 10), so whatever the Q panel holds there
 //     (the next head's values) multiplies zeros; P V runs with N = 48 and the extra accumulator columns are never stored.
 #include "tc_ptx.cuh"
@@ -21,7 +24,7 @@
 namespace {
 using namespace tcx;
 
-constexpr int XT_THREADS = 352;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 softmax + epilogue of tile parity 0 / 1, warp 10 K patcher
+constexpr int XT_THREADS = 352;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax, warps 6-9 epilogue, warp 10 K patcher
 constexpr int XQ = 128;          // query rows per tile
 
 template <int D, int NS>
@@ -38,7 +41,7 @@ struct XCfg {
   static constexpr int KV_STAGE = 2 * NPAN * KPAN_BYTES;  // K panels then V panels
   static constexpr int O_TILE = XQ * D * 2;               // dense [128][D] bf16 staging tile per softmax group
   static constexpr int O_TILE_AL = (O_TILE + 1023) / 1024 * 1024;
-  static constexpr int SMEM = QS * Q_STAGE + KVS * KV_STAGE + 2 * O_TILE_AL + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = QS * Q_STAGE + KVS * KV_STAGE + 2 * O_TILE_AL + 1024 /*align*/ + 256 /*barriers*/ + 4 * XQ * 4 /*row sums*/;
   static constexpr int S_STRIDE = NS <= 96 ? 96 : 128;  // TMEM columns: S_i (and P_i) at i * S_STRIDE, O_i at 2 * S_STRIDE + i * ON
   static constexpr int O_OFF = 2 * S_STRIDE;
   static_assert(O_OFF + 2 * ON <= 512, "TMEM budget");
@@ -79,8 +82,10 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
   uint64_t* s_full = k_ready + 2;      // [2]
   uint64_t* p_full = s_full + 2;       // [2]
   uint64_t* o_full = p_full + 2;       // [2]
-  uint64_t* t_free = o_full + 2;       // [2] TMEM columns of parity i consumed (S read, O read)
+  uint64_t* t_free = o_full + 2;       // [2] O_i drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + 2);
+  uint64_t* l_full = bars + 24;                     // [4] row sums of tile k published in slot k & 3
+  float* sL = reinterpret_cast<float*>(bars + 32);  // [4][128] softmax denominators of the tiles in flight
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = blockIdx.x * p.tiles_per_cta;
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
       mbar_init(&o_full[i], 1);
       mbar_init(&t_free[i], 4);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&l_full[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
     auto issue_pv = [&](int k) {
       const int i = k & 1;
       mbar_wait(&p_full[i], (k >> 1) & 1);
+      mbar_wait(&t_free[i], ((k >> 1) & 1) ^ 1);  // the epilogue has drained O_i of tile k - 2
       tc_fence_after();
       const uint32_t v_base = smem_u32(sKV + st_of[i] * C::KV_STAGE + NPAN * C::KPAN_BYTES);
 #pragma unroll
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
       st_of[i] = kvn % KVS;
       const int s = k % QS;
       mbar_wait(&q_full[s], (k / QS) & 1);
-      mbar_wait(&t_free[i], ((k >> 1) & 1) ^ 1);  // softmax group i has drained S / O of tile k - 2
+      mbar_wait(&o_full[i], ((k >> 1) & 1) ^ 1);  // P V of tile k - 2 has consumed P_i, which aliases S_i
       tc_fence_after();
       const uint32_t k_base = smem_u32(sKV + st_of[i] * C::KV_STAGE);
 #pragma unroll
@@ -220,20 +227,14 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
         if (lane == 0) mbar_arrive(&k_ready[st]);
       }
     }
-  } else {
-    // ===================== softmax + epilogue: warps 2-5 take even tiles, warps 6-9 odd tiles =====================
-    const int i = (warp - 2) >> 2;
+  } else if (warp < 6) {
+    // ===================== softmax warpgroup (warps 2-5): every tile =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_s = lane_base + i * C::S_STRIDE;
-    const uint32_t t_o = lane_base + C::O_OFF + i * ON;
-    uint8_t* stage = sO + i * C::O_TILE_AL;
-    const bool leader = (warp == 2 + 4 * i) && lane == 0;
-    for (int k = i; k < n_my; k += 2) {
-      const int tile = t_begin + k;
-      const int bh = tile / p.tiles_per_bh, qt = tile - bh * p.tiles_per_bh;
-      const int b = bh / p.heads, h = bh - b * p.heads;
+    for (int k = 0; k < n_my; ++k) {
+      const int i = k & 1;
+      const uint32_t t_s = lane_base + i * C::S_STRIDE;
       mbar_wait(&s_full[i], (k >> 1) & 1);
       tc_fence_after();
       uint32_t su[NS];
@@ -250,12 +251,15 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
         for (int c = 0; c < NS; ++c)
           if (c >= p.tkv) su[c] = 0xff800000u;
       }
-      float mx[4];
+      float mx[8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) mx[c] = __uint_as_float(su[c]);
+      for (int c = 0; c < 8; ++c) mx[c] = fmaxf(__uint_as_float(su[c]), __uint_as_float(su[c + 8]));
 #pragma unroll
-      for (int c = 4; c < NS; ++c) mx[c & 3] = fmaxf(mx[c & 3], __uint_as_float(su[c]));
-      const float neg_m = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+      for (int c = 16; c < NS; c += 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmax3(mx[e], __uint_as_float(su[c + e]), __uint_as_float(su[c + 8 + e]));
+      }
+      const float neg_m = -fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * p.scale_log2;
       float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       uint32_t pk[NS / 2];
 #pragma unroll
@@ -272,17 +276,38 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
                      "r"(pk[c + 3]), "r"(pk[c + 4]), "r"(pk[c + 5]), "r"(pk[c + 6]), "r"(pk[c + 7]), "r"(t_s + c)
                      : "memory");
       }
+      // the row sum rides to the epilogue warpgroup through shared memory (slot k & 3: tile k + 4 cannot get here before the epilogue of
+      // tile k is over -- its Q K^T waits for P V of k + 2, which waits for that epilogue); the arrive on l_full publishes it.  (The
+      // epilogue must NOT wait on p_full: that barrier can run a whole phase ahead of a lagging epilogue, whose parity wait would then
+      // never succeed.)
+      sL[(k & 3) * XQ + row] = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
-      const float inv = 1.0f / ((ls[0] + ls[1]) + (ls[2] + ls[3]));  // the row maximum contributes ex2(0) = 1: never zero
-
-      // ---- epilogue: O / l -> bf16 -> dense smem tile -> one TMA store ----
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store of this group has drained the tile
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + i) : "memory");
+      if (lane == 0) {
+        mbar_arrive(&l_full[k & 3]);
+        mbar_arrive(&p_full[i]);
+      }
+    }
+  } else {
+    // ===================== epilogue warpgroup (warps 6-9): O / l -> bf16 -> dense smem tile -> one TMA store per tile =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool leader = warp == 6 && lane == 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int i = k & 1;
+      const int tile = t_begin + k;
+      const int bh = tile / p.tiles_per_bh, qt = tile - bh * p.tiles_per_bh;
+      const int b = bh / p.heads, h = bh - b * p.heads;
+      const uint32_t t_o = lane_base + C::O_OFF + i * ON;
+      uint8_t* stage = sO + i * C::O_TILE_AL;
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store of tile k - 2 has drained this staging tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&l_full[k & 3], (k >> 2) & 1);  // acquires the row sums
       mbar_wait(&o_full[i], (k >> 1) & 1);
       tc_fence_after();
+      const float inv = 1.0f / sL[(k & 3) * XQ + row];  // the row maximum contributes ex2(0) = 1: never zero
       uint8_t* orow = stage + row * (D * 2);
 #pragma unroll
       for (int c = 0; c < ON; c += 16) {
@@ -303,9 +328,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_free[i]);  // S / P / O columns of parity i may be overwritten
+      if (lane == 0) mbar_arrive(&t_free[i]);  // O_i may be overwritten by P V of tile k + 2
       fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + i) : "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (leader) {
         x_tma_store_3d(&tmO, stage, h * D, qt * XQ, b);  // rows past tq are clipped by the tensor map
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -127,7 +127,7 @@ class SyntheticUtils(BaseUtils):
         self.n_classes = n_classes
         self.alia_threshold = 1.0  # logit threshold of the synthetic ALIA confidence filter
         self.clip_model = clip_model  # "RN50" (the reference, all_utils/utils.py:253) | "ViT-L/14" (BASELINE config 5)
-        self.logit_bias = 0.0  # added to each image's label logit by the synthetic classifier head (see load_filter_models)
+        self.lpips_seed = 31
         self.images_path = self.root / "images"
         names = names or [f"syn_{seed_base + i:07d}.png" for i in range(n_images)]
         self.original_images_paths = [str(self.images_path / n) for n in names]
@@ -187,6 +187,13 @@ class SyntheticUtils(BaseUtils):
         else:
             raise ValueError(f"clip_model {self.clip_model!r}: RN50 and ViT-L/14 are built")
         return WSDANClassifier(wsd, self.n_classes, self.net, device), clip, SyntheticTokenizer()
+
+    def load_lpips(self, device):
+        """Random-init LPIPS-AlexNet (lpips key layout) for the optional lpips_min / lpips_max filter."""
+        from . import checkpoints as ck
+        from .filter_nets import LPIPSAlex
+
+        return LPIPSAlex(ck.random_lpips_state_dict(self.lpips_seed), device)
 
 
 DS_UTILS_DICT: Dict[str, Callable] = {"synthetic": SyntheticUtils}

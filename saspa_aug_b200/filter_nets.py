@@ -276,6 +276,57 @@ class SafetyChecker:
         return images_u8, flags
 
 
+class LPIPSAlex:
+    """``lpips.LPIPS(net='alex')`` (all_utils/utils.py:269-270) on the sm_100a kernels: ScalingLayer folded into the u8 -> bf16
+    normalisation, torchvision-AlexNet ``features`` (11x11 stride 4 and 5x5 stems as im2col + tcgen05 GEMM, 3x3 as implicit GEMM, ReLU in
+    the epilogue, MaxPool(3, 2)), and the per-layer normalise / squared difference / ``lin`` / spatial mean in one kernel per layer.
+    State dict: the lpips package's keys (``net.slice{k}.{idx}.weight|bias``, ``lin{k}.model.1.weight``)."""
+
+    SHIFT, SCALE = (-0.030, -0.088, -0.188), (0.458, 0.448, 0.450)
+    IDX = (0, 3, 6, 8, 10)
+    GEOM = ((4, 2), (1, 2), (1, 1), (1, 1), (1, 1))  # (stride, padding) of the five convolutions
+
+    def __init__(self, sd: SD, device="cuda"):
+        dev = torch.device(device)
+        self.dev = dev
+        self.convs, self.lins = [], []
+        for k, (idx, (stride, pad)) in enumerate(zip(self.IDX, self.GEOM)):
+            w, b = sd[f"net.slice{k + 1}.{idx}.weight"], sd[f"net.slice{k + 1}.{idx}.bias"]
+            if w.shape[1] == 3:  # the normalised image is stored with 8 channels (zero padded): vectorised im2col
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 5))
+            self.convs.append(snn.Conv({}, "", dev, stride=stride, padding=pad, weight=w, bias=b))
+            self.lins.append(sd[f"lin{k}.model.1.weight"].reshape(-1).float().contiguous().to(dev))
+        # x in [-1, 1] = 2 u / 255 - 1, then (x - shift) / scale  ==  (u / 255 - (1 + shift) / 2) / (scale / 2)
+        self.mean = tuple((1.0 + s) / 2.0 for s in self.SHIFT)
+        self.std = tuple(s / 2.0 for s in self.SCALE)
+
+    def preprocess(self, img_u8: torch.Tensor, resize=(256, 256)) -> torch.Tensor:
+        """u8 [n,H,W,3] (device) -> u8 [n,256,256,3]: PIL "L" -> "RGB" -> resize (PIL's default filter, bicubic), calc_lpips_distance :577-582."""
+        g = ops.rgb_to_luma3(img_u8.contiguous())
+        if resize and tuple(g.shape[1:3]) != (resize[1], resize[0]):
+            g = ops.resize_pil(g, resize[1], resize[0], "bicubic")
+        return g
+
+    def features(self, x_u8: torch.Tensor):
+        n, H, W, _ = x_u8.shape
+        h = ops.crop_normalize(x_u8, 0, 0, H, W, self.mean, self.std, out_c=8)
+        out = []
+        for k, conv in enumerate(self.convs):
+            if k in (1, 2):
+                h = ops.pool2d(h, 3, 2, 0, True)
+            h = conv(h, act=ACT_RELU)
+            out.append(h)
+        return out
+
+    @torch.no_grad()
+    def __call__(self, a_u8: torch.Tensor, b_u8: torch.Tensor) -> torch.Tensor:
+        """Pre-processed u8 batches [n,S,S,3] -> LPIPS distances fp32 [n]."""
+        acc = torch.zeros((a_u8.shape[0],), dtype=torch.float32, device=a_u8.device)
+        for fa, fb, w in zip(self.features(a_u8), self.features(b_u8), self.lins):
+            ops.lpips_layer_accum(fa.contiguous(), fb.contiguous(), w, acc)
+        return acc
+
+
 class AugmentationFilter:
     """The per-image decisions of all_utils/utils.py:357-434 on batches of u8 images resident on the device.
     Enabled on the reference's hot path (run_aug.py:551-556):

@@ -100,18 +100,30 @@ def get_dict_of_value_counts(d: Dict[str, List[str]]) -> Dict[int, int]:
     return dict(sorted(counts.items()))
 
 
-def _load_batches(paths: Sequence[str], batch: int):
-    """Decode PNGs on the host (PIL, as the reference does at utils.py:360,404) and group equal-sized images."""
+def _load_batches(paths: Sequence[str], batch: int, threads: int = 8):
+    """Decode PNGs on the host (PIL, as the reference does at utils.py:360,404) in equal-sized batches, streaming: sizes come from the
+    image HEADERS, files are bucketed by (H, W) and decoded ``batch`` at a time by a small thread pool while the previous batch is on
+    the GPU -- host memory holds two batches, not the folder.  Yields (indices into ``paths``, u8 [n, H, W, 3])."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from PIL import Image
 
-    by_shape: Dict[Tuple[int, int], List[Tuple[int, np.ndarray]]] = {}
+    by_shape: Dict[Tuple[int, int], List[int]] = {}
     for i, p in enumerate(paths):
-        a = np.asarray(Image.open(p).convert("RGB"))
-        by_shape.setdefault(a.shape[:2], []).append((i, a))
-    for items in by_shape.values():
-        for j in range(0, len(items), batch):
-            chunk = items[j : j + batch]
-            yield [c[0] for c in chunk], np.stack([c[1] for c in chunk])
+        with Image.open(p) as im:
+            w, h = im.size
+        by_shape.setdefault((h, w), []).append(i)
+    chunks = [idx[j : j + batch] for idx in by_shape.values() for j in range(0, len(idx), batch)]
+
+    def decode(i):
+        return np.asarray(Image.open(paths[i]).convert("RGB"))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        nxt = [ex.submit(decode, i) for i in chunks[0]] if chunks else []
+        for c, idx in enumerate(chunks):
+            cur = nxt
+            nxt = [ex.submit(decode, i) for i in chunks[c + 1]] if c + 1 < len(chunks) else []
+            yield idx, np.stack([f.result() for f in cur])
 
 
 def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image_folder_path, lpips_min=None, lpips_max=None,
@@ -136,9 +148,12 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     from .filter_nets import AugmentationFilter
 
     assert not (clip_filtering and model_confidence_based_filtering), "can't use both clip_filtering and model_confidence_based_filtering"
-    for flag, nm in ((lpips_min, "lpips_min"), (lpips_max, "lpips_max")):
-        if flag:  # disabled in run_aug.py (LPIPS_*=None); needs the lpips AlexNet weights, which no offline oracle can pin
-            raise NotImplementedError(f"{nm}: the LPIPS filter is disabled on the reference's hot path and is not built (see DESIGN.md, out of scope)")
+    use_lpips = bool(lpips_min or lpips_max)
+    if use_lpips and (lpips_min is None or lpips_max is None):
+        # the reference evaluates `lpips_min <= d <= lpips_max` (utils.py:379): with one bound missing Python raises TypeError there
+        raise TypeError("lpips_min and lpips_max must both be given ('<=' not supported between a number and None, all_utils/utils.py:379)")
+    if use_lpips and decisions is not None:
+        raise NotImplementedError("gathered decisions carry the two hot-path filters only; run the LPIPS filter in one process")
     extra = bool(clip_filtering or alia_conf_filtering or filter_confidence_higher_than)
     if extra and decisions is not None:
         raise NotImplementedError("gathered decisions carry the two hot-path filters only; run the optional filters in one process")
@@ -185,6 +200,12 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
         logging.info("using alia_conf_filtering")
         image_path_to_class_id = ds_utils.get_image_path_to_class_id_dict()
         class_id_to_conf_threshold = ds_utils.get_baseline_conf_threshold()
+    lpips_net = None
+    if use_lpips:  # utils.py:269-270
+        lpips_net = ds_utils.load_lpips(device) if hasattr(ds_utils, "load_lpips") else None
+        if lpips_net is None:
+            raise FileNotFoundError("the LPIPS filter needs the lpips AlexNet weights: give the dataset class a load_lpips(device) method "
+                                    "returning filter_nets.LPIPSAlex (no such checkpoint exists offline)")
     flt = None
     if decisions is None:
         need_classifier = model_confidence_based_filtering or alia_conf_filtering
@@ -222,7 +243,7 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
                 unscored[k] = True
                 continue
             in_topk[k], sem[k] = d
-    elif (semantic_filtering or model_confidence_based_filtering or extra) and pairs:
+    elif (semantic_filtering or model_confidence_based_filtering or extra) and pairs and flt is not None:
         dev = torch.device(device)
         for idx, imgs in _load_batches([p[1] for p in pairs], batch_size):
             labels = torch.tensor([pairs[i][2] for i in idx], dtype=torch.int32, device=dev)
@@ -234,13 +255,34 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
             max_logit[idx] = out["max_logit"].cpu().numpy()
             argmax[idx] = out["argmax"].cpu().numpy()
             class_conf[idx] = out["class_conf"].cpu().numpy()
+    lpips_d = np.zeros(len(pairs), np.float32)
+    if use_lpips and pairs:  # calc_lpips_distance(source path, augmentation path, ...) (utils.py:377-381, :576-590), batched
+        from PIL import Image
+
+        dev = torch.device(device)
+        src_of = {Path(p).name: p for p in original_images_paths_list}
+        cache: Dict[str, "torch.Tensor"] = {}
+
+        def prep(path):  # L -> RGB -> resize(256, 256) on the device, one image at a time (sources differ in size), cached per file
+            if path not in cache:
+                a = torch.from_numpy(np.asarray(Image.open(path).convert("RGB"))[None]).to(dev)
+                cache[path] = lpips_net.preprocess(a, resize)[0]
+            return cache[path]
+
+        for i0 in range(0, len(pairs), batch_size):
+            chunk = pairs[i0 : i0 + batch_size]
+            a = torch.stack([prep(src_of[name]) for name, _, _ in chunk])
+            b = torch.stack([prep(path) for _, path, _ in chunk])
+            lpips_d[i0 : i0 + len(chunk)] = lpips_net(a, b).cpu().numpy()
+            for _, path, _ in chunk:
+                cache.pop(path, None)
     # Per source image, in dataset order, the reference applies (utils.py:357-434): top-k / too-high-confidence -> [LPIPS] -> CLIP class
     # confidence -> semantic -> ALIA confidence, each on the survivors of the previous one.  The ALIA filter spares a random 20 %
     # (`random.random() > 0.2`, global `random` state, drawn only when the confidence test fired): the draws happen here in the same order.
     import random
 
     result: Dict[str, List[str]] = {Path(p).name: [] for p in original_images_paths_list}
-    n_topk = n_sem = n_high = n_clip = n_alia_ok = n_alia_wrong = 0
+    n_topk = n_sem = n_high = n_clip = n_alia_ok = n_alia_wrong = n_lpips = 0
     for k, (name, path, label) in enumerate(pairs):
         if unscored[k]:
             continue
@@ -251,6 +293,9 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
             if filter_confidence_higher_than and float(label_conf[k]) > filter_confidence_higher_than:
                 n_high += 1
                 continue
+        if use_lpips and not (lpips_min <= float(lpips_d[k]) <= lpips_max):
+            n_lpips += 1
+            continue
         if clip_filtering and not float(class_conf[k]) >= clip_threshold:
             n_clip += 1
             continue
@@ -274,6 +319,8 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
         logging.info(f"For filter = not_in_top_{conf_top_k}, filtered {n_topk} images")
         if filter_confidence_higher_than:
             logging.info(f"For filter = confidence higher than {filter_confidence_higher_than}, filtered {n_high} images")
+    if use_lpips:
+        logging.info(f"For filter = lpips_min / lpips_max, filtered {n_lpips} images")
     if clip_filtering:
         logging.info(f"For filter = clip_filtering, filtered {n_clip} images")
     if alia_conf_filtering:
@@ -281,5 +328,5 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
     logging.info(f"dict_num_augmentations_per_image = {get_dict_of_value_counts(result)}")
     if return_details:
         return json_path, {"pairs": pairs, "in_topk": in_topk, "semantic": sem, "label_conf": label_conf, "max_logit": max_logit, "argmax": argmax,
-                           "class_conf": class_conf}
+                           "class_conf": class_conf, "lpips": lpips_d}
     return json_path

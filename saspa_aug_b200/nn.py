@@ -167,11 +167,14 @@ class TransformerBlock:
 
     @staticmethod
     def _folded(w, b, gamma, beta, dev):
-        """(W' = bf16(W * gamma), fp32 colsum of W' as the MMA sees it, fp32 bias b + W beta)."""
-        w32, g32, be32 = w.detach().float(), gamma.detach().float(), beta.detach().float()
-        wp = _bf(w32 * g32[None, :], dev)
-        bias = w32 @ be32 + (b.detach().float() if b is not None else 0.0)
-        return wp, wp.float().sum(dim=1).contiguous(), _f32(bias, dev)
+        """(W' = bf16(W * gamma), fp32 colsum of W' as the MMA sees it, fp32 bias b + W beta).  The two reductions run in float64 and
+        are rounded once: a float32 matmul / sum would depend on the summation order (OpenMP thread count, GPU reduction tree), and two
+        processes of one job would then build models that differ in the last bit -- enough for visibly different pixels."""
+        w64, g64, be64 = w.detach().double().cpu(), gamma.detach().double().cpu(), beta.detach().double().cpu()
+        wp = _bf((w64 * g64[None, :]).float(), dev)
+        bias = w64 @ be64 + (b.detach().double().cpu() if b is not None else 0.0)
+        colsum = wp.detach().cpu().double().sum(dim=1)
+        return wp, _f32(colsum.float(), dev), _f32(bias.float(), dev)
 
     def text_kv(self, text2d: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Step-invariant K/V projections of the text states [n*77, cross] -> two [n,77,c] views."""

@@ -524,3 +524,23 @@ def clip_score_argmax(img: torch.Tensor, txt: torch.Tensor, logit_scale: float):
     check(_lib.load().saspa_clip_score_argmax(_ptr(img), _ptr(txt), n, p, d, float(logit_scale), _ptr(logits), _ptr(arg), _stream()), "saspa_clip_score_argmax")
     _count()
     return logits, arg
+
+
+def rgb_to_luma3(img: torch.Tensor) -> torch.Tensor:
+    """u8 [..., 3] -> u8 same shape: PIL ``convert("L").convert("RGB")`` (bit-exact)."""
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.shape[-1] == 3 and img.is_contiguous()
+    out = torch.empty_like(img)
+    check(_lib.load().saspa_rgb_to_luma3_u8(_ptr(img), img.numel() // 3, _ptr(out), _stream()), "saspa_rgb_to_luma3_u8")
+    _count()
+    return out
+
+
+def lpips_layer_accum(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, accum: torch.Tensor) -> None:
+    """accum[n] += spatial mean of sum_c w_c (unit(f0) - unit(f1))^2 for NHWC bf16 feature maps [n,h,w,c]."""
+    _need_cuda(f0, f1, w, accum)
+    n, h, ww, c = f0.shape
+    assert f0.dtype == BF16 and f1.dtype == BF16 and f0.is_contiguous() and f1.is_contiguous() and f1.shape == f0.shape
+    assert w.dtype == torch.float32 and w.numel() == c and accum.dtype == torch.float32 and accum.numel() == n
+    check(_lib.load().saspa_lpips_layer_accum(_ptr(f0), _ptr(f1), _ptr(w), n, h * ww, c, _ptr(accum), _stream()), "saspa_lpips_layer_accum")
+    _count()

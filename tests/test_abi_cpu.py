@@ -27,6 +27,17 @@ def test_header_symbols_all_exported_and_bound():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_tuning_hooks_are_not_part_of_the_public_abi():
+    """The kernel-selection overrides (process-wide, for tests and A/B timing) are declared in csrc/tuning_hooks.h only."""
+    hooks = open(os.path.join(ROOT, "saspa_aug_b200", "csrc", "tuning_hooks.h")).read()
+    hooks = sorted(set(re.findall(r"\b(saspa_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hooks, flags=re.S))))
+    assert hooks == sorted(_lib.TUNING_HOOKS) and not set(hooks) & set(_declared())
+    lib = _lib.load()
+    for n in hooks:
+        assert hasattr(lib, n)
+    assert lib.saspa_attention_impl(-1) == 0 and lib.saspa_conv_impl(-1) == 0 and lib.saspa_gemm_force_ctas(-1) == 0  # the library starts in auto
+
+
 def test_version_and_error_string():
     lib = _lib.load()
     assert lib.saspa_version() == 100

@@ -187,5 +187,11 @@ def test_one_rank_and_two_rank_runs_write_the_same_json_and_pixels(cuda_device, 
     f1, f2 = os.path.dirname(j1[0]) + "/images", os.path.dirname(j2[0]) + "/images"
     names = sorted(os.listdir(f1))
     assert names == sorted(os.listdir(f2)) and sum("_prompt_" in n for n in names) == 20
+    from PIL import Image
+
+    bad = []
     for n in names:
-        assert open(os.path.join(f1, n), "rb").read() == open(os.path.join(f2, n), "rb").read(), n
+        if open(os.path.join(f1, n), "rb").read() != open(os.path.join(f2, n), "rb").read():
+            a, b = np.asarray(Image.open(os.path.join(f1, n))).astype(int), np.asarray(Image.open(os.path.join(f2, n))).astype(int)
+            bad.append((n, a.shape, int(np.abs(a - b).max()), float((a != b).mean())))
+    assert not bad, bad

@@ -237,7 +237,9 @@ def test_layernorm_folded_into_gemm(cuda_device, M, C, N, act):
     h, st = ops.gemm(a, wp, residual=res, beta=1.0, row_stats=True)
     assert st.shape == (M, ops.row_stats_slots(C), 2) and st.dtype == torch.float32
     hf = h.float()
-    assert torch.allclose(st[..., 0].sum(1), hf.sum(1), rtol=1e-5, atol=1e-3) and torch.allclose(st[..., 1].sum(1), (hf * hf).sum(1), rtol=1e-5, atol=1e-2)
+    # the sums are taken on the fp32 values just before the bf16 rounding of the store: each term is within 2^-9 relative of the stored one
+    assert ((st[..., 0].sum(1) - hf.sum(1)).abs() <= 2.0 ** -8 * hf.abs().sum(1) + 1e-3).all()
+    assert ((st[..., 1].sum(1) - (hf * hf).sum(1)).abs() <= 2.0 ** -7 * (hf * hf).sum(1) + 1e-2).all()
     # a row's statistics do not depend on how many rows share the launch
     h2, st2 = ops.gemm(a[:130], wp, residual=res[:130], beta=1.0, row_stats=True)
     assert torch.equal(h2, h[:130]) and torch.equal(st2, st[:130])

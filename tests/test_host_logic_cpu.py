@@ -323,3 +323,55 @@ def test_world_size_2_run_sharded_host_logic_gloo(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29613", str(w), ROOT, str(tmp_path / "ds")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_reference_consumer_reads_the_json_we_write(tmp_path):
+    """The aug JSON is a contract with the reference's training side: its OWN AugWrapperDataset (fgvc/datasets/aug_wrapper_dataset.py:106-186,
+    imported from /root/reference) loads the file written by our writer, drops the sources without kept augmentations at ratio 1 and serves
+    the kept files."""
+    import importlib.util
+    import random
+
+    from PIL import Image
+
+    from saspa_aug_b200 import filtering
+    from saspa_aug_b200.datasets import SyntheticUtils
+
+    spec = importlib.util.spec_from_file_location("ref_aug_wrapper", os.path.join(ref_import.REFERENCE_ROOT, "fgvc", "datasets", "aug_wrapper_dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    ds = SyntheticUtils(root=str(tmp_path / "ds"), n_images=6, size=(32, 32)).materialize()
+    cfg = run_aug.AugConfig()
+    out_dir = run_aug.output_folder(str(tmp_path / "ds"), cfg)
+    os.makedirs(out_dir)
+    decisions = {}
+    for index, p in enumerate(ds.original_images_paths):
+        stem = os.path.splitext(os.path.basename(p))[0]
+        for i in range(2):
+            path = os.path.join(out_dir, run_aug.aug_file_name(stem, f"an airplane, take {i}", i))
+            Image.new("RGB", (8, 8), (index * 40, 200, i * 200)).save(path)
+            decisions[(os.path.basename(p), path)] = (int(index % 3 != 0), int(i == 0 or index == 4))  # sources 0 and 3 keep nothing
+    jp = filtering.create_json_of_image_name_to_augmented_images_paths("synthetic", out_dir, semantic_filtering=True, model_confidence_based_filtering=True,
+                                                                       init_log=False, ds_utils=ds, decisions=decisions)
+
+    class Train(mod.AugWrapperDataset):
+        def __init__(self, **kw):
+            self._image_files = list(ds.original_images_paths)
+            self._labels = [ds.label_of(i) for i in range(len(self._image_files))]
+            self.num_classes, self.dataset_name = ds.num_classes, "synthetic"
+            super().__init__(root=str(tmp_path / "ds"), split="train", print_func=lambda *a: None, **kw)
+
+    random.seed(0)
+    t = Train(aug_json=jp, aug_sample_ratio=1)
+    assert len(t) == 4 and sorted(os.path.basename(p) for p in t._image_files) == [os.path.basename(ds.original_images_paths[i]) for i in (1, 2, 4, 5)]
+    served = set()
+    for rep in range(8):
+        for idx in range(len(t)):
+            img, label = t[idx]
+            assert img.size == (8, 8) and label == t._labels[idx]  # always an augmentation at ratio 1
+            served.add(img.getpixel((0, 0)))
+    kept = {p for (_, p), (a, b) in decisions.items() if a and b}
+    assert served == {Image.open(p).getpixel((0, 0)) for p in kept} and len(kept) == 5
+    assert t.times_used_aug_images == 32 and t.times_used_orig_images == 0

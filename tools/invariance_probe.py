@@ -32,7 +32,11 @@ class Recorder:
             def wrap(*a, _f=f, _n=name, **k):
                 out = _f(*a, **k)
                 shapes = [tuple(t.shape) for t in a if isinstance(t, torch.Tensor)]
-                self.log.append((_n, shapes, out.detach().clone()))
+                if isinstance(out, tuple):  # gemm(row_stats=True) -> (out, partial row statistics): both are checked
+                    self.log.append((_n, shapes, out[0].detach().clone()))
+                    self.log.append((_n + ":row_stats", shapes, out[1].detach().clone()))
+                else:
+                    self.log.append((_n, shapes, out.detach().clone()))
                 return out
 
             setattr(ops, name, wrap)
@@ -44,12 +48,13 @@ class Recorder:
 
 
 def run(pipe, B, res, steps, record=True):
+    H, W = res if isinstance(res, tuple) else (res, res)
     vocab = pipe.text_encoder.tok.shape[0]
     ids = torch.cat([synthetic_token_ids(10 + j, batch=1, vocab=vocab) for j in range(B)])
     nids = synthetic_token_ids(99, batch=1, vocab=vocab).repeat(B, 1)
-    src = np.stack([synthetic_source(j, res, res) for j in range(B)])
+    src = np.stack([synthetic_source(j, H, W) for j in range(B)])
     edges, _ = ops.canny(torch.from_numpy(src).cuda(), 120, 200, out_channels=3)
-    noise = torch.cat([torch.randn((1, 4, res // 8, res // 8), generator=torch.Generator().manual_seed(1000 + j)) for j in range(B)]).cuda()
+    noise = torch.cat([torch.randn((1, 4, H // 8, W // 8), generator=torch.Generator().manual_seed(1000 + j)) for j in range(B)]).cuda()
     text, neg = pipe.encode_prompt_ids(ids), pipe.encode_prompt_ids(nids)
     if record:
         with Recorder() as r:
@@ -71,7 +76,8 @@ def rows_of(t, rows):
 def main():
     cfg = sys.argv[1] if len(sys.argv) > 1 else "tiny"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    res = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    res = sys.argv[3] if len(sys.argv) > 3 else "128"
+    res = tuple(int(v) for v in res.split("x")) if "x" in res else int(res)
     steps = 2
     pipe = SaspaControlNetPipeline.random_init(cfg, seed=7, sampler="ddim")
     imgA, logA = run(pipe, B, res, steps)
