@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(LP_THREADS) lpips_layer_kernel(const __nv_bflo
     for (int k = 0; k < LP_MAXV; ++k) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = x[k][j] * ix - y[k][j] * iy;
+        const float t = __fsub_rn(__fmul_rn(x[k][j], ix), __fmul_rn(y[k][j], iy));  // no FMA contraction: identical inputs give exactly 0
         d = fmaf(wv[k][j] * t, t, d);
       }
     }

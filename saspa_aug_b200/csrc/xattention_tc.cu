@@ -5,9 +5,12 @@
 // and Tkv <= 128 keys.  The whole key sequence is ONE tile, so there is no online-softmax recurrence; the op is bound by streaming
 // Q in and O out of HBM (2 x Tq x d x 2 B per head), and the kernel is organised around that:
 //
-//   * persistent CTAs (one per SM) walk a contiguous range of 128-query tiles ordered (batch, head, tile): K / V of a head are
-//     loaded once per head change into a 2-deep ring and stay resident while its query tiles stream through a Q ring (TMA, 128B swizzle,
-//     64-column panels straight out of the projection outputs -- nothing is repacked);
+//   * persistent CTAs (one per SM) take RUNS of R consecutive 128-query tiles of one (batch, head), round-robin over the order
+//     [batch][query chunk][head]: at any moment neighbouring CTAs work on the heads of the SAME token rows, so every 640-byte token row
+//     of Q is fetched from HBM once and its other heads hit L2 (with head-major ranges per CTA the same lines were fetched once per
+//     head: ncu showed 663 MB read for 168 MB of Q).  K / V of the run's head are loaded once per run into a 2-deep ring and stay
+//     resident while its query tiles stream through a Q ring (TMA, 128B swizzle, 64-column panels straight out of the projection
+//     outputs -- nothing is repacked);
 //   * warp 1 issues S = Q K^T (SS, N = keys rounded up to 16) and O = P V (TS: P read from TMEM, V MN-major in smem) for two tiles in
 //     flight: S / P / O of tile parity i live in their own TMEM columns, P aliases the columns of the S it was computed from;
 //   * one softmax warpgroup (warps 2-5, one thread per query row) does EVERY tile: tcgen05.ld S -> mask -> max -> ex2 -> bf16 P back
@@ -51,7 +54,10 @@ struct XCfg {
 
 struct XParams {
   int heads, tq, tkv;
-  int tiles_per_bh, total_tiles, tiles_per_cta;
+  int tiles_per_bh;    // 128-query tiles per (batch, head)
+  int run;             // R: consecutive tiles of one head per run (divides tiles_per_bh)
+  int chunks_per_bh;   // tiles_per_bh / R
+  int total_runs;      // batch * chunks_per_bh * heads, ordered [batch][chunk][head]
   float scale_log2;
 };
 
@@ -88,9 +94,19 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
   float* sL = reinterpret_cast<float*>(bars + 32);  // [4][128] softmax denominators of the tiles in flight
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
-  const int n_my = max(t_end - t_begin, 0);
+  // local tile k of this CTA = tile (k % R) of its run number k / R; run g = (k / R) * gridDim.x + blockIdx.x
+  const int my_runs = (p.total_runs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_my = my_runs * p.run;
+  auto decode = [&](int k, int& b, int& h, int& qt) {
+    const int lr = k / p.run, r = k - lr * p.run;
+    const int g = lr * (int)gridDim.x + (int)blockIdx.x;
+    h = g % p.heads;
+    const int t = g / p.heads;
+    const int qc = t % p.chunks_per_bh;
+    b = t / p.chunks_per_bh;
+    qt = qc * p.run + r;
+    return r == 0;  // first tile of a run: a new head's K / V
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -126,14 +142,12 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane per instruction) =====================
-    int kvn = -1, prev_bh = -1;
+    int kvn = -1;
     for (int k = 0; k < n_my; ++k) {
-      const int tile = t_begin + k;
-      const int bh = tile / p.tiles_per_bh, qt = tile - bh * p.tiles_per_bh;
-      const int b = bh / p.heads, h = bh - b * p.heads;
+      int b, h, qt;
+      const bool new_head = decode(k, b, h, qt);
       const int col0 = h * D;
-      if (bh != prev_bh) {
-        prev_bh = bh;
+      if (new_head) {
         ++kvn;
         const int st = kvn % KVS;
         mbar_wait(&kv_empty[st], ((kvn / KVS) & 1) ^ 1);
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = make_idesc(XQ, NS, 0);
     constexpr uint32_t idesc_pv = make_idesc(XQ, ON, 1);
-    int kvn = -1, prev_bh = -1;
+    int kvn = -1;
     int st_of[2] = {0, 0};  // K/V stage of the tile in flight on parity i
     auto issue_pv = [&](int k) {
       const int i = k & 1;
@@ -173,19 +187,23 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
       if (elect_one()) tc_commit(&o_full[i]);
     };
     for (int k = 0; k < n_my; ++k) {
-      const int tile = t_begin + k;
-      const int bh = tile / p.tiles_per_bh;
       const int i = k & 1;
       bool pv_issued = false;
-      if (bh != prev_bh) {
-        // head switch: the previous head's K / V stage is released once every MMA that reads it has completed, and its last reader
-        // is tile k - 1's P V -- issue that first (with a one-deep ring the producer cannot load the new head before it)
+      int release = -1;  // K / V stage whose last reader is tile k - 1's P V
+      if (k % p.run == 0) {
+        // new run = new head.  The previous head's stage may be refilled once every MMA that reads it has completed; its last reader is
+        // tile k - 1's P V.  With a two-deep ring the new head already sits in the other stage, so that P V keeps its usual place (after
+        // this tile's Q K^T) and the stage is released right behind it; with a one-deep ring the producer cannot load the new head
+        // before the release, so the P V has to go first.
         if (k > 0) {
-          issue_pv(k - 1);
-          pv_issued = true;
-          if (elect_one()) tc_commit(&kv_empty[st_of[(k - 1) & 1]]);
+          release = st_of[(k - 1) & 1];
+          if (KVS == 1) {
+            issue_pv(k - 1);
+            pv_issued = true;
+            if (elect_one()) tc_commit(&kv_empty[release]);
+            release = -1;
+          }
         }
-        prev_bh = bh;
         ++kvn;
         mbar_wait(C::PAD ? &k_ready[kvn % KVS] : &kv_full[kvn % KVS], (kvn / KVS) & 1);
         tc_fence_after();
@@ -205,18 +223,16 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
       }
       if (elect_one()) tc_commit(&s_full[i]);
       if (elect_one()) tc_commit(&q_empty[s]);
-      if (k > 0 && !pv_issued) issue_pv(k - 1);  // Q K^T of tile k is already queued behind it: S_k is ready when group i needs it
+      if (k > 0 && !pv_issued) issue_pv(k - 1);  // Q K^T of tile k is already queued in front of it: S_k is ready when the softmax needs it
+      if (release >= 0 && elect_one()) tc_commit(&kv_empty[release]);
     }
     if (n_my > 0) issue_pv(n_my - 1);
   } else if (warp == 10) {
     // ===================== K patcher: zero the pad chunk [D, D + 8) of every landed K tile (head_dim % 16 == 8) =====================
     if (C::PAD) {
       constexpr int ch = D / 8, pn = ch / 8, lc = ch % 8;
-      int kvn = -1, prev_bh = -1;
-      for (int k = 0; k < n_my; ++k) {
-        const int bh = (t_begin + k) / p.tiles_per_bh;
-        if (bh == prev_bh) continue;
-        prev_bh = bh;
+      int kvn = -1;
+      for (int k = 0; k < n_my; k += p.run) {
         ++kvn;
         const int st = kvn % KVS;
         mbar_wait(&kv_full[st], (kvn / KVS) & 1);
@@ -297,9 +313,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
     const bool leader = warp == 6 && lane == 0;
     for (int k = 0; k < n_my; ++k) {
       const int i = k & 1;
-      const int tile = t_begin + k;
-      const int bh = tile / p.tiles_per_bh, qt = tile - bh * p.tiles_per_bh;
-      const int b = bh / p.heads, h = bh - b * p.heads;
+      int b, h, qt;
+      decode(k, b, h, qt);
       const uint32_t t_o = lane_base + C::O_OFF + i * ON;
       uint8_t* stage = sO + i * C::O_TILE_AL;
       if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store of tile k - 2 has drained this staging tile
@@ -406,12 +421,18 @@ int launch_xtc(const void* q, int ldq, const void* k, int ldk, const void* v, in
   p.tq = tq;
   p.tkv = tkv;
   p.tiles_per_bh = ceil_div(tq, XQ);
-  p.total_tiles = p.tiles_per_bh * batch * heads;
+  p.run = 1;
+  for (int r = 4; r > 1; r >>= 1)
+    if (p.tiles_per_bh % r == 0) {
+      p.run = r;
+      break;
+    }
+  p.chunks_per_bh = p.tiles_per_bh / p.run;
+  p.total_runs = batch * p.chunks_per_bh * heads;
   const int sms = saspa_num_sms();
-  const int ctas = p.total_tiles < sms ? p.total_tiles : sms;
-  p.tiles_per_cta = ceil_div(p.total_tiles, ctas);
+  const int ctas = p.total_runs < sms ? p.total_runs : sms;
   p.scale_log2 = scale * 1.4426950408889634f;
-  xattn_tc_kernel<D, NS><<<ceil_div(p.total_tiles, p.tiles_per_cta), XT_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, tmO, p);
+  xattn_tc_kernel<D, NS><<<ctas, XT_THREADS, C::SMEM, stream>>>(tmQ, tmK, tmV, tmO, p);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }

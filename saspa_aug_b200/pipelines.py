@@ -11,6 +11,7 @@ per launch list).  All compute is sm_100a kernels (saspa_aug_b200.nn / ops); no 
 """
 from __future__ import annotations
 
+import os
 import zlib
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Union
@@ -81,8 +82,44 @@ class SaspaControlNetPipeline:
         # Random-init runs keep it off (a random checker would blank images at random); assign one built from real weights to match
         # the reference pipeline bit for bit in behaviour.
         self.safety_checker = None
+        # The reference calls the pipeline once per image (run_aug.py:464): ~9000 kernel launches per call, each a ctypes call that also
+        # encodes its TMA descriptors -- at batch 1 the host, not the GPU, sets the latency.  The denoise loop + decode of a call shape
+        # is therefore captured ONCE into a CUDA graph (descriptors and scheduler coefficients are kernel arguments, so they are baked
+        # in) and replayed for every later call of that shape.  SASPA_CUDA_GRAPH=0 disables it; large batches (the sharded driver,
+        # bench.py) are GPU-bound and launch directly.
+        self.cuda_graph_max_images = 0 if os.environ.get("SASPA_CUDA_GRAPH", "1") == "0" else 4
+        self._graphs = {}
 
-    # ---- construction -----------------------------------------------------------------------
+    # ---- CUDA-graph replay of one call shape ---------------------------------------------------------
+    def _generate_graphed(self, tensors: dict, **kw):
+        """``generate_batch(**tensors, **kw)`` through a captured graph.  ``tensors``: name -> device tensor | None (the data that changes
+        from call to call); ``kw``: the scalars that define the launch list.  Returns the graph's static u8 output (valid until the next
+        replay of the same shape)."""
+        key = (tuple((n, None if t is None else (tuple(t.shape), t.dtype)) for n, t in sorted(tensors.items())), tuple(sorted(kw.items())),
+               type(self.scheduler).__name__, id(self.scheduler))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = {n: (None if t is None else t.clone()) for n, t in tensors.items()}
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside the capture: function attributes, lazy module loading, allocator pools
+                self.generate_batch(**static, **kw)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (PNG writers, samplers) keep working
+                out = self.generate_batch(**static, **kw)
+            if len(self._graphs) >= 4:  # a handful of call shapes per run (square + two aspect ratios): drop the oldest
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = (graph, static, out)
+        graph, static, out = ent
+        for n, t in tensors.items():
+            if t is not None:
+                static[n].copy_(t, non_blocking=True)
+        graph.replay()
+        return out
+
     @classmethod
     def from_state_dicts(cls, unet_sd, controlnet_sd, vae_sd, text_sd, *, unet_cfg=None, vae_cfg=None, text_cfg=None, sampler="ddim",
                          device="cuda", tokenizer=None, img2img=True):
@@ -284,9 +321,13 @@ class SaspaControlNetPipeline:
         noise = noise.float().to(self.device)
         per_step = [] if return_latents_per_step else None
         cb = (lambda i, t, x: per_step.append(x.detach().clone())) if return_latents_per_step else None
-        out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, num_inference_steps=num_inference_steps,
-                                  guidance_scale=guidance_scale, strength=strength, controlnet_conditioning_scale=controlnet_conditioning_scale,
-                                  step_callback=cb, added=added)
+        scalars = dict(num_inference_steps=int(num_inference_steps), guidance_scale=float(guidance_scale), strength=float(strength),
+                       controlnet_conditioning_scale=float(controlnet_conditioning_scale))
+        if cb is None and added is None and 0 < B <= self.cuda_graph_max_images:
+            out = self._generate_graphed(dict(text_embeds=text, neg_embeds=neg, control_u8=control_u8, source_u8=source_u8, noise=noise,
+                                              noise_posterior=post), **scalars)
+        else:
+            out = self.generate_batch(text, neg, control_u8, source_u8, noise=noise, noise_posterior=post, step_callback=cb, added=added, **scalars)
         nsfw = None
         if self.safety_checker is not None:  # run_safety_checker of the SD v1.5 pipelines
             out, nsfw = self.safety_checker(out)

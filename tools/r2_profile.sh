@@ -12,7 +12,7 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_tc_kernel -s 30 -c 3 -f -o gpurun_out/r2_full_gemm_tc_kernel \
     python tools/profile_step.py --mb 32 --steps 1 > gpurun_out/r2_full_gemm_tc_kernel.log 2>&1
 for k in canny_nms_kernel canny_hysteresis resample_pass_kernel layernorm_sub_kernel crop_normalize_kernel; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/r2_full_$k \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/r2_full_$k \
       python tools/membound_once.py > gpurun_out/r2_full_$k.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep
