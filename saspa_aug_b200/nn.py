@@ -469,15 +469,23 @@ class ControlNet(_EncoderBase):
             x = c(x, act=ACT_SILU)
         return self.ce_out(x)
 
-    def inject(self, x0, temb_all, kv, cond_emb, scale: float, unet_state):
-        """ControlNet forward; every zero-conv accumulates `scale * residual` into the UNet's skip tensors /
-        mid output in its epilogue (diffusers: down_block_additional_residuals / mid_block_additional_residual)."""
+    def trunk(self, x0, temb_all, kv, cond_emb):
+        """The ControlNet's own encoder + mid block -> (mid hidden, per-skip hiddens); independent of the UNet until ``accumulate``."""
         x, outs = self.run_encoder(x0, temb_all, kv, None, add_after_conv_in=cond_emb)
-        x = self.run_mid(x, temb_all, kv)
+        return self.run_mid(x, temb_all, kv), outs
+
+    def accumulate(self, x, outs, scale: float, unet_state):
+        """Every zero-conv accumulates `scale * residual` into the UNet's skip tensors / mid output in its epilogue (diffusers:
+        down_block_additional_residuals / mid_block_additional_residual)."""
         for conv, o, dst in zip(self.zero, outs, unet_state["skips"]):
             conv(o, out=dst, alpha=scale, residual=dst, beta=1.0)
         m = unet_state["mid"]
         self.zero_mid(x, out=m, alpha=scale, residual=m, beta=1.0)
+
+    def inject(self, x0, temb_all, kv, cond_emb, scale: float, unet_state):
+        """ControlNet forward + residual injection on the current stream."""
+        x, outs = self.trunk(x0, temb_all, kv, cond_emb)
+        self.accumulate(x, outs, scale, unet_state)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -89,6 +89,8 @@ class SaspaControlNetPipeline:
         # bench.py) are GPU-bound and launch directly.
         self.cuda_graph_max_images = 0 if os.environ.get("SASPA_CUDA_GRAPH", "1") == "0" else 4
         self._graphs = {}
+        self.two_stream = os.environ.get("SASPA_TWO_STREAM", "0") == "1"  # ControlNet trunk beside the UNet encoder (see _eps)
+        self._side_stream = None
 
     # ---- CUDA-graph replay of one call shape ---------------------------------------------------------
     def _generate_graphed(self, tensors: dict, **kw):
@@ -279,10 +281,27 @@ class SaspaControlNetPipeline:
         if do_cfg:
             ops.nchw_f32_to_nhwc_bf16(latents, out=x2[B:])
         temb_u = self.unet.time_embed(tvec, aug_u)
-        st = self.unet.encode(x2, temb_u, kv_u, rows, lh, lw)
-        if self.controlnet is not None:
+        if self.controlnet is not None and self.two_stream:
+            # The ControlNet trunk and the UNet encoder + mid block are independent until the zero-convs: run them on two streams so the
+            # small-map levels of one (8x8 / 16x16: fewer tiles than SMs) share the machine with the other's kernels.
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
             temb_c = self.controlnet.time_embed(tvec, aug_c)
-            self.controlnet.inject(x2, temb_c, kv_c, cond_emb, cond_scale, st)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                x_c, outs_c = self.controlnet.trunk(x2, temb_c, kv_c, cond_emb)
+            st = self.unet.encode(x2, temb_u, kv_u, rows, lh, lw)
+            main.wait_stream(side)
+            for t in outs_c + [x_c]:
+                t.record_stream(main)  # allocated on the side stream, consumed (and later freed) on the main one
+            self.controlnet.accumulate(x_c, outs_c, cond_scale, st)
+        else:
+            st = self.unet.encode(x2, temb_u, kv_u, rows, lh, lw)
+            if self.controlnet is not None:
+                temb_c = self.controlnet.time_embed(tvec, aug_c)
+                self.controlnet.inject(x2, temb_c, kv_c, cond_emb, cond_scale, st)
         eps_nhwc = self.unet.decode(st, temb_u, kv_u)
         return ops.nhwc_to_nchw_f32(eps_nhwc)
 

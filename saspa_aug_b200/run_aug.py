@@ -752,15 +752,16 @@ def run_sharded(cfg: AugConfig, ds_utils, prompts, ds_root: str, pipe=None, devi
         def extra(pairs):
             """(source, augmentation) pairs the substring rule of utils.py:352-354 adds beyond each rank's own records (one source's stem
             inside another's file name; files left by earlier runs): scored here, against THAT source's label."""
-            lab = ds_utils.get_image_path_to_class_id_dict() if cfg.MODEL_CONFIDENCE_BASED_FILTERING else {}
             by_name = {Path(p).name: k for k, p in enumerate(paths)}
             w = [(by_name[name], -1, path) for name, path in pairs]
+            ok = {rec[2] for rec in verify_written(w)}  # files nobody generated in this run (leftovers): same verify-or-delete policy
+            w = [rec for rec in w if rec[2] in ok]
             rr = (filter_fn or filter_shard)(cfg, ds_utils, w, device=device, filter_models=filter_models)
-            return {pair: (int(x[2]), int(x[3])) for pair, x in zip(pairs, rr)}
+            return {(Path(paths[rec[0]]).name, rec[2]): (int(x[2]), int(x[3])) for rec, x in zip(w, rr)}
 
         json_path = filtering.create_json_of_image_name_to_augmented_images_paths(
             cfg.DATASET, out_dir, semantic_filtering=bool(cfg.SEMANTIC_FILTERING), model_confidence_based_filtering=bool(cfg.MODEL_CONFIDENCE_BASED_FILTERING),
-            conf_top_k=cfg.CONF_TOP_K, init_log=False, ds_utils=ds_utils, decisions=decisions, missing_decisions=extra)
+            conf_top_k=cfg.CONF_TOP_K, init_log=False, ds_utils=ds_utils, decisions=decisions, missing_decisions=extra, assume_verified=True)
         stats.update(records=int(allrec.shape[0]), kept=int(sum(1 for a, b in decisions.values() if a and b)), json_s=time.perf_counter() - t3)
     if world > 1:
         dist.barrier()
