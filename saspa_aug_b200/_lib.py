@@ -38,6 +38,9 @@ class Epilogue(Structure):
         ("ln_slots", c_int),
         ("ln_colsum", c_void_p),
         ("ln_eps", c_float),
+        ("gn_table", c_void_p),
+        ("gn_ld", c_int),
+        ("gn_act", c_int),
     ]
 
 
@@ -71,6 +74,8 @@ SIGNATURES = {
     ),
     "saspa_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, POINTER(Epilogue), _P]),
     "saspa_gemm_row_stats_slots": (c_int, [c_int]),
+    "saspa_groupnorm_table": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, c_int, _P, c_size_t, _P]),
+    "saspa_conv2d_gn_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "saspa_conv2d_igemm_bf16": (
         c_int,
         [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, POINTER(Epilogue), _P],

@@ -42,7 +42,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int XF_WARPS = 2;  // transform warps (GroupNorm + SiLU applied to the landed halo tiles of a 3x3 convolution)
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // column offset between the two accumulator buffers
@@ -90,6 +91,10 @@ struct GemmParams {
   // per-row partial statistics of THIS GEMM's bf16 output (the next LayerNorm's input): slot = 2 * n_tile + epilogue group
   float2* stats_out;
   int stats_slots;
+  // GroupNorm (+ SiLU) of the convolution's INPUT, applied to the halo tiles in shared memory (mode 2): table[img][ch] = (scale, shift)
+  const float2* gn_table;
+  int gn_ld;
+  int gn_act;
 };
 
 using namespace tcx;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tempty = bars + 22;  // (CTAS == 2: only the leader's are waited on)
   uint64_t* rfull = bars + 24;   // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
+  uint64_t* aready = bars + 34;  // [HALO_STAGES] halo tile normalised in place (GroupNorm fused into the convolution)
   float* sBias = reinterpret_cast<float*>(bars) + 128;  // [2][256]: the tile's bias slice, staged once per tile (512 B past the barriers)
   float* sColsum = sBias + 512;                         // [2][256]: the tile's slice of the LayerNorm column sums
 
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     for (int a = 0; a < HALO_STAGES; ++a) {
       mbar_init(&afull[a], 1);
       mbar_init(&aempty[a], 1);
+      mbar_init(&aready[a], XF_WARPS);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
         for (int cc = 0; cc < cchunks; ++cc) {
-          mbar_wait(&afull[sa], pa);
+          mbar_wait(p.gn_table ? &aready[sa] : &afull[sa], pa);
           tc_fence_after();
           const uint32_t halo = smem_u32(sHalo + sa * HALO_STAGE_BYTES);
 #pragma unroll 1
@@ -456,6 +463,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         }
         if (elect_one()) op_commit<CTAS>(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================== transform warps (10, 11): GroupNorm (+ SiLU) of the conv input, in the landed halo tile =====================
+    // The statistics come from a streaming pass (saspa_groupnorm_table); here every halo tile is normalised in place between the TMA
+    // landing (afull) and the MMAs (aready): y = silu(x * scale[img][ch] + shift[img][ch]).  One 23 KB tile feeds 36 MMAs (nine taps),
+    // so the transform is amortised nine-fold; pixels outside the image were zero-filled by TMA and STAY zero (the convolution pads the
+    // normalised tensor with zeros).  A lane owns one 16-byte channel octet (lane & 7) of every eighth pixel: its eight (scale, shift)
+    // pairs live in registers for the whole chunk.  SiLU as h + h * tanh(h), h = x / 2: one MUFU per element.
+    if (p.mode == 2 && p.gn_table != nullptr) {
+      const int xl = (warp - (2 + EPI_WARPS)) * 32 + lane;  // 0 .. 32 * XF_WARPS - 1
+      const int oct = xl & 7;
+      const bool silu = p.gn_act == SASPA_ACT_SILU;
+      const float pre = silu ? 0.5f : 1.0f;
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = cid; tile < total_tiles; tile += num_clusters) {
+        const int m_blk = tile_m(tile);
+        const int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
+        const int ty = r % p.tiles_y, tn = r / p.tiles_y;
+        const int x_lo = tx * HALO_BW - 1, y_lo = ty * HALO_BH - 1;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const float2* tb = p.gn_table + (size_t)tn * p.gn_ld + cc * BK + oct * 8;
+          float sc[8], sh[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + j));
+            sc[j] = t4.x * pre; sh[j] = t4.y * pre; sc[j + 1] = t4.z * pre; sh[j + 1] = t4.w * pre;
+          }
+          mbar_wait(&afull[sa], pa);
+          uint8_t* ts = sHalo + sa * HALO_STAGE_BYTES;
+#pragma unroll 2
+          for (int it = xl; it < HALO_ROWS * 8; it += 32 * XF_WARPS) {
+            const int row = it >> 3;
+            const int hy = row / (HALO_BW + 2), hx = row - hy * (HALO_BW + 2);
+            const int y = y_lo + hy, x = x_lo + hx;
+            if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+            uint4* ptr = reinterpret_cast<uint4*>(ts + row * 128 + ((oct ^ (row & 7)) << 4));
+            const uint4 u = *ptr;
+            float f[8];
+            f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+            f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float h = fmaf(f[j], sc[j], sh[j]);
+              if (silu) {
+                float th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                f[j] = fmaf(h, th, h);
+              } else {
+                f[j] = h;
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+            *ptr = o;
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aready[sa]);
+          if (++sa == HALO_STAGES) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
       }
     }
   } else {
@@ -966,7 +1038,7 @@ int dispatch(int bn, int ctas, const CUtensorMap& a0, const CUtensorMap& a1, con
 std::atomic<int> g_conv_impl{0};  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
 
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
-  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f};
+  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f, nullptr, 0, 0};
   if (!ep) ep = &kDefault;
   p.bias = ep->bias;
   p.row_bias = ep->row_bias;
@@ -988,6 +1060,12 @@ int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int l
   p.ln_slots = ep->ln_slots;
   p.ln_colsum = ep->ln_colsum;
   p.ln_eps = ep->ln_eps;
+  p.gn_table = static_cast<const float2*>(ep->gn_table);
+  p.gn_ld = ep->gn_ld;
+  p.gn_act = ep->gn_act;
+  SASPA_CHECK_ARG(!ep->gn_table || ((reinterpret_cast<uintptr_t>(ep->gn_table) & 15) == 0 && ep->gn_ld % 2 == 0 && ep->gn_ld > 0 &&
+                                    (ep->gn_act == SASPA_ACT_NONE || ep->gn_act == SASPA_ACT_SILU)),
+                  "epilogue: gn_table must be 16-byte aligned with an even gn_ld, gn_act NONE or SILU");
   SASPA_CHECK_ARG(!ep->row_stats_out || (!ep->out_fp32 && ep->act != SASPA_ACT_GEGLU && N % 32 == 0 && (reinterpret_cast<uintptr_t>(ep->row_stats_out) & 7) == 0),
                   "epilogue: row_stats_out needs a bf16, non-GEGLU output with N %% 32 == 0 (N=%d)", N);
   SASPA_CHECK_ARG(!ep->ln_stats || (ep->ln_colsum && ep->ln_slots > 0 && ep->ln_slots <= 64 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
@@ -1027,6 +1105,7 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, N, D, ldd);
   if (rc) return rc;
+  SASPA_CHECK_ARG(!p.gn_table, "saspa_gemm_bf16: gn_table is an option of the 3x3 convolution entry point");
   p.M = M;
   p.N = N;
   p.K = K;
@@ -1047,6 +1126,12 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
     if (p.residual && (rc = encode_2d(&tmR, p.residual, M, p.n_out, p.ld_res, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   return dispatch(bn, ctas, tmA, tmA, tmB, tmD, tmR, p, stream);
+}
+
+// 1 when the convolution can apply GroupNorm (+ SiLU) to its own input (saspa_epilogue.gn_table): the halo main loop of the 3x3 stride-1
+// "same" convolution on maps of at least 16 x 8 pixels, one source, channels a multiple of 64.
+extern "C" int saspa_conv2d_gn_fusable(int h, int w, int ksize, int stride, int c) {
+  return (ksize == 3 && stride == 1 && h >= HALO_BH && w >= HALO_BW && c % BK == 0 && g_conv_impl.load() != 1) ? 1 : 0;
 }
 
 // Slots per row of the partial row statistics a GEMM with N output columns writes (2 epilogue groups x N tiles; the tile width is
@@ -1113,6 +1198,11 @@ extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0,
     best_bw = HALO_BW;
     best_bh = HALO_BH;
     best_bi = 1;
+  }
+  if (p.gn_table && (!halo || (c0 + c1) % BK != 0 || c1 != 0 || p.gn_ld < c0)) {
+    saspa_set_error("saspa_conv2d_igemm_bf16: gn_table needs the halo main loop (3x3, stride 1, map >= 16 x 8) and one source with c %% 64 == 0 "
+                    "(see saspa_conv2d_gn_fusable)");
+    return SASPA_ERR_UNSUPPORTED;
   }
   p.mode = halo ? 2 : 1;
   p.n_img = n;
