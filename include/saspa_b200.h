@@ -80,6 +80,15 @@ int saspa_resize_pil_u8(const uint8_t* img, int n, int h, int w, int c, uint8_t*
 int saspa_rgb_to_luma3_u8(const uint8_t* img, long long pixels, uint8_t* out, cudaStream_t stream);
 int saspa_lpips_layer_accum(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* accum, cudaStream_t stream);
 
+/* HED conditioning (run_aug/run_aug.py:311-312, :438-439: controlnet_aux.HEDdetector.__call__, un-vendored): the detector's tail.
+ * side[k] (k = 0..4): the network's fp32 side outputs [n, side_h[k], side_w[k]] with a pixel stride of side_ld[k] floats (the 1x1
+ * projections' output rows).  Each is resized to H x W like cv2.resize(INTER_LINEAR) on a float map, the five are averaged (fp32,
+ * numpy's reduction order), edge = sigmoid (fp64); safe != 0 applies controlnet_aux's safe_step(edge, 2);
+ * out u8 [n, H, W, out_channels] (1 or 3 = HWC3 replication) = trunc(clip(edge * 255, 0, 255)).  `side` and the three int arrays are
+ * HOST arrays of five entries. */
+int saspa_hed_fuse_u8(const float* const* side, const int* side_h, const int* side_w, const int* side_ld, int n, int H, int W, int safe,
+                      uint8_t* out, int out_channels, cudaStream_t stream);
+
 /* u8 [n,h,w,3] -> crop -> (x/255 - mean[c]) / std[c] -> bf16 NHWC [n,crop_h,crop_w,out_c] (channels >= 3 zero padded) */
 int saspa_crop_normalize_bf16(const uint8_t* img, int n, int h, int w, int crop_y, int crop_x, int crop_h, int crop_w, float mean0,
                               float mean1, float mean2, float std0, float std1, float std2, void* out, int out_c,

@@ -115,6 +115,7 @@ SIGNATURES = {
     "saspa_clip_score_argmax": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P]),
     "saspa_rgb_to_luma3_u8": (c_int, [_P, ctypes.c_longlong, _P, _P]),
     "saspa_lpips_layer_accum": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "saspa_hed_fuse_u8": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
 }
 
 # kernel-selection overrides for tests / A-B timing (saspa_aug_b200/csrc/tuning_hooks.h): not part of the product ABI

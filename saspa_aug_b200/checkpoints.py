@@ -639,3 +639,33 @@ def random_lpips_state_dict(seed: int) -> Dict[str, torch.Tensor]:
         else:
             sd[name] = torch.randn(shape, generator=g) * (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
     return sd
+
+
+HED_BLOCKS = ((3, 64, 2), (64, 128, 2), (128, 256, 3), (256, 512, 3), (512, 512, 3))  # (in, out, convolutions) of block1..block5
+
+
+def hed_shapes() -> Shapes:
+    """State-dict layout of the ControlNet annotators' HED network (``ControlNetHED.pth``, loaded by controlnet_aux's
+    ``HEDdetector.from_pretrained``; run_aug/run_aug.py:311-312)."""
+    yield "norm", (1, 3, 1, 1)
+    for k, (cin, cout, layers) in enumerate(HED_BLOCKS, 1):
+        for i in range(layers):
+            yield from _conv(f"block{k}.convs.{i}", cin if i == 0 else cout, cout)
+        yield from _conv(f"block{k}.projection", cout, 1, 1)
+
+
+def random_hed_state_dict(seed: int) -> Dict[str, torch.Tensor]:
+    """He-normal trunk (ReLU net, activations keep the 0..255 input scale), projections scaled so that the five side outputs are
+    O(1) logits (a saturated sigmoid would hide every numerical difference), ``norm`` near the usual per-channel image mean."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in hed_shapes():
+        if name == "norm":
+            sd[name] = torch.tensor([123.7, 116.3, 103.5]).view(1, 3, 1, 1) + torch.randn(shape, generator=g)
+        elif ".projection." in name:
+            sd[name] = torch.randn(shape, generator=g) * (0.03 / shape[1] ** 0.5) if name.endswith("weight") else 0.2 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            sd[name] = 2.0 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = torch.randn(shape, generator=g) * (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+    return sd

@@ -572,3 +572,23 @@ def lpips_layer_accum(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, accum
     assert w.dtype == torch.float32 and w.numel() == c and accum.dtype == torch.float32 and accum.numel() == n
     check(_lib.load().saspa_lpips_layer_accum(_ptr(f0), _ptr(f1), _ptr(w), n, h * ww, c, _ptr(accum), _stream()), "saspa_lpips_layer_accum")
     _count()
+
+
+def hed_fuse(sides, H: int, W: int, safe: bool = False, out_channels: int = 3) -> torch.Tensor:
+    """Five fp32 side outputs [n,h_k,w_k,1] (the HED projections) -> u8 control map [n,H,W,out_channels]: cv2-style bilinear resize of
+    each to H x W, mean, sigmoid, (safe_step,) * 255 truncated (controlnet_aux HEDdetector.__call__)."""
+    import ctypes
+
+    assert len(sides) == 5
+    _need_cuda(*sides)
+    n = sides[0].shape[0]
+    for s in sides:
+        assert s.dtype == torch.float32 and s.dim() == 4 and s.shape[0] == n and s.shape[3] == 1 and s.is_contiguous()
+    out = torch.empty((n, H, W, out_channels), dtype=torch.uint8, device=sides[0].device)
+    ptrs = (ctypes.c_void_p * 5)(*[s.data_ptr() for s in sides])
+    hs = (ctypes.c_int * 5)(*[s.shape[1] for s in sides])
+    ws = (ctypes.c_int * 5)(*[s.shape[2] for s in sides])
+    lds = (ctypes.c_int * 5)(*[1] * 5)
+    check(_lib.load().saspa_hed_fuse_u8(ptrs, hs, ws, lds, n, int(H), int(W), 1 if safe else 0, _ptr(out), int(out_channels), _stream()), "saspa_hed_fuse_u8")
+    _count()
+    return out

@@ -1,4 +1,4 @@
-"""Sharded generation driver: host-side mirror of the reference's ``run_aug/run_aug.py`` for the ControlNet-canny path.
+"""Sharded generation driver: host-side mirror of the reference's ``run_aug/run_aug.py`` for the ControlNet (canny | hed) path.
 
 Kept from the reference (names / defaults / behaviour): the module-level constants as ``AugConfig`` fields
 (run_aug.py:513-577), ``init_pipeline`` (:128-230), ``pass_thorugh_pipe`` (:233-279), the output-folder and file naming
@@ -161,7 +161,8 @@ BASE_MODEL_DICT = {  # run_aug.py:53-62 (the entries whose ControlNet-canny pipe
     "sd_xl-turbo": "stabilityai/sdxl-turbo",
     "blip_diffusion": "Salesforce/blipdiffusion-controlnet",  # :181 -- the ControlNet flavour has its own repo, ControlNet included
 }
-CONTROLNET_DICT_SD = {"canny": "lllyasviel/control_v11p_sd15_canny"}        # :64-67
+CONTROLNET_DICT_SD = {"canny": "lllyasviel/control_v11p_sd15_canny", "hed": "lllyasviel/sd-controlnet-hed"}  # :64-67
+HED_ANNOTATOR = "lllyasviel/ControlNet"                                       # :312 HEDdetector.from_pretrained(...)
 CONTROLNET_DICT_SD_XL = {"canny": "diffusers/controlnet-canny-sdxl-1.0"}    # :69-72
 SDXL_VAE = "madebyollin/sdxl-vae-fp16-fix"                                    # :189
 
@@ -197,7 +198,9 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
                             sdxl_configs)
 
     assert sampler in ["ddim", "unipcmultistep"]
-    assert controlnet in ("canny",), "only the canny ControlNet is on the hot path"
+    assert controlnet in ("canny", "hed"), "ControlNet conditioning: canny | hed (run_aug.py:132)"
+    if controlnet == "hed" and base_model not in ("sd_v1.5", "tiny"):
+        raise KeyError(f"no HED ControlNet for {base_model!r} (run_aug.py:69-72 lists canny only for SD-XL; BLIP-Diffusion ships its canny ControlNet)")
     loaded = _local_checkpoints(base_model, controlnet, model_dirs) if state_dicts is None else None
     cfgs = loaded["configs"] if loaded else {}
     toks = {k: loaded.get(k) for k in ("tokenizer", "tokenizer_2")} if loaded else {}
@@ -234,8 +237,18 @@ def init_pipeline(base_model, controlnet, SDEdit, use_compile=False, sampler="dd
     if cfgs:
         kw = dict(unet_cfg=cfgs["unet"], vae_cfg=cfgs["vae"], text_cfg=cfgs["text"])
     smp = "unipc" if sampler == "unipcmultistep" else "ddim"
-    return SaspaControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sampler=smp, device=device, img2img=bool(SDEdit),
+    pipe = SaspaControlNetPipeline.from_state_dicts(sds["unet"], sds["controlnet"], sds["vae"], sds["text"], sampler=smp, device=device, img2img=bool(SDEdit),
                                                     tokenizer=toks.get("tokenizer"), **kw)
+    if controlnet == "hed":  # run_aug.py:311-312: the detector rides with the pipeline (generate() reads pipe.hed_detector)
+        from .hed import HEDdetector
+
+        if sds.get("hed") is not None:
+            pipe.hed_detector = HEDdetector.from_state_dict(sds["hed"], device)
+        elif loaded:
+            pipe.hed_detector = HEDdetector.from_pretrained(HED_ANNOTATOR, device=device)
+        else:
+            pipe.hed_detector = HEDdetector.from_state_dict(ck.random_hed_state_dict(4321), device)
+    return pipe
 
 
 def pass_thorugh_pipe(base_model, pipe, prompt, orig_img, SDEdit, SDEdit_strength, num_inference_steps, generator, guidance_scale, control_cond_scale,
@@ -482,6 +495,8 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts, out_dir: str, rank: int = 
     dev = pipe.device
     blip = "blip" in cfg.BASE_MODEL
     assert not (blip and cfg.SDEDIT), "BLIP-Diffusion has no img2img ControlNet pipeline in the reference (run_aug.py:185-187)"
+    if cfg.CONTROLNET == "hed" and getattr(pipe, "hed_detector", None) is None:
+        raise ValueError('CONTROLNET == "hed" needs pipe.hed_detector (init_pipeline(base_model, "hed", ...) attaches it)')
     do_cfg = cfg.GUIDANCE_SCALE > 1.0
     pool = ThreadPoolExecutor(max_workers=io_threads)
     loaders = ThreadPoolExecutor(max_workers=max(2, io_threads // 2))
@@ -525,7 +540,11 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts, out_dir: str, rank: int = 
                     saves.append((pool.submit(Image.fromarray(loaded[paths[u]]).save, src_out), None))
                 saved_sources.add(u)
             src_t = torch.from_numpy(np.stack([loaded[paths[u]] for u in uniq])).to(dev)
-            edges, ctrl = ops.canny(src_t, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, out_channels=3, want_ctrl=True)
+            if cfg.CONTROLNET == "hed":  # run_aug.py:438-439, once per source instead of once per prompt
+                edges = pipe.hed_detector.detect_batch(src_t)
+                ctrl = ops.crop_normalize(edges, 0, 0, src_t.shape[1], src_t.shape[2], (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), out_c=3)
+            else:
+                edges, ctrl = ops.canny(src_t, cfg.LOW_THRESHOLD_CANNY, cfg.HIGH_THRESHOLD_CANNY, out_channels=3, want_ctrl=True)
             sel = torch.tensor([uniq.index(w.index) for w in chunk], device=dev)
             for u_i, u in enumerate(uniq):
                 if u < 10:  # first 10 control images are saved (run_aug.py:441-442)
