@@ -136,13 +136,6 @@ typedef struct saspa_epilogue {
   int ln_slots;
   const float* ln_colsum;  /* fp32 [N]: sum_k B[j, k] of the bf16 weights */
   float ln_eps;
-  /* GroupNorm (+ SiLU) of the convolution's INPUT folded into the 3x3 implicit GEMM (diffusers ResnetBlock2D norm1/norm2 -> nonlinearity
-   * -> conv1/conv2, models/resnet.py): gn_table[img][ch] = (rstd * gamma, beta - mean * rstd * gamma) from saspa_groupnorm_table; the
-   * kernel normalises its halo tiles in shared memory (zero padding stays zero), so the normalised tensor never exists in HBM.
-   * Convolution entry points only, where saspa_conv2d_gn_fusable(...) == 1. */
-  const void* gn_table;    /* float2 [n, gn_ld] or NULL */
-  int gn_ld;               /* row stride of gn_table in float2 elements (>= c0) */
-  int gn_act;              /* SASPA_ACT_NONE | SASPA_ACT_SILU applied after the normalisation */
 } saspa_epilogue;
 
 /* D[M,N] = epilogue(A[M,K] . B[N,K]^T).  A, B bf16 row-major (K contiguous); lda/ldb/ldd in elements,
@@ -150,12 +143,6 @@ typedef struct saspa_epilogue {
  * saspa_geglu_interleave_rows semantics and D is [M, N/2]. */
 int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
                     const saspa_epilogue* ep_host, cudaStream_t stream);
-
-/* GroupNorm statistics only: x bf16 [n, hw, c] (pixel stride ldx) -> table float2 [n, ld_table]: (scale, shift) per image and channel
- * for saspa_epilogue.gn_table.  One streaming read of x; deterministic, batch invariant.  Workspace as saspa_groupnorm_nhwc_bf16. */
-int saspa_groupnorm_table(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma, const float* beta,
-                          void* table, int ld_table, void* stats_ws, size_t ws_bytes, cudaStream_t stream);
-int saspa_conv2d_gn_fusable(int h, int w, int ksize, int stride, int c);
 
 /* Slots per row of the partial statistics a GEMM with N output columns writes to row_stats_out (a function of N only, so that a
  * row's statistics do not depend on how many rows share the launch). */

@@ -38,9 +38,6 @@ class Epilogue(Structure):
         ("ln_slots", c_int),
         ("ln_colsum", c_void_p),
         ("ln_eps", c_float),
-        ("gn_table", c_void_p),
-        ("gn_ld", c_int),
-        ("gn_act", c_int),
     ]
 
 
@@ -74,8 +71,6 @@ SIGNATURES = {
     ),
     "saspa_gemm_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, POINTER(Epilogue), _P]),
     "saspa_gemm_row_stats_slots": (c_int, [c_int]),
-    "saspa_groupnorm_table": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, c_int, _P, c_size_t, _P]),
-    "saspa_conv2d_gn_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "saspa_conv2d_igemm_bf16": (
         c_int,
         [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, POINTER(Epilogue), _P],
@@ -119,7 +114,7 @@ SIGNATURES = {
 }
 
 # kernel-selection overrides for tests / A-B timing (saspa_aug_b200/csrc/tuning_hooks.h): not part of the product ABI
-TUNING_HOOKS = {name: (c_int, [c_int]) for name in ("saspa_attention_impl", "saspa_conv_impl", "saspa_groupnorm_impl", "saspa_gemm_force_ctas",
+TUNING_HOOKS = {name: (c_int, [c_int]) for name in ("saspa_attention_impl", "saspa_conv_impl", "saspa_groupnorm_impl", "saspa_gemm_force_ctas", "saspa_gemm_reverse_m",
                                                     "saspa_gemm_force_bn")}
 
 _lib = None

@@ -246,114 +246,6 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics only -> per-(image, channel) scale / shift table for a consumer that applies the normalisation itself
-// (the 3x3 implicit-GEMM convolution transforms its halo tiles in shared memory, gemm.cu): x is read ONCE (2 B / element) and the
-// normalised tensor never exists in HBM.  Same deterministic reduction as gn_fused_kernel's phase 1 (per-CTA partials over a pixel
-// range that depends on hw only); the LAST CTA of an image to arrive folds the partials in index order (double) and writes
-// table[img][ch] = (rstd * gamma, beta - mean * rstd * gamma) -- no CTA ever waits for another.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS) gn_table_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int c, int groups, float eps,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int ctas_per_img,
-                                                              int pix_per_cta, float2* __restrict__ partials, unsigned int* __restrict__ counters,
-                                                              float2* __restrict__ table, int ld_table) {
-  extern __shared__ float gn_smem[];  // [pix_par][c] sums + [pix_par][c] squares
-  __shared__ float s_stat[2 * 64];
-  __shared__ unsigned int s_last;
-  const int img = blockIdx.x / ctas_per_img, part = blockIdx.x % ctas_per_img;
-  const int p0 = part * pix_per_cta;
-  const int p1 = min(p0 + pix_per_cta, hw);
-  const int cv = c / 8;
-  const int pix_par = GN_THREADS / cv;
-  const int my_v = threadIdx.x % cv, my_p = threadIdx.x / cv;
-  const __nv_bfloat16* xi = x + (size_t)img * hw * ldx;
-  float* s_sum = gn_smem;
-  float* s_sq = gn_smem + (size_t)pix_par * c;
-  if (my_p < pix_par) {
-    float s[8], ss[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.0f;
-    const __nv_bfloat16* base = xi + my_v * 8;
-    int p = p0 + my_p;
-    for (; p + 3 * pix_par < p1; p += 4 * pix_par) {  // four loads in flight
-      uint4 u[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + k * pix_par) * ldx));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float f[8];
-        unpack8(u[k], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += f[j];
-          ss[j] = fmaf(f[j], f[j], ss[j]);
-        }
-      }
-    }
-    for (; p < p1; p += pix_par) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ldx));
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        ss[j] = fmaf(f[j], f[j], ss[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s_sum[my_p * c + my_v * 8 + j] = s[j];
-      s_sq[my_p * c + my_v * 8 + j] = ss[j];
-    }
-  }
-  __syncthreads();
-  const int cg = c / groups;
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int g = warp; g < groups; g += GN_THREADS / 32) {
-      float a = 0.0f, b = 0.0f;
-      for (int i = lane; i < pix_par * cg; i += 32) {
-        const int pp = i / cg, ch = g * cg + (i - pp * cg);
-        a += s_sum[pp * c + ch];
-        b += s_sq[pp * c + ch];
-      }
-      a = warp_sum(a);
-      b = warp_sum(b);
-      if (lane == 0) partials[((size_t)img * ctas_per_img + part) * groups + g] = make_float2(a, b);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = (atomicAdd(&counters[img], 1u) == (unsigned int)(ctas_per_img - 1)) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    double a = 0.0, b = 0.0;
-    for (int q = 0; q < ctas_per_img; ++q) {
-      const float2 v = __ldcg(&partials[((size_t)img * ctas_per_img + q) * groups + g]);
-      a += (double)v.x;
-      b += (double)v.y;
-    }
-    const double cnt = (double)hw * cg;
-    const double mean = a / cnt;
-    double var = b / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_stat[g] = (float)mean;
-    s_stat[64 + g] = (float)(1.0 / sqrt(var + (double)eps));
-  }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += GN_THREADS) {
-    const int g = ch / cg;
-    const float ga = gamma ? gamma[ch] : 1.0f, be = beta ? beta[ch] : 0.0f;
-    const float sc = s_stat[64 + g] * ga;
-    table[(size_t)img * ld_table + ch] = make_float2(sc, be - s_stat[g] * sc);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // GroupNorm, register-resident variant (every UNet / ControlNet level: hw <= ~8K pixels per image).
 // A CTA owns (image, channel slice, pixel part): a slice is a whole number of groups (and of 16-byte vectors), a part
 // is pix_par x GN_VPT pixels.  Every thread issues all of its <= GN_VPT 16-byte loads up front (memory-level
@@ -976,34 +868,6 @@ extern "C" int saspa_groupnorm_nhwc_bf16(const void* x, int ldx, int n, int hw, 
   }
   gn_fused_kernel<<<n * p.ctas_per_img, GN_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, eps, gamma, beta, act,
                                                                     static_cast<__nv_bfloat16*>(y), ldy, p.ctas_per_img, p.pix_per_cta, partials, counters);
-  SASPA_LAUNCH_CHECK();
-  return SASPA_OK;
-}
-
-extern "C" int saspa_groupnorm_table(const void* x, int ldx, int n, int hw, int c, int groups, float eps, const float* gamma, const float* beta,
-                                     void* table, int ld_table, void* stats_ws, size_t ws_bytes, cudaStream_t stream) {
-  SASPA_CHECK_ARG(n >= 0 && hw >= 0 && c > 0 && groups > 0 && groups <= 64 && c % groups == 0, "saspa_groupnorm_table: bad shape (c=%d groups=%d)", c, groups);
-  SASPA_CHECK_ARG(c % 8 == 0 && ldx % 8 == 0 && c <= 8 * GN_THREADS && ld_table >= c, "saspa_groupnorm_table: c, ldx must be multiples of 8, c <= %d, ld_table >= c", 8 * GN_THREADS);
-  if (n == 0 || hw == 0) return SASPA_OK;
-  SASPA_CHECK_ARG(x && table && stats_ws, "saspa_groupnorm_table: null pointer");
-  SASPA_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(table) & 7) == 0, "saspa_groupnorm_table: misaligned workspace / table");
-  const GnPlan p = gn_plan(n, hw, groups);
-  if (ws_bytes < p.total_bytes) {
-    saspa_set_error("saspa_groupnorm_table: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
-    return SASPA_ERR_WORKSPACE;
-  }
-  unsigned int* counters = reinterpret_cast<unsigned int*>(stats_ws);
-  float2* partials = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats_ws) + p.counters_bytes);
-  SASPA_CUDA(cudaMemsetAsync(counters, 0, (size_t)n * 4, stream));
-  const int pix_par = GN_THREADS / (c / 8);
-  const size_t smem = sizeof(float) * 2 * (size_t)(pix_par > 1 ? pix_par : 1) * c;
-  static size_t smem_configured = 0;
-  if (smem > 48 * 1024 && smem > smem_configured) {
-    SASPA_CUDA(cudaFuncSetAttribute(gn_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_configured = smem;
-  }
-  gn_table_kernel<<<n * p.ctas_per_img, GN_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, c, groups, eps, gamma, beta, p.ctas_per_img,
-                                                                    p.pix_per_cta, partials, counters, static_cast<float2*>(table), ld_table);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }

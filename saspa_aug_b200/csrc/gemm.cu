@@ -42,8 +42,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int EPI_WARPS = 8;
-constexpr int XF_WARPS = 2;  // transform warps (GroupNorm + SiLU applied to the landed halo tiles of a 3x3 convolution)
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
+constexpr int HELPER_WARPS = 2;  // one per epilogue group: issues the group's TMA stores and residual prefetches
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * HELPER_WARPS;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // column offset between the two accumulator buffers
@@ -91,10 +91,7 @@ struct GemmParams {
   // per-row partial statistics of THIS GEMM's bf16 output (the next LayerNorm's input): slot = 2 * n_tile + epilogue group
   float2* stats_out;
   int stats_slots;
-  // GroupNorm (+ SiLU) of the convolution's INPUT, applied to the halo tiles in shared memory (mode 2): table[img][ch] = (scale, shift)
-  const float2* gn_table;
-  int gn_ld;
-  int gn_act;
+  int m_rev;  // GEMM mode: row tiles in descending order
 };
 
 using namespace tcx;
@@ -157,7 +154,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // ---- operand loads / MMA / commit, one- and two-CTA flavours.  `bar` is a shared::cluster address: the CTA's own
 // barrier for CTAS == 1, the leader CTA's barrier (mapa rank 0) for CTAS == 2. ----
@@ -252,7 +248,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tempty = bars + 22;  // (CTAS == 2: only the leader's are waited on)
   uint64_t* rfull = bars + 24;   // [2 groups][NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * NBUF);
-  uint64_t* aready = bars + 34;  // [HALO_STAGES] halo tile normalised in place (GroupNorm fused into the convolution)
+  uint64_t* pfull = bars + 34;   // [2 groups][4] staging panel written by the group's four epilogue warps (-> store helper)
+  uint64_t* pfree = bars + 42;   // [2 groups][4] the store that read a staging panel has drained (store helper -> epilogue warps)
   float* sBias = reinterpret_cast<float*>(bars) + 128;  // [2][256]: the tile's bias slice, staged once per tile (512 B past the barriers)
   float* sColsum = sBias + 512;                         // [2][256]: the tile's slice of the LayerNorm column sums
 
@@ -265,7 +262,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const int total_tiles = ((p.num_m_tiles + CTAS - 1) / CTAS) * p.num_n_tiles;
   const int cchunks = (p.mode != 0) ? (p.c0 + p.c1 + BK - 1) / BK : 0;
   const int num_kb = (p.mode != 0) ? p.ksize * p.ksize * cchunks : (p.K + BK - 1) / BK;
-  auto tile_m = [&](int tile) { return (tile / p.num_n_tiles) * CTAS + (int)rank; };
+  // m_rev walks the row tiles from the last to the first: a GEMM that reads what the previous launch wrote front to back then starts on
+  // the rows that are still in L2
+  const int m_groups = (p.num_m_tiles + CTAS - 1) / CTAS;
+  auto tile_m = [&](int tile) {
+    const int g = tile / p.num_n_tiles;
+    return (p.m_rev ? m_groups - 1 - g : g) * CTAS + (int)rank;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -282,7 +285,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     for (int a = 0; a < HALO_STAGES; ++a) {
       mbar_init(&afull[a], 1);
       mbar_init(&aempty[a], 1);
-      mbar_init(&aready[a], XF_WARPS);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&pfull[i], 4);
+      mbar_init(&pfree[i], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -305,6 +311,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ---- staging-panel bookkeeping shared by the epilogue warps and their store helpers: group g owns panels k = g, g + 2, ... of a tile ----
+  const bool geglu = (p.act == SASPA_ACT_GEGLU);
+  const int out_bn = geglu ? BN / 2 : BN;
+  const int NP = out_bn / PANEL;
+  auto panel_valid = [&](int tile, int k) { return (tile % p.num_n_tiles) * out_bn + k * PANEL < p.n_out; };
+  auto panel_next = [&](int& tile, int& k, int g) {  // next valid (tile, panel) of group g; tile >= total_tiles at the end
+    for (;;) {
+      k += 2;
+      if (k >= NP) {
+        tile += num_clusters;
+        k = g;
+        if (tile >= total_tiles) return;
+      }
+      if (k < NP && panel_valid(tile, k)) return;
+    }
+  };
+  auto panel_coords = [&](int tile, int k, int& col, int& c1, int& c2, int& c3) {
+    const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
+    col = n_blk * out_bn + k * PANEL;
+    if (p.mode == 0) {
+      c1 = m_blk * BM;
+      c2 = c3 = 0;
+    } else {
+      int tx = m_blk % p.tiles_x, rr = m_blk / p.tiles_x;
+      int ty = rr % p.tiles_y, tn = rr / p.tiles_y;
+      c1 = tx * p.bw;
+      c2 = ty * p.bh;
+      c3 = tn * p.bn;
+    }
+  };
+  auto issue_res_load = [&](int tile, int k, uint8_t* dst, uint64_t* bar) {
+    int col, c1, c2, c3;
+    panel_coords(tile, k, col, c1, c2, c3);
+    mbar_expect_tx(bar, PANEL_BYTES);
+    if (p.mode == 0)
+      tma_load_2d(&tmR, dst, bar, col, c1);
+    else
+      tma_load_4d(&tmR, dst, bar, col, c1, c2, c3);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA fills its own smem; completion lands on the leader's barrier) =====================
@@ -406,7 +452,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
         for (int cc = 0; cc < cchunks; ++cc) {
-          mbar_wait(p.gn_table ? &aready[sa] : &afull[sa], pa);
+          mbar_wait(&afull[sa], pa);
           tc_fence_after();
           const uint32_t halo = smem_u32(sHalo + sa * HALO_STAGE_BYTES);
 #pragma unroll 1
@@ -466,136 +512,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else if (warp >= 2 + EPI_WARPS) {
-    // ===================== transform warps (10, 11): GroupNorm (+ SiLU) of the conv input, in the landed halo tile =====================
-    // The statistics come from a streaming pass (saspa_groupnorm_table); here every halo tile is normalised in place between the TMA
-    // landing (afull) and the MMAs (aready): y = silu(x * scale[img][ch] + shift[img][ch]).  One 23 KB tile feeds 36 MMAs (nine taps),
-    // so the transform is amortised nine-fold; pixels outside the image were zero-filled by TMA and STAY zero (the convolution pads the
-    // normalised tensor with zeros).  A lane owns one 16-byte channel octet (lane & 7) of every eighth pixel: its eight (scale, shift)
-    // pairs live in registers for the whole chunk.  SiLU as h + h * tanh(h), h = x / 2: one MUFU per element.
-    if (p.mode == 2 && p.gn_table != nullptr) {
-      const int xl = (warp - (2 + EPI_WARPS)) * 32 + lane;  // 0 .. 32 * XF_WARPS - 1
-      const int oct = xl & 7;
-      const bool silu = p.gn_act == SASPA_ACT_SILU;
-      const float pre = silu ? 0.5f : 1.0f;
-      int sa = 0;
-      uint32_t pa = 0;
-      for (int tile = cid; tile < total_tiles; tile += num_clusters) {
-        const int m_blk = tile_m(tile);
-        const int tx = m_blk % p.tiles_x, r = m_blk / p.tiles_x;
-        const int ty = r % p.tiles_y, tn = r / p.tiles_y;
-        const int x_lo = tx * HALO_BW - 1, y_lo = ty * HALO_BH - 1;
-        for (int cc = 0; cc < cchunks; ++cc) {
-          const float2* tb = p.gn_table + (size_t)tn * p.gn_ld + cc * BK + oct * 8;
-          float sc[8], sh[8];
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + j));
-            sc[j] = t4.x * pre; sh[j] = t4.y * pre; sc[j + 1] = t4.z * pre; sh[j + 1] = t4.w * pre;
-          }
-          mbar_wait(&afull[sa], pa);
-          uint8_t* ts = sHalo + sa * HALO_STAGE_BYTES;
-#pragma unroll 2
-          for (int it = xl; it < HALO_ROWS * 8; it += 32 * XF_WARPS) {
-            const int row = it >> 3;
-            const int hy = row / (HALO_BW + 2), hx = row - hy * (HALO_BW + 2);
-            const int y = y_lo + hy, x = x_lo + hx;
-            if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
-            uint4* ptr = reinterpret_cast<uint4*>(ts + row * 128 + ((oct ^ (row & 7)) << 4));
-            const uint4 u = *ptr;
-            float f[8];
-            f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-            f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float h = fmaf(f[j], sc[j], sh[j]);
-              if (silu) {
-                float th;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                f[j] = fmaf(h, th, h);
-              } else {
-                f[j] = h;
-              }
-            }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-            *ptr = o;
-          }
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&aready[sa]);
-          if (++sa == HALO_STAGES) {
-            sa = 0;
-            pa ^= 1;
-          }
+    // ===================== store helpers (warps 10, 11): one per epilogue group =====================
+    // All of a group's TMA traffic is issued here -- the bf16 output panels and the residual prefetch -- so that no epilogue warp ever
+    // waits for another one: an epilogue warp fills its 32 rows of a staging panel and arrives on the panel's `pfull` barrier (count 4);
+    // this warp waits for the four arrivals, issues the store and recycles the buffer, either by loading the next residual panel into
+    // it (its `rfull` barrier then tells the epilogue warps the buffer is theirs again) or by arriving on `pfree` once the store has
+    // drained.  (With the group leader issuing, the other three warps of a group sat at a barrier for the leader's bookkeeping on every
+    // panel: 28 % of the epilogue warps' time on the K = 320 GEMMs, profiles/r2_smallk_gemm_epilogue.txt.)
+    const int grp = warp - (2 + EPI_WARPS);
+    if (p.tma_store) {
+      const bool tma_res = p.residual != nullptr;
+      uint8_t* stg = sStage + grp * NBUF * PANEL_BYTES;
+      uint64_t* rf = rfull + grp * NBUF;
+      uint64_t* pf = pfull + grp * 4;
+      uint64_t* fr = pfree + grp * 4;
+      int pf_tile = cid, pf_k = grp - 2, pf_n = 0;  // residual prefetch cursor
+      if (tma_res) {
+        panel_next(pf_tile, pf_k, grp);
+        for (int i = 0; i < PD && pf_tile < total_tiles; ++i) {
+          if (lane == 0) issue_res_load(pf_tile, pf_k, stg + (pf_n % NBUF) * PANEL_BYTES, &rf[pf_n % NBUF]);
+          ++pf_n;
+          panel_next(pf_tile, pf_k, grp);
         }
       }
+      int s_tile = cid, s_k = grp - 2;  // store cursor
+      panel_next(s_tile, s_k, grp);
+      int n = 0, freed = 0;
+      constexpr int KEEP = NBUF >= 2 ? NBUF - 2 : 0;  // stores that may still be reading their panel after the wait below
+      while (s_tile < total_tiles) {
+        const int buf = n % NBUF;
+        if (tma_res && pf_tile < total_tiles) {
+          // panel n + PD reuses the buffer of store n + PD - NBUF, which must have drained
+          if (lane == 0) {
+            bulk_wait_read<NBUF - PD - 1>();
+            issue_res_load(pf_tile, pf_k, stg + (pf_n % NBUF) * PANEL_BYTES, &rf[pf_n % NBUF]);
+          }
+          ++pf_n;
+          panel_next(pf_tile, pf_k, grp);
+        }
+        mbar_wait(&pf[buf], (uint32_t)(n / NBUF) & 1u);
+        if (lane == 0) {
+          int col, c1, c2, c3;
+          panel_coords(s_tile, s_k, col, c1, c2, c3);
+          if (p.mode == 0)
+            tma_store_2d(&tmD, stg + buf * PANEL_BYTES, col, c1);
+          else
+            tma_store_4d(&tmD, stg + buf * PANEL_BYTES, col, c1, c2, c3);
+          bulk_commit();
+          if (!tma_res) {
+            bulk_wait_read<KEEP>();  // stores <= n - KEEP have drained
+            for (; freed <= n - KEEP; ++freed) mbar_arrive(&fr[freed % NBUF]);
+          }
+        }
+        ++n;
+        panel_next(s_tile, s_k, grp);
+        __syncwarp();
+      }
+      if (lane == 0) bulk_wait_read<0>();  // staging panels must outlive the stores that read them
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int grp = (warp - 2) >> 2;  // epilogue group: owns panels k = grp, grp + 2, ...
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;      // accumulator row of this thread
-    const bool leader = (warp == 2 + 4 * grp) && lane == 0;
-    const bool geglu = (p.act == SASPA_ACT_GEGLU);
-    const int out_bn = geglu ? BN / 2 : BN;
-    const int NP = out_bn / PANEL;
     uint8_t* stg = sStage + grp * NBUF * PANEL_BYTES;
     uint64_t* rf = rfull + grp * NBUF;
+    uint64_t* pf = pfull + grp * 4;
+    uint64_t* fr = pfree + grp * 4;
     const uint32_t row_off = (uint32_t)r * 64u;
     const uint32_t row_swz = (uint32_t)(r >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
     const bool use_tma = p.tma_store != 0;
     const bool tma_res = use_tma && p.residual != nullptr;
 
-    // (tile, k) sequence of this group's valid panels
-    auto panel_valid = [&](int tile, int k) { return (tile % p.num_n_tiles) * out_bn + k * PANEL < p.n_out; };
-    auto panel_next = [&](int& tile, int& k) {
-      for (;;) {
-        k += 2;
-        if (k >= NP) {
-          tile += num_clusters;
-          k = grp;
-          if (tile >= total_tiles) return;
-        }
-        if (k < NP && panel_valid(tile, k)) return;
-      }
-    };
-    auto panel_coords = [&](int tile, int k, int& col, int& c1, int& c2, int& c3) {
-      const int m_blk = tile_m(tile), n_blk = tile % p.num_n_tiles;
-      col = n_blk * out_bn + k * PANEL;
-      if (p.mode == 0) {
-        c1 = m_blk * BM;
-        c2 = c3 = 0;
-      } else {
-        int tx = m_blk % p.tiles_x, rr = m_blk / p.tiles_x;
-        int ty = rr % p.tiles_y, tn = rr / p.tiles_y;
-        c1 = tx * p.bw;
-        c2 = ty * p.bh;
-        c3 = tn * p.bn;
-      }
-    };
-    auto issue_res_load = [&](int tile, int k, int buf) {
-      int col, c1, c2, c3;
-      panel_coords(tile, k, col, c1, c2, c3);
-      mbar_expect_tx(&rf[buf], PANEL_BYTES);
-      if (p.mode == 0)
-        tma_load_2d(&tmR, stg + buf * PANEL_BYTES, &rf[buf], col, c1);
-      else
-        tma_load_4d(&tmR, stg + buf * PANEL_BYTES, &rf[buf], col, c1, c2, c3);
-    };
-
-    // residual prefetch state (leader only)
-    int pf_tile = cid, pf_k = grp - 2, pf_n = 0;
-    if (tma_res && leader) {
-      panel_next(pf_tile, pf_k);
-      for (int i = 0; i < PD && pf_tile < total_tiles; ++i) {
-        issue_res_load(pf_tile, pf_k, pf_n % NBUF);
-        ++pf_n;
-        panel_next(pf_tile, pf_k);
-      }
-    }
-
     int n_seq = 0;  // panels processed by this group so far
     int it = 0;
+    int bias_n_blk = -1, bias_buf = 0;
+    // Folded LayerNorm with four statistics slots per row (a 320-wide producer): the row's partial sums are fetched ONE TILE AHEAD.  At
+    // that width the epilogue is the critical path (K = 320 gives the tensor core 1600 clk of work per tile), the accumulator is ready
+    // when a tile starts and the L2 latency of the loads used to be exposed on every tile.
+    const bool ln_ahead = p.ln_stats != nullptr && p.ln_slots == 4 && p.mode == 0 && (reinterpret_cast<uintptr_t>(p.ln_stats) & 15) == 0;
+    float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+    auto ln_fetch = [&](int tile) {
+      const long long row = (long long)tile_m(tile) * BM + r;
+      if (row < p.M) {
+        const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)row * 4);
+        pre0 = __ldg(sp);
+        pre1 = __ldg(sp + 1);
+      }
+    };
+    if (ln_ahead && cid < total_tiles) ln_fetch(cid);
     for (int tile = cid; tile < total_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -621,30 +626,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int col_base_out = n_blk * out_bn;  // column in the output
       // the bias slice of this tile goes through shared memory: its global-load latency is paid once per tile, off the
       // accumulator-drain path (it used to stall every panel).  Two buffers: nobody runs more than a tile ahead.
-      float* sb = sBias + (it & 1) * 256;
-      float* sc = sColsum + (it & 1) * 256;
-      if (p.bias || p.ln_colsum) {
+      // It is reloaded only when the CTA moves to another N tile (with 148 CTAs and an even number of N tiles: never after the
+      // first tile), so the barrier below is off the steady-state path.  Safe with two buffers: a warp that is still on the previous
+      // tile reads the other buffer, and nobody is more than one reload behind (the barrier).
+      if ((p.bias || p.ln_colsum) && n_blk != bias_n_blk) {
+        bias_n_blk = n_blk;
+        bias_buf ^= 1;
         const int t = (int)threadIdx.x - 64;
         if (t < BN) {
-          if (p.bias) sb[t] = (col_base_in + t < p.N) ? __ldg(p.bias + col_base_in + t) : 0.0f;
-          if (p.ln_colsum) sc[t] = (col_base_in + t < p.N) ? __ldg(p.ln_colsum + col_base_in + t) : 0.0f;
+          if (p.bias) sBias[bias_buf * 256 + t] = (col_base_in + t < p.N) ? __ldg(p.bias + col_base_in + t) : 0.0f;
+          if (p.ln_colsum) sColsum[bias_buf * 256 + t] = (col_base_in + t < p.N) ? __ldg(p.ln_colsum + col_base_in + t) : 0.0f;
         }
         asm volatile("bar.sync 3, 256;" ::: "memory");
       }
+      const float* sb = sBias + bias_buf * 256;
+      const float* sc = sColsum + bias_buf * 256;
       // folded LayerNorm: this row's mean / rstd from the producer's partials, summed in slot order (fixed => batch invariant);
       // the loads are in flight while the accumulator is still being produced
       float ln_mean = 0.0f, ln_rstd = 1.0f;
       if (p.ln_stats && row_ok) {
-        const float2* sp = p.ln_stats + (size_t)pix * p.ln_slots;
         float a = 0.0f, b = 0.0f;
-        for (int s2 = 0; s2 < p.ln_slots; ++s2) {
-          const float2 v2 = __ldg(sp + s2);
-          a += v2.x;
-          b += v2.y;
+        if (ln_ahead) {  // fetched while the previous tile drained; same summation order as the loop below
+          a = ((pre0.x + pre0.z) + pre1.x) + pre1.z;
+          b = ((pre0.y + pre0.w) + pre1.y) + pre1.w;
+        } else {
+          const float2* sp = p.ln_stats + (size_t)pix * p.ln_slots;
+          for (int s2 = 0; s2 < p.ln_slots; ++s2) {
+            const float2 v2 = __ldg(sp + s2);
+            a += v2.x;
+            b += v2.y;
+          }
         }
         ln_mean = a * p.ln_inv_k;
         ln_rstd = rsqrtf(fmaxf(b * p.ln_inv_k - ln_mean * ln_mean, 0.0f) + p.ln_eps);
       }
+      if (ln_ahead && tile + num_clusters < total_tiles) ln_fetch(tile + num_clusters);
       float st_sum = 0.0f, st_sq = 0.0f;  // row statistics of this tile's bf16 output (p.stats_out)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -732,14 +748,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int buf = n_seq % NBUF;
           uint8_t* pbuf = stg + buf * PANEL_BYTES + row_off;
           if (tma_res) {
-            if (leader && pf_tile < total_tiles) {
-              // panel n_seq + PD reuses the buffer of store n_seq + PD - NBUF, which must have drained
-              bulk_wait_read<NBUF - PD - 1>();
-              issue_res_load(pf_tile, pf_k, pf_n % NBUF);
-              ++pf_n;
-              panel_next(pf_tile, pf_k);
-            }
-            mbar_wait(&rf[buf], (uint32_t)(n_seq / NBUF) & 1u);
+            mbar_wait(&rf[buf], (uint32_t)(n_seq / NBUF) & 1u);  // the residual panel has landed (=> the buffer's last store drained)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const uint4 u = *reinterpret_cast<const uint4*>(pbuf + ((c ^ row_swz) << 4));
@@ -749,6 +758,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               f[j + 4] += p.beta * bf16_lo(u.z); f[j + 5] += p.beta * bf16_hi(u.z);
               f[j + 6] += p.beta * bf16_lo(u.w); f[j + 7] += p.beta * bf16_hi(u.w);
             }
+          } else if (n_seq >= NBUF) {
+            mbar_wait(&fr[buf], (uint32_t)(n_seq / NBUF - 1) & 1u);  // the store that last read this buffer has drained
           }
           if (p.act_post) {
 #pragma unroll
@@ -765,20 +776,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             *reinterpret_cast<uint4*>(pbuf + ((c ^ row_swz) << 4)) = u;
           }
           if (p.stats_out) row_stats_add(f, st_sum, st_sq);
-          fence_proxy_async_smem();
-          // after this barrier every thread knows stores <= n_seq - NBUF + 1 have drained their panel
-          if (leader && !tma_res) bulk_wait_read<(NBUF >= 2 ? NBUF - 2 : 0)>();
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store the helper warp issues
           __syncwarp();
-          group_bar(1 + grp);
-          if (leader) {
-            int col, c1, c2, c3;
-            panel_coords(tile, k, col, c1, c2, c3);
-            if (p.mode == 0)
-              tma_store_2d(&tmD, stg + buf * PANEL_BYTES, col, c1);
-            else
-              tma_store_4d(&tmD, stg + buf * PANEL_BYTES, col, c1, c2, c3);
-            bulk_commit();
-          }
+          if (lane == 0) mbar_arrive(&pf[buf]);
           ++n_seq;
           continue;
         }
@@ -845,7 +845,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
     }
-    if (use_tma && leader) bulk_wait_read<0>();  // staging panels must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -990,7 +989,13 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_
     }
     return best;
   }
-  if (N % 160 == 0 && N % 256 != 0) return 160;
+  if (N % 160 == 0 && N % 256 != 0) {
+    // 160 tiles N exactly, but the wider tile moves fewer operand bytes per flop (these launches run at the L2 -> SM bandwidth:
+    // (BM + BN) * 128 B per 2 * BM * BN * 64 flop): once the padding of the last 256-wide tile is under 1/12 of N the wide tile wins
+    // -- N = 960 / 1920 (the fused q|k|v projections), measured 282 -> 222 us and 190 -> 157 us (profiles/r2_gemm_shape_sweep.txt)
+    const int padded = ceil_div(N, 256) * 256 - N;
+    return padded * 12 <= N ? 256 : 160;
+  }
   if (N <= 128) return 128;
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
@@ -1006,6 +1011,7 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_
   return best;
 }
 
+std::atomic<int> g_reverse_m{0};   // tuning hook (saspa_gemm_reverse_m): 1 = GEMM row tiles in descending order
 std::atomic<int> g_force_ctas{0};  // tuning hook (saspa_gemm_force_ctas): 0 = heuristic, 1 / 2 = CTAs per tile
 
 // Two-CTA tiles (cta_group::2, 256 x BN): measured +14% at BN = 256 and +9% at BN = 160 on the plain GEMM main loop, a loss
@@ -1038,7 +1044,7 @@ int dispatch(int bn, int ctas, const CUtensorMap& a0, const CUtensorMap& a1, con
 std::atomic<int> g_conv_impl{0};  // 0 auto, 1 per-tap boxes only, 2 halo only (tests / A-B timing)
 
 int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int ldd) {
-  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f, nullptr, 0, 0};
+  static const saspa_epilogue kDefault = {nullptr, nullptr, 1, 0, SASPA_ACT_NONE, 1.0f, nullptr, 0, 0.0f, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0.0f};
   if (!ep) ep = &kDefault;
   p.bias = ep->bias;
   p.row_bias = ep->row_bias;
@@ -1060,12 +1066,6 @@ int fill_epilogue(GemmParams& p, const saspa_epilogue* ep, int N, void* D, int l
   p.ln_slots = ep->ln_slots;
   p.ln_colsum = ep->ln_colsum;
   p.ln_eps = ep->ln_eps;
-  p.gn_table = static_cast<const float2*>(ep->gn_table);
-  p.gn_ld = ep->gn_ld;
-  p.gn_act = ep->gn_act;
-  SASPA_CHECK_ARG(!ep->gn_table || ((reinterpret_cast<uintptr_t>(ep->gn_table) & 15) == 0 && ep->gn_ld % 2 == 0 && ep->gn_ld > 0 &&
-                                    (ep->gn_act == SASPA_ACT_NONE || ep->gn_act == SASPA_ACT_SILU)),
-                  "epilogue: gn_table must be 16-byte aligned with an even gn_ld, gn_act NONE or SILU");
   SASPA_CHECK_ARG(!ep->row_stats_out || (!ep->out_fp32 && ep->act != SASPA_ACT_GEGLU && N % 32 == 0 && (reinterpret_cast<uintptr_t>(ep->row_stats_out) & 7) == 0),
                   "epilogue: row_stats_out needs a bf16, non-GEGLU output with N %% 32 == 0 (N=%d)", N);
   SASPA_CHECK_ARG(!ep->ln_stats || (ep->ln_colsum && ep->ln_slots > 0 && ep->ln_slots <= 64 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
@@ -1105,11 +1105,11 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
   GemmParams p = {};
   int rc = fill_epilogue(p, ep, N, D, ldd);
   if (rc) return rc;
-  SASPA_CHECK_ARG(!p.gn_table, "saspa_gemm_bf16: gn_table is an option of the 3x3 convolution entry point");
   p.M = M;
   p.N = N;
   p.K = K;
   p.mode = 0;
+  p.m_rev = g_reverse_m.load();
   p.num_m_tiles = ceil_div(M, BM);
   const int bn = pick_bn(N, p.act, p.num_m_tiles, K >= 2048, p.stats_out != nullptr);
   p.num_n_tiles = ceil_div(N, bn);
@@ -1126,12 +1126,6 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
     if (p.residual && (rc = encode_2d(&tmR, p.residual, M, p.n_out, p.ld_res, BM, PANEL, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   return dispatch(bn, ctas, tmA, tmA, tmB, tmD, tmR, p, stream);
-}
-
-// 1 when the convolution can apply GroupNorm (+ SiLU) to its own input (saspa_epilogue.gn_table): the halo main loop of the 3x3 stride-1
-// "same" convolution on maps of at least 16 x 8 pixels, one source, channels a multiple of 64.
-extern "C" int saspa_conv2d_gn_fusable(int h, int w, int ksize, int stride, int c) {
-  return (ksize == 3 && stride == 1 && h >= HALO_BH && w >= HALO_BW && c % BK == 0 && g_conv_impl.load() != 1) ? 1 : 0;
 }
 
 // Slots per row of the partial row statistics a GEMM with N output columns writes (2 epilogue groups x N tiles; the tile width is
@@ -1199,11 +1193,6 @@ extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0,
     best_bh = HALO_BH;
     best_bi = 1;
   }
-  if (p.gn_table && (!halo || (c0 + c1) % BK != 0 || c1 != 0 || p.gn_ld < c0)) {
-    saspa_set_error("saspa_conv2d_igemm_bf16: gn_table needs the halo main loop (3x3, stride 1, map >= 16 x 8) and one source with c %% 64 == 0 "
-                    "(see saspa_conv2d_gn_fusable)");
-    return SASPA_ERR_UNSUPPORTED;
-  }
   p.mode = halo ? 2 : 1;
   p.n_img = n;
   p.H = h;
@@ -1264,6 +1253,12 @@ extern "C" int saspa_gemm_force_bn(int bn) {
 }
 
 // Tuning hook: force one- or two-CTA tiles (0 restores the heuristic).  Not part of the product API.
+extern "C" int saspa_gemm_reverse_m(int on) {
+  const int prev = g_reverse_m.load();
+  if (on == 0 || on == 1) g_reverse_m = on;
+  return prev;
+}
+
 extern "C" int saspa_gemm_force_ctas(int ctas) {
   const int prev = g_force_ctas.load();
   if (ctas >= 0 && ctas <= 2) g_force_ctas = ctas;

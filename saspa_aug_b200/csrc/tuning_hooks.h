@@ -11,6 +11,9 @@ extern "C" {
 int saspa_conv_impl(int impl);
 /* CTAs per output tile of the tcgen05 GEMM / conv kernel: 0 auto, 1 single-CTA tiles, 2 cta_group::2 pairs */
 int saspa_gemm_force_ctas(int ctas);
+/* GEMM row tiles walked last to first (1) instead of first to last (0): an A operand written front to back by the previous launch is
+ * then read starting with the rows still in L2.  Same results, different tile order. */
+int saspa_gemm_reverse_m(int on);
 /* N tile width of the non-GEGLU GEMM kernels: 0 auto, or 32 / 64 / 128 / 160 / 256 */
 int saspa_gemm_force_bn(int bn);
 /* GroupNorm: 0 auto, 1 two-pass kernel only */

@@ -125,13 +125,7 @@ class ResnetBlock:
             self.temb_slice = (off, off + self.conv1.cout)
 
     def _norm_conv(self, x: torch.Tensor, norm: "Norm", conv: "Conv", **epi) -> torch.Tensor:
-        """conv(silu(GroupNorm(x))).  Where the 3x3 implicit GEMM runs its halo main loop, only the STATISTICS are a kernel of their own
-        (one streaming read): the convolution normalises its own halo tiles in shared memory (north_star: GroupNorm + SiLU fused into
-        the contraction); elsewhere (8x8 maps, odd channel counts) the stand-alone GroupNorm kernel runs first."""
         n, h, w, c = x.shape
-        if FUSE_GROUPNORM and conv.direct and ops.conv_gn_fusable(h, w, conv.k, 1, c):
-            table = ops.groupnorm_table(pix3d(x), self.groups, self.eps, norm.g, norm.b)
-            return conv(x, gn_table=table, gn_act=ACT_SILU, **epi)
         a = ops.groupnorm(pix3d(x), self.groups, self.eps, norm.g, norm.b, ACT_SILU).view(n, h, w, c)
         return conv(a, **epi)
 
@@ -142,10 +136,6 @@ class ResnetBlock:
         return self._norm_conv(h1, self.norm2, self.conv2, out=out, residual=res, beta=1.0)
 
 
-# GroupNorm + SiLU applied inside the consuming 3x3 convolution (statistics as a streaming pass, gemm.cu's transform warps normalise the
-# halo tiles).  Correct (tests/test_gemm_gpu.py) but OFF by default: with two transform warps the convolutions run 1.3-1.5x longer
-# (UNet+ControlNet step 105.2 ms against 93.5 ms, profiles/r2_gn_conv_fusion_experiment.txt) for 1.4 ms of GroupNorm time saved.
-FUSE_GROUPNORM = os.environ.get("SASPA_FUSE_GN", "0") == "1"
 FOLD_LAYERNORM = os.environ.get("SASPA_FOLD_LN", "1") != "0"  # A/B switch for tools and tests; the product default is the folded path
 
 

@@ -82,11 +82,8 @@ def canny(img: torch.Tensor, low: int, high: int, out_channels: int = 1, want_ct
 # GEMM / conv
 # ------------------------------------------------------------------------------------------------
 def make_epilogue(bias=None, row_bias=None, rows_per_group=1, act=ACT_NONE, alpha=1.0, residual=None, ld_res=0, beta=1.0, out_fp32=False,
-                  act_after_residual=False, row_stats_out=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5, gn_table=None, gn_act=ACT_NONE):
+                  act_after_residual=False, row_stats_out=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5):
     ep = Epilogue()
-    ep.gn_table = _ptr(gn_table)
-    ep.gn_ld = int(gn_table.stride(0)) // 2 if gn_table is not None else 0  # in (scale, shift) pairs
-    ep.gn_act = int(gn_act)
     ep.row_stats_out = _ptr(row_stats_out)
     ep.row_stats_slots = int(row_stats_out.shape[1]) if row_stats_out is not None else 0
     ep.ln_stats = _ptr(ln_stats)
@@ -147,31 +144,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     return (out, stats) if row_stats else out
 
 
-def conv_gn_fusable(h: int, w: int, ksize: int, stride: int, c: int) -> bool:
-    """True when conv2d_igemm can apply GroupNorm (+ SiLU) to its own input (``gn_table=``)."""
-    return bool(_lib.load().saspa_conv2d_gn_fusable(int(h), int(w), int(ksize), int(stride), int(c)))
-
-
-def groupnorm_table(x: torch.Tensor, groups: int, eps: float, gamma, beta) -> torch.Tensor:
-    """x bf16 [n, hw, c] view -> fp32 [n, c, 2]: (scale, shift) per image and channel = (rstd * gamma, beta - mean * rstd * gamma).
-    The statistics pass of a GroupNorm whose application is folded into the consuming 3x3 convolution."""
-    _need_cuda(x)
-    n, hw, c = x.shape
-    assert x.dtype == BF16 and x.stride(2) == 1 and x.stride(0) == hw * x.stride(1)
-    lib = _lib.load()
-    ws_bytes = lib.saspa_groupnorm_workspace_bytes(n, hw, groups)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    table = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
-    check(lib.saspa_groupnorm_table(_ptr(x), x.stride(1), n, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta), _ptr(table), c, _ptr(ws), ws_bytes, _stream()),
-          "saspa_groupnorm_table")
-    _count(1)
-    return table
-
-
 def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optional[torch.Tensor] = None, *, x1: Optional[torch.Tensor] = None,
                  bias=None, row_bias=None, act=ACT_NONE, alpha=1.0, residual=None, beta=1.0, out_fp32=False, act_after_residual=False,
-                 stride: int = 1, pad: Optional[int] = None, out_hw: Optional[tuple] = None, gn_table: Optional[torch.Tensor] = None,
-                 gn_act: int = ACT_NONE) -> torch.Tensor:
+                 stride: int = 1, pad: Optional[int] = None, out_hw: Optional[tuple] = None) -> torch.Tensor:
     """Implicit-GEMM conv on NHWC bf16 views [n,h,w,c] (channel stride 1, dense n/h/w strides); weight bf16 [cout, ksize*ksize*(c0+c1)].
     Default: stride 1, "same" padding.  stride 2 / explicit top-left ``pad`` / ``out_hw`` = (oh, ow): taps outside the input read zeros."""
     _need_cuda(x, weight)
@@ -192,10 +167,7 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(3) == 1 and residual.stride(1) == ow * residual.stride(2)
         ld_res = residual.stride(2)
-    if gn_table is not None:
-        assert gn_table.dtype == torch.float32 and gn_table.is_contiguous() and gn_table.shape == (n, c0, 2) and x1 is None
-    ep = make_epilogue(bias, row_bias, oh * ow, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual,
-                       gn_table=gn_table, gn_act=gn_act)
+    ep = make_epilogue(bias, row_bias, oh * ow, act, alpha, residual, ld_res, beta, out.dtype == torch.float32, act_after_residual)
     ev = _prof_begin()
     check(
         _lib.load().saspa_conv2d_igemm_strided_bf16(_ptr(x), x.stride(2), c0, _ptr(x1), x1.stride(2) if x1 is not None else 0, c1, n, h, w,
