@@ -144,6 +144,16 @@ typedef struct saspa_epilogue {
 int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
                     const saspa_epilogue* ep_host, cudaStream_t stream);
 
+/* Direct 3x3 convolution for small channel counts (cin <= 32, cout <= 128, stride 1 | 2, padding 1), NHWC bf16 -> NHWC bf16 with
+ * bias + activation (SASPA_ACT_NONE | SILU | RELU | GELU | QUICKGELU) in the epilogue: the ControlNet conditioning embedding's first five
+ * layers (diffusers ControlNetConditioningEmbedding, models/controlnets/controlnet.py; once per image before the denoise loop of
+ * run_aug/run_aug.py:278), the VAE encoder's conv_in and the HED stem.  x [n, h, w, cin] with pixel stride ldx, weight bf16
+ * [cout, kpad] in (ky, kx, cin) order (the layout of saspa_conv2d_igemm_bf16 / saspa_im2col_bf16 weights), out [n, oh, ow, cout] with
+ * pixel stride ldo.  Replaces im2col + GEMM (cin = 3) and the 64-channel-granular implicit GEMM (cin = 16 / 32) on these layers. */
+int saspa_conv3x3_small_supported(int cin, int cout, int stride, int pad);
+int saspa_conv3x3_small_bf16(const void* x, int ldx, int cin, int n, int h, int w, const void* weight, int kpad, const float* bias, int act,
+                             int stride, int pad, void* out, int ldo, int cout, int oh, int ow, cudaStream_t stream);
+
 /* Slots per row of the partial statistics a GEMM with N output columns writes to row_stats_out (a function of N only, so that a
  * row's statistics do not depend on how many rows share the launch). */
 int saspa_gemm_row_stats_slots(int N);

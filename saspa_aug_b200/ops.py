@@ -180,6 +180,28 @@ def conv2d_igemm(x: torch.Tensor, weight: torch.Tensor, ksize: int, out: Optiona
     return out
 
 
+def conv3x3_small_supported(cin: int, cout: int, stride: int, pad: int) -> bool:
+    return bool(_lib.load().saspa_conv3x3_small_supported(int(cin), int(cout), int(stride), int(pad)))
+
+
+def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE, stride: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / padding 1 convolution for cin <= 32, cout <= 128 on NHWC bf16 [n,h,w,cin] (dense pixel strides); weight bf16 [cout, kpad]
+    in (ky, kx, cin) order.  Bias + activation in the epilogue, bf16 out [n,oh,ow,cout]."""
+    _need_cuda(x, weight)
+    n, h, w, cin = x.shape
+    assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    cout, kpad = weight.shape
+    assert weight.dtype == BF16 and weight.is_contiguous() and kpad >= 9 * cin
+    oh, ow = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+    if out is None:
+        out = torch.empty((n, oh, ow, cout), dtype=BF16, device=x.device)
+    assert out.dtype == BF16 and out.shape == (n, oh, ow, cout) and out.stride(3) == 1 and out.stride(1) == ow * out.stride(2) and out.stride(0) == oh * out.stride(1)
+    check(_lib.load().saspa_conv3x3_small_bf16(_ptr(x), x.stride(2), cin, n, h, w, _ptr(weight), kpad, _ptr(bias), int(act), int(stride), 1, _ptr(out),
+                                               out.stride(2), cout, oh, ow, _stream()), "saspa_conv3x3_small_bf16")
+    _count()
+    return out
+
+
 def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, oh: int, ow: int, kpad: int) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c = x.shape

@@ -262,3 +262,42 @@ def test_layernorm_folded_into_gemm(cuda_device, M, C, N, act):
     e_fold, e_unf = (got - want).abs().max().item(), (unfused - want).abs().max().item()
     print(f"LN fold M={M} C={C} N={N} act={act}: max err folded {e_fold:.4g}, unfused {e_unf:.4g}, max|ref| {want.abs().max().item():.3g}")
     assert e_fold <= max(1.5 * e_unf, 2e-2 * want.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,act,sliced", [
+    (2, 40, 56, 3, 16, 1, "silu", False), (2, 64, 48, 16, 16, 1, "silu", False), (3, 33, 47, 16, 32, 2, "silu", False),
+    (1, 64, 64, 32, 32, 1, "none", False), (2, 32, 32, 32, 96, 2, "silu", False), (1, 48, 48, 3, 128, 1, "none", False),
+    (1, 48, 40, 3, 64, 1, "relu", False), (2, 17, 19, 4, 20, 1, "gelu", False), (2, 24, 24, 16, 16, 1, "silu", True),
+    (4, 128, 128, 16, 16, 1, "silu", False)])
+def test_conv3x3_small_channels(cuda_device, n, h, w, cin, cout, stride, act, sliced):
+    """saspa_conv3x3_small_bf16 (ControlNet conditioning embedding 3->16->16->32->32->96, VAE / HED stems) against torch conv2d in fp32 on
+    the same bf16 inputs and weights: odd map sizes (partial tiles, image borders = zero padding), stride 2, Cin 3 / 4 (scalar staging),
+    Cout not a multiple of 8, a channel-sliced input view, every epilogue activation.  Also equal to the im2col + GEMM path it replaces
+    up to the bf16 rounding of the output."""
+    import torch.nn.functional as F
+
+    from saspa_aug_b200.layout import conv_weight_kmajor
+
+    g = torch.Generator().manual_seed(n * 100 + cin + cout)
+    acts = {"none": (ops.ACT_NONE, lambda t: t), "silu": (ops.ACT_SILU, F.silu), "relu": (ops.ACT_RELU, F.relu), "gelu": (ops.ACT_GELU, F.gelu)}
+    code, fn = acts[act]
+    xs = torch.randn((n, h, w, cin + (8 if sliced else 0)), generator=g).to(torch.bfloat16).cuda()
+    x = xs[..., :cin] if sliced else xs
+    wt = torch.randn((cout, cin, 3, 3), generator=g) / (9 * cin) ** 0.5
+    bias = (0.2 * torch.randn(cout, generator=g)).cuda()
+    kpad = (9 * cin + 7) // 8 * 8
+    wk = conv_weight_kmajor(wt, kpad).to(torch.bfloat16).cuda()
+    assert ops.conv3x3_small_supported(cin, cout, stride, 1)
+    got = ops.conv3x3_small(x, wk, bias, code, stride).float()
+    want = fn(F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float().cuda(), bias, stride=stride, padding=1)).permute(0, 2, 3, 1)
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item()
+    assert err <= 1e-2 * want.abs().max().item() + 1e-3, (err, want.abs().max().item())
+    # the path it replaces: im2col + tcgen05 GEMM
+    oh, ow = want.shape[1:3]
+    cols = ops.im2col(x.contiguous(), 3, 3, stride, 1, 1, oh, ow, kpad)
+    old = ops.gemm(cols, wk, bias=bias, act=code).view(n, oh, ow, cout).float()
+    assert (got - old).abs().max().item() <= 1.6e-2 * want.abs().max().item() + 1e-3
+    # per-image results do not depend on the batch
+    one = ops.conv3x3_small(x[:1], wk, bias, code, stride).float()
+    assert torch.equal(one, got[:1])
