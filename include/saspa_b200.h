@@ -149,10 +149,13 @@ int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int
  * layers (diffusers ControlNetConditioningEmbedding, models/controlnets/controlnet.py; once per image before the denoise loop of
  * run_aug/run_aug.py:278), the VAE encoder's conv_in and the HED stem.  x [n, h, w, cin] with pixel stride ldx, weight bf16
  * [cout, kpad] in (ky, kx, cin) order (the layout of saspa_conv2d_igemm_bf16 / saspa_im2col_bf16 weights), out [n, oh, ow, cout] with
- * pixel stride ldo.  Replaces im2col + GEMM (cin = 3) and the 64-channel-granular implicit GEMM (cin = 16 / 32) on these layers. */
+ * pixel stride ldo; residual (bf16 [n, oh, ow, cout], pixel stride ld_res, or NULL) is added before the activation (the ControlNet adds its
+ * conditioning embedding to conv_in's output).  Wider layers run as slices of <= 128 output channels (weight rows / out / residual offset by
+ * the caller: the UNet's and ControlNet's conv_in 4 -> 320).  Replaces im2col + GEMM (cin = 3) and the 64-channel-granular implicit GEMM (cin = 16 / 32) on these layers. */
 int saspa_conv3x3_small_supported(int cin, int cout, int stride, int pad);
 int saspa_conv3x3_small_bf16(const void* x, int ldx, int cin, int n, int h, int w, const void* weight, int kpad, const float* bias, int act,
-                             int stride, int pad, void* out, int ldo, int cout, int oh, int ow, cudaStream_t stream);
+                             const void* residual, int ld_res, int stride, int pad, void* out, int ldo, int cout, int oh, int ow,
+                             cudaStream_t stream);
 
 /* Slots per row of the partial statistics a GEMM with N output columns writes to row_stats_out (a function of N only, so that a
  * row's statistics do not depend on how many rows share the launch). */

@@ -111,7 +111,7 @@ SIGNATURES = {
     "saspa_rgb_to_luma3_u8": (c_int, [_P, ctypes.c_longlong, _P, _P]),
     "saspa_lpips_layer_accum": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "saspa_conv3x3_small_supported": (c_int, [c_int, c_int, c_int, c_int]),
-    "saspa_conv3x3_small_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    "saspa_conv3x3_small_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "saspa_hed_fuse_u8": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
 }
 

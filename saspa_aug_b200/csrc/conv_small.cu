@@ -41,6 +41,8 @@ struct ConvSmallParams {
   int kpad;
   const float* bias;
   int act;
+  const __nv_bfloat16* residual;  // [n, OH, OW, cout] with pixel stride ld_res, added before the activation (or nullptr)
+  int ld_res;
   __nv_bfloat16* out;
   int ldo, cout, OH, OW;
   int pad;
@@ -150,13 +152,20 @@ __global__ void __launch_bounds__(CS_THREADS) conv3x3_small_kernel(const ConvSma
         for (int half = 0; half < 2; ++half) {
           const int ox = ox0 + (lane >> 2) + half * 8;
           if (ox >= p.OW) continue;
-          __nv_bfloat16* op = p.out + (((size_t)img * p.OH + oy) * p.OW + ox) * p.ldo;
+          const size_t pix = ((size_t)img * p.OH + oy) * p.OW + ox;
+          __nv_bfloat16* op = p.out + pix * p.ldo;
+          const __nv_bfloat16* rp = p.residual ? p.residual + pix * p.ld_res : nullptr;
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
             const int c = j * 8 + (lane & 3) * 2;
             if (c >= p.cout) continue;
-            const float v0 = cs_act(acc[j][half * 2] + bz[j][0], p.act);
-            const float v1 = cs_act(acc[j][half * 2 + 1] + bz[j][1], p.act);
+            float v0 = acc[j][half * 2] + bz[j][0], v1 = acc[j][half * 2 + 1] + bz[j][1];
+            if (rp) {
+              v0 += __bfloat162float(rp[c]);
+              if (c + 1 < p.cout) v1 += __bfloat162float(rp[c + 1]);
+            }
+            v0 = cs_act(v0, p.act);
+            v1 = cs_act(v1, p.act);
             if (c + 1 < p.cout && (p.ldo & 1) == 0) {
               *reinterpret_cast<__nv_bfloat162*>(op + c) = __floats2bfloat162_rn(v0, v1);
             } else {
@@ -210,13 +219,15 @@ extern "C" int saspa_conv3x3_small_supported(int cin, int cout, int stride, int 
 }
 
 extern "C" int saspa_conv3x3_small_bf16(const void* x, int ldx, int cin, int n, int h, int w, const void* weight, int kpad, const float* bias, int act,
-                                        int stride, int pad, void* out, int ldo, int cout, int oh, int ow, cudaStream_t stream) {
+                                        const void* residual, int ld_res, int stride, int pad, void* out, int ldo, int cout, int oh, int ow,
+                                        cudaStream_t stream) {
   SASPA_CHECK_ARG(n >= 0 && h >= 0 && w >= 0 && oh >= 0 && ow >= 0, "saspa_conv3x3_small_bf16: negative dims");
   if (n == 0 || oh == 0 || ow == 0) return SASPA_OK;
   SASPA_CHECK_ARG(x && weight && out, "saspa_conv3x3_small_bf16: null pointer");
   SASPA_CHECK_ARG(saspa_conv3x3_small_supported(cin, cout, stride, pad), "saspa_conv3x3_small_bf16: needs cin <= 32, cout <= 128, stride 1 | 2, pad 1 (cin=%d cout=%d stride=%d pad=%d)",
                   cin, cout, stride, pad);
-  SASPA_CHECK_ARG(ldx >= cin && ldo >= cout && kpad >= 9 * cin, "saspa_conv3x3_small_bf16: ldx >= cin, ldo >= cout, kpad >= 9 * cin");
+  SASPA_CHECK_ARG(ldx >= cin && ldo >= cout && kpad >= 9 * cin && (!residual || ld_res >= cout),
+                  "saspa_conv3x3_small_bf16: ldx >= cin, ldo >= cout, ld_res >= cout, kpad >= 9 * cin");
   SASPA_CHECK_ARG((cin % 8 != 0) || (kpad % 8 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0),
                   "saspa_conv3x3_small_bf16: cin %% 8 == 0 takes 16-byte loads (aligned x / weight, kpad %% 8 == 0)");
   SASPA_CHECK_ARG(act == SASPA_ACT_NONE || act == SASPA_ACT_SILU || act == SASPA_ACT_RELU || act == SASPA_ACT_GELU || act == SASPA_ACT_QUICKGELU,
@@ -232,6 +243,8 @@ extern "C" int saspa_conv3x3_small_bf16(const void* x, int ldx, int cin, int n, 
   p.kpad = kpad;
   p.bias = bias;
   p.act = act;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.ld_res = ld_res;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.cout = cout;

@@ -52,7 +52,8 @@ def pix3d(x: torch.Tensor) -> torch.Tensor:
 class Conv:
     """Conv2d.  1x1/3x3 with Cin % 8 == 0 and stride 1 ("same") or stride 2 (padding 1, or the VAE encoder's bottom/right-only
     padding) run as TMA implicit GEMM; 3x3 / padding-1 layers with Cin <= 32 and Cout <= 128 (conditioning embedding, image stems) on
-    the direct small-channel kernel; everything else (Cin 4 -> 320, 7x7 / 14x14 stems, strides > 2) as im2col + GEMM."""
+    the direct small-channel kernel (conv_in 4 -> 320 as slices of 128 output channels); everything else (7x7 / 14x14 stems, strides > 2)
+    as im2col + GEMM."""
 
     def __init__(self, sd: SD, prefix: str, dev, stride: int = 1, padding: Optional[int] = None, weight=None, bias=None):
         w = sd[prefix + ".weight"] if weight is None else weight
@@ -65,7 +66,7 @@ class Conv:
         self.bias = _f32(b, dev)
         # 3x3 layers with a handful of channels (conditioning embedding, image stems): direct mma.sync kernel, no im2col buffer and no
         # 64-channel k-block padding (csrc/conv_small.cu)
-        self.small = self.k == 3 and self.pad == 1 and stride in (1, 2) and self.cin <= 32 and self.cout <= 128
+        self.small = self.k == 3 and self.pad == 1 and stride in (1, 2) and self.cin <= 32 and (self.cout <= 128 or self.cin <= 8)
         self.direct = not self.small and stride == 1 and self.pad == self.k // 2 and self.k in (1, 3) and self.cin % 8 == 0
         self.direct_strided = not self.small and stride == 2 and self.k == 3 and self.pad in (0, 1) and self.cin % 8 == 0
         if self.direct or self.direct_strided:
@@ -78,8 +79,8 @@ class Conv:
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, pad_extra_br: int = 0, **epi) -> torch.Tensor:
         n, h, w, c = x.shape
         assert c == self.cin, (c, self.cin)
-        if self.small and pad_extra_br == 0 and set(epi) <= {"act"}:
-            return ops.conv3x3_small(x, self.w, self.bias, epi.get("act", ACT_NONE), self.stride, out=out)
+        if self.small and pad_extra_br == 0 and set(epi) <= {"act", "residual", "beta"} and epi.get("beta", 1.0) == 1.0:
+            return ops.conv3x3_small(x, self.w, self.bias, epi.get("act", ACT_NONE), self.stride, out=out, residual=epi.get("residual"))
         if self.direct:
             return ops.conv2d_igemm(x, self.w, self.k, out=out, bias=self.bias, **epi)
         oh = (h + 2 * self.pad + pad_extra_br - self.k) // self.stride + 1

@@ -184,9 +184,11 @@ def conv3x3_small_supported(cin: int, cout: int, stride: int, pad: int) -> bool:
     return bool(_lib.load().saspa_conv3x3_small_supported(int(cin), int(cout), int(stride), int(pad)))
 
 
-def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE, stride: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 / padding 1 convolution for cin <= 32, cout <= 128 on NHWC bf16 [n,h,w,cin] (dense pixel strides); weight bf16 [cout, kpad]
-    in (ky, kx, cin) order.  Bias + activation in the epilogue, bf16 out [n,oh,ow,cout]."""
+def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE, stride: int = 1, out: Optional[torch.Tensor] = None,
+                  residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / padding 1 convolution for cin <= 32 on NHWC bf16 [n,h,w,cin] (dense pixel strides); weight bf16 [cout, kpad] in
+    (ky, kx, cin) order.  Bias (+ residual [n,oh,ow,cout]) + activation in the epilogue, bf16 out [n,oh,ow,cout] (any pixel stride).
+    cout > 128 runs as slices of 128 output channels."""
     _need_cuda(x, weight)
     n, h, w, cin = x.shape
     assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
@@ -195,10 +197,15 @@ def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE
     oh, ow = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
     if out is None:
         out = torch.empty((n, oh, ow, cout), dtype=BF16, device=x.device)
-    assert out.dtype == BF16 and out.shape == (n, oh, ow, cout) and out.stride(3) == 1 and out.stride(1) == ow * out.stride(2) and out.stride(0) == oh * out.stride(1)
-    check(_lib.load().saspa_conv3x3_small_bf16(_ptr(x), x.stride(2), cin, n, h, w, _ptr(weight), kpad, _ptr(bias), int(act), int(stride), 1, _ptr(out),
-                                               out.stride(2), cout, oh, ow, _stream()), "saspa_conv3x3_small_bf16")
-    _count()
+    for t in (out, residual):
+        assert t is None or (t.dtype == BF16 and t.shape == (n, oh, ow, cout) and t.stride(3) == 1 and t.stride(1) == ow * t.stride(2) and t.stride(0) == oh * t.stride(1))
+    lib = _lib.load()
+    for c0 in range(0, cout, 128):
+        c1 = min(cout, c0 + 128)
+        check(lib.saspa_conv3x3_small_bf16(_ptr(x), x.stride(2), cin, n, h, w, _ptr(weight[c0:c1]), kpad, _ptr(bias[c0:c1]) if bias is not None else None, int(act),
+                                           _ptr(residual[..., c0:c1]) if residual is not None else None, residual.stride(2) if residual is not None else 0,
+                                           int(stride), 1, _ptr(out[..., c0:c1]), out.stride(2), c1 - c0, oh, ow, _stream()), "saspa_conv3x3_small_bf16")
+        _count()
     return out
 
 

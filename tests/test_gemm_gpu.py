@@ -301,3 +301,24 @@ def test_conv3x3_small_channels(cuda_device, n, h, w, cin, cout, stride, act, sl
     # per-image results do not depend on the batch
     one = ops.conv3x3_small(x[:1], wk, bias, code, stride).float()
     assert torch.equal(one, got[:1])
+
+
+def test_conv3x3_small_wide_output_with_residual(cuda_device):
+    """conv_in 4 -> 320 of the UNet / ControlNet (the ControlNet adds its conditioning embedding as a residual) on the small-channel kernel:
+    slices of 128 output channels written into a channel slice of a wider buffer."""
+    import torch.nn.functional as F
+
+    from saspa_aug_b200.layout import conv_weight_kmajor
+
+    g = torch.Generator().manual_seed(5)
+    n, h, w, cin, cout = 3, 24, 40, 4, 320
+    x = torch.randn((n, h, w, cin), generator=g).to(torch.bfloat16).cuda()
+    wt = torch.randn((cout, cin, 3, 3), generator=g) / 6.0
+    bias = (0.2 * torch.randn(cout, generator=g)).cuda()
+    res = torch.randn((n, h, w, cout), generator=g).to(torch.bfloat16).cuda()
+    wk = conv_weight_kmajor(wt, 40).to(torch.bfloat16).cuda()
+    wide = torch.zeros((n, h, w, cout + 64), dtype=torch.bfloat16, device="cuda")
+    got = ops.conv3x3_small(x, wk, bias, ops.ACT_NONE, 1, out=wide[..., 32 : 32 + cout], residual=res)
+    want = (F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float().cuda(), bias, padding=1).permute(0, 2, 3, 1) + res.float())
+    assert (got.float() - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+    assert wide[..., :32].abs().max().item() == 0 and wide[..., 32 + cout :].abs().max().item() == 0
