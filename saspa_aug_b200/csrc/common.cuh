@@ -71,8 +71,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+// x * sigmoid(s * x) as FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL.  The flush-to-zero PTX forms are spelled out: __expf / __fdividef wrap the same
+// two MUFU ops in denormal-range fix-ups (an extra compare and two predicated multiplies each) that matter only beyond |s * x| > 87, where
+// this form already returns the right limit (t = inf -> rcp = 0 -> -0; t = 0 -> x).
+__device__ __forceinline__ float x_sigmoid_f(float x, float neg_s_log2e) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * neg_s_log2e));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return x * r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x_sigmoid_f(x, -1.4426950408889634f); }
+__device__ __forceinline__ float quick_gelu_f(float x) { return x_sigmoid_f(x, -1.702f * 1.4426950408889634f); }
 // erf-GELU on the FMA pipe only (GEGLU epilogue of the 64x64-level feed-forward GEMM: 16K gate values per 128 x 256 tile made the two
 // MUFU ops of gelu_erf_f a 2048-clk-per-tile XU bill next to a 2560-clk main loop).  erf(u / sqrt 2) = u * Q(u^2), Q = degree-7
 // near-minimax fit on |u| <= 4 (|erf error| <= 4.3e-5, i.e. |Phi error| <= 2.6e-5 incl. the clamp: erf(4 / sqrt 2) = 0.99994);
