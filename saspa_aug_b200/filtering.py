@@ -287,7 +287,7 @@ def create_json_of_image_name_to_augmented_images_paths(dataset, augmented_image
 
         def prep(path):  # L -> RGB -> resize(256, 256) on the device, one image at a time (sources differ in size), cached per file
             if path not in cache:
-                a = torch.from_numpy(np.asarray(Image.open(path).convert("RGB"))[None]).to(dev)
+                a = torch.from_numpy(np.array(Image.open(path).convert("RGB"))[None]).to(dev)
                 cache[path] = lpips_net.preprocess(a, resize)[0]
             return cache[path]
 
