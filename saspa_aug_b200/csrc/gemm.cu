@@ -214,8 +214,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Accumulator hand-back of a CTA pair ("this warp has read its TMEM rows"): ordered against the tcgen05.ld's by the
+// tcgen05.fence::before_thread_sync that precedes it; no generic-memory write has to be published to the MMA issuer, so the arrive is
+// RELAXED.  With .release.cluster the compiler put a cluster-scope memory barrier in front of every arrive (MEMBAR stalls: 18 % of all
+// warp samples of a K = 320 pair launch, profiles/r2_pair_handback_membar.txt) -- the reason pairs lost to single-CTA tiles below K = 1024.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -1016,10 +1020,13 @@ std::atomic<int> g_force_ctas{0};  // tuning hook (saspa_gemm_force_ctas): 0 = h
 
 // Two-CTA tiles (cta_group::2, 256 x BN): measured +14% at BN = 256 and +9% at BN = 160 on the plain GEMM main loop, a loss
 // for narrower tiles and for the halo conv (profiles/r1_bn_sweep_y.txt), so only the wide long-K GEMM tiles pair up.
-int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K) {
+int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K, bool has_residual) {
   if (const int forced = g_force_ctas.load()) return num_m_tiles >= 2 || forced == 1 ? forced : 1;
-  // epilogue-bound launches (GEGLU, short K) lose from coupling two CTAs (measured 325 -> 381 us on the 64x64 GEGLU GEMM)
-  return (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= 1024 && num_m_tiles >= 2) ? 2 : 1;
+  // CTA pairs halve the B bytes each CTA pulls from L2.  They pay from K = 1024 up, and from K = 640 for the residual-carrying output
+  // projections (64.5 vs 72.2 us at 65536 x 640 x 640); the epilogue-bound launches (GEGLU, LayerNorm-folded, K = 320) are level with
+  // single-CTA tiles since the hand-back lost its memory barrier (profiles/r2_pair_handback_membar.txt) and stay single
+  const int k_min = has_residual ? 640 : 1024;
+  return (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= k_min && num_m_tiles >= 2) ? 2 : 1;
 }
 
 template <int CTAS>
@@ -1118,7 +1125,7 @@ extern "C" int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, v
                   2 * p.num_n_tiles, p.stats_slots);
   CUtensorMap tmA, tmB;
   if ((rc = encode_2d(&tmA, A, M, K, lda, BM))) return rc;
-  const int ctas = pick_ctas(p.num_m_tiles, bn, 0, p.act, K);
+  const int ctas = pick_ctas(p.num_m_tiles, bn, 0, p.act, K, p.residual != nullptr);
   if ((rc = encode_2d(&tmB, B, N, K, ldb, bn / ctas))) return rc;  // each CTA of a pair loads its share of the B tile
   CUtensorMap tmD = tmA, tmR = tmA;
   if (p.tma_store) {
@@ -1222,7 +1229,7 @@ extern "C" int saspa_conv2d_igemm_strided_bf16(const void* x0, int ldx0, int c0,
   } else {
     tmA1 = tmA0;
   }
-  const int ctas = pick_ctas(p.num_m_tiles, bn_tile, p.mode, p.act, p.K);
+  const int ctas = pick_ctas(p.num_m_tiles, bn_tile, p.mode, p.act, p.K, p.residual != nullptr);
   if ((rc = encode_2d(&tmB, weight, cout, p.K, p.K, bn_tile / ctas))) return rc;
   CUtensorMap tmD = tmA0, tmR = tmA0;
   if (p.tma_store) {

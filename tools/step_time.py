@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=int, default=32)
     ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--graph", action="store_true", help="replay the whole generation from a captured CUDA graph instead of launching it")
     ap.add_argument("--attn", type=int, default=0, help="saspa_attention_impl value (3 = older cross-attention kernel)")
     a = ap.parse_args()
     from saspa_aug_b200 import _lib
@@ -35,6 +36,9 @@ def main():
     text = pipe.encode_prompt_ids(ids)
 
     def run(steps):
+        if a.graph:
+            return pipe._generate_graphed(dict(text_embeds=text, neg_embeds=neg, control_bf16=c, noise=noise), num_inference_steps=steps, guidance_scale=7.5,
+                                          controlnet_conditioning_scale=0.75, decode=False)
         return pipe.generate_batch(text, neg, None, None, noise=noise, num_inference_steps=steps, guidance_scale=7.5, controlnet_conditioning_scale=0.75,
                                    control_bf16=c, decode=False)
 
@@ -55,7 +59,7 @@ def main():
         ms = s.elapsed_time(e) / a.steps  # includes the once-per-image work (text K/V, cond embedding) amortised over the steps
         best = ms if best is None else min(best, ms)
     frac = 2135e9 * a.mb / (best * 1e-3) / (peak * 1e12)
-    print(f"fold_ln={os.environ.get('SASPA_FOLD_LN', '1')} attn_impl={a.attn} mb={a.mb}: {best:.2f} ms per step ({best / a.mb:.3f} ms per image-step), "
+    print(f"fold_ln={os.environ.get('SASPA_FOLD_LN', '1')} attn_impl={a.attn} graph={int(a.graph)} mb={a.mb}: {best:.2f} ms per step ({best / a.mb:.3f} ms per image-step), "
           f"step_tensor_frac {frac:.3f} of {peak:.0f} TF/s")
 
 
