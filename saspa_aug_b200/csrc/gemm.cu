@@ -978,7 +978,7 @@ int pick_bn(int N, int act, int num_m_tiles, bool mainloop_bound, bool fixed_by_
   if (N <= 64) return 64;
   if (mainloop_bound) {
     const int cands[4] = {256, 160, 128, 64};
-    const double t_rel[4] = {1.0, 0.69, 0.63, 0.49};
+    const double t_rel[4] = {1.0, 0.69, 0.66, 0.49};  // 128: 0.63 on a compute-bound GEMM, worse on per-tap convolutions (operand bytes per flop)
     const int sms = saspa_num_sms();
     int best = 256;
     double best_cost = 1e30;
@@ -1026,7 +1026,10 @@ int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K, bool has_residu
   // projections (64.5 vs 72.2 us at 65536 x 640 x 640); the epilogue-bound launches (GEGLU, LayerNorm-folded, K = 320) are level with
   // single-CTA tiles since the hand-back lost its memory barrier (profiles/r2_pair_handback_membar.txt) and stay single
   const int k_min = has_residual ? 640 : 1024;
-  return (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= k_min && num_m_tiles >= 2) ? 2 : 1;
+  if (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= k_min && num_m_tiles >= 2) return 2;
+  // halo convolutions for which the wave model already chose the 256-wide tile (the 16 x 16 level): the pair tile is 3-5 % faster
+  // (295 vs 311 us at 64 x 16 x 16, 1280 -> 1280; profiles/r2_conv_pair_sweep.txt); narrower tiles and per-tap convolutions are not
+  return (mode == 2 && bn == 256 && num_m_tiles >= 2) ? 2 : 1;
 }
 
 template <int CTAS>

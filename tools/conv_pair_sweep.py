@@ -13,7 +13,8 @@ from saspa_aug_b200 import _lib, ops
 def main():
     lib = _lib.load()
     shapes = [(64, 8, 8, 1280, 1280, 1), (64, 8, 8, 2560, 1280, 1), (64, 16, 16, 1280, 1280, 2), (64, 32, 32, 640, 640, 2), (64, 64, 64, 320, 320, 2),
-              (64, 16, 16, 1280, 1280, 1), (64, 16, 16, 2560, 1280, 1)]
+              (64, 16, 16, 1280, 1280, 1), (64, 16, 16, 2560, 1280, 1), (64, 32, 32, 640, 640, 1), (64, 32, 32, 1280, 640, 1), (64, 64, 64, 320, 320, 1),
+              (64, 64, 64, 640, 320, 1)]
     for n, h, w, cin, cout, stride in shapes:
         x, wk = rnd(n, h, w, cin), rnd(cout, 9 * cin) * (1.0 / (9 * cin) ** 0.5)
         bias = torch.zeros(cout, device="cuda")
