@@ -1023,10 +1023,15 @@ std::atomic<int> g_force_ctas{0};  // tuning hook (saspa_gemm_force_ctas): 0 = h
 int pick_ctas(int num_m_tiles, int bn, int mode, int act, int K, bool has_residual) {
   if (const int forced = g_force_ctas.load()) return num_m_tiles >= 2 || forced == 1 ? forced : 1;
   // CTA pairs halve the B bytes each CTA pulls from L2.  They pay from K = 1024 up, and from K = 640 for the residual-carrying output
-  // projections (64.5 vs 72.2 us at 65536 x 640 x 640); the epilogue-bound launches (GEGLU, LayerNorm-folded, K = 320) are level with
+  // projections (64.5 vs 72.2 us at 65536 x 640 x 640); the other short-K launches (LayerNorm-folded, K = 320) are level with
   // single-CTA tiles since the hand-back lost its memory barrier (profiles/r2_pair_handback_membar.txt) and stay single
   const int k_min = has_residual ? 640 : 1024;
-  if (bn >= 160 && mode == 0 && act != SASPA_ACT_GEGLU && K >= k_min && num_m_tiles >= 2) return 2;
+  if (bn >= 160 && mode == 0 && num_m_tiles >= 2) {
+    // the GEGLU feed-forward GEMMs: 5 / 11 / 8 % faster as pairs at K = 640 / 1280 (16 x 16 and 8 x 8 levels), level at K = 320
+    // (profiles/r2_pair_handback_membar.txt; they were excluded while the hand-back carried its barrier: 325 -> 381 us then)
+    if (act == SASPA_ACT_GEGLU) return 2;
+    if (K >= k_min) return 2;
+  }
   // halo convolutions for which the wave model already chose the 256-wide tile (the 16 x 16 level): the pair tile is 3-5 % faster
   // (295 vs 311 us at 64 x 16 x 16, 1280 -> 1280; profiles/r2_conv_pair_sweep.txt); narrower tiles and per-tap convolutions are not
   return (mode == 2 && bn == 256 && num_m_tiles >= 2) ? 2 : 1;
