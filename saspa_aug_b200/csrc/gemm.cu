@@ -7,7 +7,7 @@
 // AutoencoderKL forward (reference: pipe(**pipe_args), run_aug/run_aug.py:278) and the filter nets
 // (all_utils/utils.py:361 WSDAN_CAL, :152-164 CLIP).
 //
-// Structure per CTA (320 threads, 1 CTA / SM):
+// Structure per CTA (384 threads, 1 CTA / SM):
 //   warp 0   : TMA producer  - cp.async.bulk.tensor into a ring of 128B-swizzled smem tiles, signalled by mbarrier
 //              complete_tx.  GEMM: 2-D boxes.  Conv, per-tap mode: nine shifted 4-D NHWC boxes per 64-channel chunk
 //              (TMA's out-of-bounds zero fill IS the conv padding).  Conv, halo mode (3x3): ONE box of (16+2)x(8+2)
@@ -21,16 +21,20 @@
 //              32-column output panels k = g, g+2, ...:  tcgen05.ld 32x32b.x32 (one output row per thread),
 //              fused bias / per-image row bias (time embedding) / activation / GEGLU / alpha / residual.
 //              bf16 outputs leave through shared memory: each thread writes its 64-byte row slice into a
-//              64B-swizzled [128 x 32] staging panel and one thread issues a TMA store; the residual arrives the
+//              64B-swizzled [128 x 32] staging panel and arrives on the panel's mbarrier; the residual arrives the
 //              same way (TMA load into the staging panel, prefetched two panels ahead, across tile boundaries).
-//              fp32 / unaligned outputs take the direct (row-per-thread, 16-byte) global path.
+//              fp32 / unaligned outputs take the direct (row-per-thread, 16-byte) global path.  LayerNorm folded into
+//              the GEMMs around it: per-row partial (sum, sum of squares) out, mean / rstd applied to the accumulator.
+//   warps 10-11: store helpers, one per epilogue group: wait for a panel's four arrivals, issue its TMA store, prefetch
+//              the next residual panel into a drained buffer (or signal it free) -- no epilogue warp waits for another.
 //
 // CTAS = 2 (cta_group::2): two CTAs of a cluster (one TPC) compute a 256 x BN tile.  Each CTA loads its own 128 rows
 // of A and HALF of the B tile; the leader CTA issues tcgen05.mma.cta_group::2, which reads B from both CTAs' shared
 // memory and writes each CTA's 128 accumulator rows into that CTA's TMEM.  This halves the B bytes every SM pulls
 // from L2 and reads from shared memory per MMA -- the single-CTA 128 x 160 tile is shared-memory-bandwidth bound.
 // TMA loads of both CTAs complete on the leader's "full" barrier; tcgen05.commit multicasts "empty" / "accumulator
-// ready" to both CTAs; the peer's epilogue warps release the accumulator with a remote mbarrier arrive.
+// ready" to both CTAs; the peer's epilogue warps release the accumulator with a remote, RELAXED mbarrier arrive (a release
+// at cluster scope costs a memory barrier per arrive and made pairs lose below K = 1024).
 #include "tc_ptx.cuh"
 #include <atomic>
 
