@@ -116,6 +116,21 @@ def resized_hw(h: int, w: int, smaller_side_res: int):
     return int(np.round(H / 64.0)) * 64, int(np.round(W / 64.0)) * 64, k
 
 
+def set_seed(seed: int) -> None:
+    """all_utils/utils.py:32-36: the reference seeds ``random``, ``np.random`` and torch once per run (run_aug.py:588).  The sharded driver
+    does not depend on this global state (``replay_prompt_draws`` / ``reference_order_noise`` re-create the streams from ``cfg.SEED`` on
+    every rank); the function exists for callers that drive ``pass_thorugh_pipe`` themselves, as the reference's loop does."""
+    import random
+
+    import torch
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
 def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
     """all_utils/utils.py:58-79 (host-side pre-processing; identity for sources already at HxW % 64 == 0, min side = res)."""
     import cv2
