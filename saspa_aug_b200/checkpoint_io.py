@@ -16,7 +16,7 @@ import json
 import os
 import struct
 from pathlib import Path
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 import torch

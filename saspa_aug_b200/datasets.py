@@ -16,7 +16,6 @@ import os
 from pathlib import Path
 from typing import Callable, Dict, List, Optional
 
-import numpy as np
 
 DATASETS_SUPPORTED = ["planes", "cars", "dtd", "compcars-parts", "cub", "planes_biased", "synthetic"]
 

@@ -14,7 +14,7 @@ import torch
 from . import nn as snn
 from . import ops
 from .checkpoints import RESNET_LAYERS
-from .ops import ACT_NONE, ACT_QUICKGELU, ACT_RELU, BF16
+from .ops import ACT_QUICKGELU, ACT_RELU, BF16
 
 SD = Dict[str, torch.Tensor]
 

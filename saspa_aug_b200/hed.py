@@ -5,14 +5,13 @@ reference uses it (run_aug/run_aug.py:20 import, :311-312 ``HEDdetector.from_pre
 Same call surface (``from_pretrained(path_or_id, filename=None, cache_dir=None)``, ``.to(device)``, ``__call__(input_image,
 detect_resolution=512, image_resolution=512, safe=False, output_type="pil", scribble=False)``) and the same state-dict layout
 (``ControlNetHED.pth``: ``norm``, ``block{k}.convs.{i}``, ``block{k}.projection``), computed on the B200: the VGG-shaped trunk on the
-tcgen05 implicit-GEMM convolutions with the ReLU in their epilogue (the 3-channel stem as im2col + GEMM), 2x2 max pooling on
+tcgen05 implicit-GEMM convolutions with the ReLU in their epilogue (the 3-channel stem on the small-channel kernel), 2x2 max pooling on
 saspa_pool2d_nhwc_bf16, the 1x1 projections with fp32 output, and the detector's resize / mean / sigmoid / quantise tail as ONE kernel
 (saspa_hed_fuse_u8, csrc/hed.cu).  ``detect_batch`` is the batched entry the sharded driver uses (all sources of a micro-batch in one
 pass; the reference runs the detector per prompt on one image).  controlnet_aux is un-vendored and absent offline: oracle/hed.py
 restates it, parity unpinned."""
 from __future__ import annotations
 
-import os
 from pathlib import Path
 from typing import Dict, List, Optional
 
