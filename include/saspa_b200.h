@@ -150,7 +150,7 @@ int saspa_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int
  * run_aug/run_aug.py:278), the VAE encoder's conv_in and the HED stem.  x [n, h, w, cin] with pixel stride ldx, weight bf16
  * [cout, kpad] in (ky, kx, cin) order (the layout of saspa_conv2d_igemm_bf16 / saspa_im2col_bf16 weights), out [n, oh, ow, cout] with
  * pixel stride ldo; residual (bf16 [n, oh, ow, cout], pixel stride ld_res, or NULL) is added before the activation (the ControlNet adds its
- * conditioning embedding to conv_in's output).  Wider layers run as slices of <= 128 output channels (weight rows / out / residual offset by
+ * conditioning embedding to conv_in's output).  Wider layers run as slices of output channels (the host side uses 64: two CTAs per SM) (weight rows / out / residual offset by
  * the caller: the UNet's and ControlNet's conv_in 4 -> 320).  Replaces im2col + GEMM (cin = 3) and the 64-channel-granular implicit GEMM (cin = 16 / 32) on these layers. */
 int saspa_conv3x3_small_supported(int cin, int cout, int stride, int pad);
 int saspa_conv3x3_small_bf16(const void* x, int ldx, int cin, int n, int h, int w, const void* weight, int kpad, const float* bias, int act,

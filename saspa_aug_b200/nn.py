@@ -52,7 +52,7 @@ def pix3d(x: torch.Tensor) -> torch.Tensor:
 class Conv:
     """Conv2d.  1x1/3x3 with Cin % 8 == 0 and stride 1 ("same") or stride 2 (padding 1, or the VAE encoder's bottom/right-only
     padding) run as TMA implicit GEMM; 3x3 / padding-1 layers with Cin <= 32 and Cout <= 128 (conditioning embedding, image stems) on
-    the direct small-channel kernel (conv_in 4 -> 320 as slices of 128 output channels); everything else (7x7 / 14x14 stems, strides > 2)
+    the direct small-channel kernel (conv_in 4 -> 320 as slices of 64 output channels); everything else (7x7 / 14x14 stems, strides > 2)
     as im2col + GEMM."""
 
     def __init__(self, sd: SD, prefix: str, dev, stride: int = 1, padding: Optional[int] = None, weight=None, bias=None):

@@ -188,7 +188,7 @@ def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE
                   residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3x3 / padding 1 convolution for cin <= 32 on NHWC bf16 [n,h,w,cin] (dense pixel strides); weight bf16 [cout, kpad] in
     (ky, kx, cin) order.  Bias (+ residual [n,oh,ow,cout]) + activation in the epilogue, bf16 out [n,oh,ow,cout] (any pixel stride).
-    cout > 128 runs as slices of 128 output channels."""
+    cout > 96 runs as slices of 64 output channels."""
     _need_cuda(x, weight)
     n, h, w, cin = x.shape
     assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
@@ -200,8 +200,9 @@ def conv3x3_small(x: torch.Tensor, weight: torch.Tensor, bias=None, act=ACT_NONE
     for t in (out, residual):
         assert t is None or (t.dtype == BF16 and t.shape == (n, oh, ow, cout) and t.stride(3) == 1 and t.stride(1) == ow * t.stride(2) and t.stride(0) == oh * t.stride(1))
     lib = _lib.load()
-    for c0 in range(0, cout, 128):
-        c1 = min(cout, c0 + 128)
+    step = 128 if cout <= 96 else 64  # wide layers: 64-channel slices keep two CTAs per SM (the 128-channel kernel holds 179 registers)
+    for c0 in range(0, cout, step):
+        c1 = min(cout, c0 + step)
         check(lib.saspa_conv3x3_small_bf16(_ptr(x), x.stride(2), cin, n, h, w, _ptr(weight[c0:c1]), kpad, _ptr(bias[c0:c1]) if bias is not None else None, int(act),
                                            _ptr(residual[..., c0:c1]) if residual is not None else None, residual.stride(2) if residual is not None else 0,
                                            int(stride), 1, _ptr(out[..., c0:c1]), out.stride(2), c1 - c0, oh, ow, _stream()), "saspa_conv3x3_small_bf16")
