@@ -72,6 +72,16 @@ int saspa_pil_ksize(int in_size, int out_size, int filter);
 int saspa_resize_pil_u8(const uint8_t* img, int n, int h, int w, int c, uint8_t* tmp /* [n,h,out_w,c] */, uint8_t* out, int out_h,
                         int out_w, const int32_t* bounds_x, const int32_t* coeffs_x, int ksize_x, const int32_t* bounds_y,
                         const int32_t* coeffs_y, int ksize_y, cudaStream_t stream);
+/* cv2.resize(u8 HWC, (dw, dh), interpolation = cv2.INTER_AREA) of ONE image on the device, bit for bit on OpenCV's three 8-bit code paths
+ * (integer block sums / float area tables / fixed-point bilinear with area coefficients when one axis is up-scaled): the resize of
+ * utils.resize_image for sources at least `resolution` px on their short side (all_utils/utils.py:58-79, k <= 1; called at
+ * run_aug/run_aug.py:373 and again inside preprocess_canny, all_utils/utils.py:93-94).  src [sh, sw, c], dst [dh, dw, c], c <= 4, both
+ * dense.  The per-axis tables are built on the host as OpenCV builds them and staged in `workspace`
+ * (saspa_resize_area_workspace_bytes, 256-byte aligned; unused when both scale factors are integers or the sizes are equal). */
+size_t saspa_resize_area_workspace_bytes(int sh, int sw, int dh, int dw);
+int saspa_resize_area_u8(const uint8_t* src, int sh, int sw, int c, uint8_t* dst, int dh, int dw, void* workspace, size_t ws_bytes,
+                         cudaStream_t stream);
+
 /* LPIPS distance of the optional lpips_min / lpips_max filter (all_utils/utils.py:269-270, :377-381, calc_lpips_distance :576-590;
  * arithmetic of the un-vendored `lpips` package, net='alex').
  *   saspa_rgb_to_luma3_u8: PIL Image.convert("L").convert("RGB") (ITU-R 601-2 luma in 16-bit fixed point, replicated), u8 [pixels,3].

@@ -594,3 +594,17 @@ def hed_fuse(sides, H: int, W: int, safe: bool = False, out_channels: int = 3) -
     check(_lib.load().saspa_hed_fuse_u8(ptrs, hs, ws, lds, n, int(H), int(W), 1 if safe else 0, _ptr(out), int(out_channels), _stream()), "saspa_hed_fuse_u8")
     _count()
     return out
+
+
+def resize_area(img: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA) for ONE u8 HWC image on the device (bit-exact, see csrc/resize_area.cu)."""
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    sh, sw, c = img.shape
+    lib = _lib.load()
+    ws_bytes = lib.saspa_resize_area_workspace_bytes(sh, sw, int(dh), int(dw))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+    out = torch.empty((int(dh), int(dw), c), dtype=torch.uint8, device=img.device)
+    check(lib.saspa_resize_area_u8(_ptr(img), sh, sw, c, _ptr(out), int(dh), int(dw), _ptr(ws), ws_bytes, _stream()), "saspa_resize_area_u8")
+    _count()
+    return out

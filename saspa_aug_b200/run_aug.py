@@ -60,6 +60,7 @@ class AugConfig:
     SAMPLER: str = "ddim"
     RNG_MODE: str = "per_item"  # "per_item" (partition independent) | "reference_order" (replays the global generator)
     MICRO_BATCH: int = 16
+    DEVICE_RESIZE: bool = False  # loader threads resize down-scaled sources on the GPU (bit-exact INTER_AREA) instead of with cv2
 
     def __post_init__(self):
         if self.USE_ARTISTIC_PROMPTS is None:
@@ -139,6 +140,21 @@ def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
     if (H, W) == input_image.shape[:2]:
         return input_image
     return cv2.resize(input_image, (W, H), interpolation=cv2.INTER_LANCZOS4 if k > 1 else cv2.INTER_AREA)
+
+
+def resize_image_device(img_u8, smaller_side_res: int):
+    """``resize_image`` for a u8 HWC image that is already on the device (e.g. decoded there): same size rule; the INTER_AREA down-scale
+    (k <= 1: every source at least ``smaller_side_res`` px on its short side) runs on the GPU bit-exactly (saspa_resize_area_u8).  Smaller
+    sources need OpenCV's LANCZOS4 up-scale, which stays on the host (``resize_image``): this function refuses them instead of
+    approximating."""
+    from . import ops
+
+    H, W, k = resized_hw(int(img_u8.shape[0]), int(img_u8.shape[1]), smaller_side_res)
+    if (H, W) == tuple(img_u8.shape[:2]):
+        return img_u8
+    if k > 1:
+        raise NotImplementedError("up-scaling (cv2.INTER_LANCZOS4) is done on the host: run_aug.resize_image")
+    return ops.resize_area(img_u8.contiguous(), H, W)
 
 
 def HWC3(x: np.ndarray) -> np.ndarray:
@@ -518,7 +534,15 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts, out_dir: str, rank: int = 
     saves = []  # (future, (index, i, out_path) | None)
 
     def load(path):
-        return resize_image(np.array(Image.open(path).convert("RGB")), cfg.RESOLUTION)
+        img = np.array(Image.open(path).convert("RGB"))
+        if cfg.DEVICE_RESIZE and resized_hw(img.shape[0], img.shape[1], cfg.RESOLUTION)[2] <= 1:
+            # same pixels as cv2 (saspa_resize_area_u8), on this loader thread's own stream so it never queues behind the denoising kernels
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                out = resize_image_device(torch.from_numpy(img).to(dev, non_blocking=True), cfg.RESOLUTION).cpu()
+            side.synchronize()
+            return out.numpy()
+        return resize_image(img, cfg.RESOLUTION)
 
     def submit_loads(chunk):
         """-> {path: future} for every distinct image the chunk reads (sources, BLIP subjects)."""
