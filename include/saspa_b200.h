@@ -82,6 +82,14 @@ size_t saspa_resize_area_workspace_bytes(int sh, int sw, int dh, int dw);
 int saspa_resize_area_u8(const uint8_t* src, int sh, int sw, int c, uint8_t* dst, int dh, int dw, void* workspace, size_t ws_bytes,
                          cudaStream_t stream);
 
+/* cv2.resize(u8 HWC, (dw, dh), interpolation = cv2.INTER_LANCZOS4) of ONE image on the device, bit for bit: the k > 1 branch of
+ * utils.resize_image (sources under `resolution` px on their short side; all_utils/utils.py:77).  interpolateLanczos4 weights built on
+ * the host (double sin / cos, float normalisation, 11-bit fixed point) as OpenCV builds them, 8 x 8 taps with a replicated border in
+ * int32, FixedPtCast<int, uchar, 22>.  Same buffer conventions as saspa_resize_area_u8. */
+size_t saspa_resize_lanczos4_workspace_bytes(int dh, int dw);
+int saspa_resize_lanczos4_u8(const uint8_t* src, int sh, int sw, int c, uint8_t* dst, int dh, int dw, void* workspace, size_t ws_bytes,
+                             cudaStream_t stream);
+
 /* LPIPS distance of the optional lpips_min / lpips_max filter (all_utils/utils.py:269-270, :377-381, calc_lpips_distance :576-590;
  * arithmetic of the un-vendored `lpips` package, net='alex').
  *   saspa_rgb_to_luma3_u8: PIL Image.convert("L").convert("RGB") (ITU-R 601-2 luma in 16-bit fixed point, replicated), u8 [pixels,3].

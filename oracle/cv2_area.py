@@ -1,6 +1,6 @@
-"""CPU restatement of ``cv2.resize(u8 HWC, (W, H), interpolation=cv2.INTER_AREA)`` -- the call the reference's ``utils.resize_image``
-(all_utils/utils.py:58-79) makes for every source that is at least 512 px on its short side (k <= 1), and controlnet_aux's
-``resize_image`` likewise.
+"""CPU restatement of ``cv2.resize(u8 HWC, (W, H), interpolation=cv2.INTER_AREA | cv2.INTER_LANCZOS4)`` -- the calls the reference's
+``utils.resize_image`` (all_utils/utils.py:58-79) makes: INTER_AREA for every source that is at least 512 px on its short side (k <= 1),
+INTER_LANCZOS4 for smaller ones (k > 1); controlnet_aux's ``resize_image`` likewise.
 
 TEST INFRASTRUCTURE.  OpenCV is a third-party dependency of the reference (``opencv-python==4.8.0.74``, environment.yml:24; 4.13.0 is what
 is installed here and on the GPU box); this file restates the three code paths ``modules/imgproc/src/resize.cpp`` takes for 8-bit
@@ -124,3 +124,59 @@ def resize_area(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
             return _area_fast(src, dw, dh)
         return _area_float(src, dw, dh)
     return _area_linear(src, dw, dh)
+
+
+_S45 = 0.70710678118654752440084436210485
+_CS = ((1, 0), (-_S45, -_S45), (0, 1), (_S45, -_S45), (-1, 0), (_S45, _S45), (0, -1), (-_S45, _S45))
+
+
+def lanczos4_coeffs(x) -> np.ndarray:
+    """interpolateLanczos4: eight float32 weights for the fractional position x in [0, 1)."""
+    x = np.float32(x)
+    co = np.zeros(8, np.float32)
+    x3 = np.float32(x + np.float32(3))
+    y0 = -float(x3) * math.pi * 0.25
+    s0, c0 = math.sin(y0), math.cos(y0)
+    sm = np.float32(0)
+    for i in range(8):
+        y0_ = np.float32(x3 - np.float32(i))
+        if abs(y0_) >= np.float32(1e-6):
+            y = -float(y0_) * math.pi * 0.25
+            co[i] = np.float32((_CS[i][0] * s0 + _CS[i][1] * c0) / (y * y))
+        else:
+            co[i] = np.float32(1e30)
+        sm = np.float32(sm + co[i])
+    return (co * np.float32(np.float32(1.0) / sm)).astype(np.float32)
+
+
+def lanczos4_tab(ssize: int, dsize: int):
+    """(floor of the source coordinate, 11-bit weights of taps ofs - 3 .. ofs + 4) per destination index."""
+    scale = ssize / dsize
+    ofs = np.zeros(dsize, np.int64)
+    w = np.zeros((dsize, 8), np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = math.floor(f)
+        ofs[d] = s
+        w[d] = np.clip(np.rint(lanczos4_coeffs(np.float32(f - np.float32(s))) * np.float32(2048)), -32768, 32767).astype(np.int64)
+    return ofs, w
+
+
+def resize_lanczos4(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4) for uint8 HWC: HResizeLanczos4 (int sums, replicated border) then
+    VResizeLanczos4 with FixedPtCast<int, uchar, 22>."""
+    assert src.dtype == np.uint8 and src.ndim == 3
+    sh, sw, cn = src.shape
+    if (sh, sw) == (dh, dw):
+        return src.copy()
+    xofs, xw = lanczos4_tab(sw, dw)
+    yofs, yw = lanczos4_tab(sh, dh)
+    S = src.astype(np.int64)
+    H = np.zeros((sh, dw, cn), np.int64)
+    for d in range(dw):
+        H[:, d] = sum(S[:, min(max(xofs[d] - 3 + k, 0), sw - 1)] * xw[d, k] for k in range(8))
+    out = np.zeros((dh, dw, cn), np.uint8)
+    for d in range(dh):
+        acc = sum(H[min(max(yofs[d] - 3 + k, 0), sh - 1)] * yw[d, k] for k in range(8))
+        out[d] = np.clip((acc + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return out

@@ -114,6 +114,8 @@ SIGNATURES = {
     "saspa_conv3x3_small_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "saspa_resize_area_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "saspa_resize_area_u8": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, c_size_t, _P]),
+    "saspa_resize_lanczos4_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "saspa_resize_lanczos4_u8": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, c_size_t, _P]),
     "saspa_hed_fuse_u8": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
 }
 

@@ -1,4 +1,4 @@
-// cv2.resize(u8 HWC, dsize, interpolation = INTER_AREA) on the device, bit for bit: the resize the reference applies to every source that
+// cv2.resize(u8 HWC, dsize, interpolation = INTER_AREA | INTER_LANCZOS4) on the device, bit for bit: the resize the reference applies to every source that
 // is at least `resolution` pixels on its short side (utils.resize_image, all_utils/utils.py:58-79: k <= 1 -> cv2.INTER_AREA; again inside
 // preprocess_canny :93-94 and in controlnet_aux's detectors).  OpenCV takes one of three 8-bit code paths (modules/imgproc/src/resize.cpp;
 // restated and pinned against the installed cv2 in oracle/cv2_area.py), all three are here:
@@ -7,6 +7,8 @@
 //                                              order), sum (+)= beta * buf along y, cvRound -- float32, unfused multiply and add
 //   mode 2  one axis < 1 (the x64 rounding of resize_image can make ONE axis a slight up-scale)
 //                                              the fixed-point bilinear kernels with INTER_AREA's coefficient rule (11-bit weights)
+//   lanczos (k > 1: sources under `resolution` px)  INTER_LANCZOS4: interpolateLanczos4 weights (double sin / cos on the host), 11-bit fixed point,
+//                                              8 x 8 taps with a replicated border, (v + 2^21) >> 22
 // The tables are built on the host in double precision exactly as OpenCV builds them and copied into the caller's workspace; one thread
 // per output element (a 512 x 704 x 3 destination is 1.08 M elements: HBM-bound on the source read).
 #include <math.h>
@@ -85,6 +87,44 @@ LinTab lin_tab(int ssize, int dsize) {
   return t;
 }
 
+struct LanczosTab {
+  std::vector<int> ofs;  // [dsize] floor of the source coordinate
+  std::vector<int> w;    // [dsize][8] 11-bit weights of taps ofs - 3 .. ofs + 4
+};
+
+// interpolateLanczos4 + the fixed-point conversion of resize()'s general path (INTER_LANCZOS4, 8-bit)
+LanczosTab lanczos_tab(int ssize, int dsize) {
+  static const double s45 = 0.70710678118654752440084436210485;
+  static const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double pi = 3.1415926535897932384626433832795;
+  LanczosTab t;
+  const double scale = (double)ssize / dsize;
+  for (int d = 0; d < dsize; ++d) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    const int s = (int)floorf(fx);
+    fx -= (float)s;
+    float co[8], sum = 0.f;
+    const double y0 = -(fx + 3) * pi * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; ++i) {
+      const float y0_ = (fx + 3 - i);
+      if (fabsf(y0_) >= 1e-6f) {
+        const double y = -y0_ * pi * 0.25;
+        co[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+      } else {
+        co[i] = 1e30f;
+      }
+      sum += co[i];
+    }
+    sum = 1.f / sum;
+    t.ofs.push_back(s);
+    for (int i = 0; i < 8; ++i) {
+      long v = lrintf(co[i] * sum * 2048.f);
+      t.w.push_back((int)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)));
+    }
+  }
+  return t;
+}
+
 __device__ __forceinline__ uint8_t sat_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 __global__ void area_fast_kernel(const uint8_t* __restrict__ src, int sw, int c, uint8_t* __restrict__ dst, int dh, int dw, int iy, int ix, float scale) {
@@ -143,6 +183,34 @@ __global__ void area_linear_kernel(const uint8_t* __restrict__ src, int sh, int 
     }
     const int v = (((yw[2 * dy] * (h0 >> 4)) >> 16) + ((yw[2 * dy + 1] * (h1 >> 4)) >> 16) + 2) >> 2;
     dst[i] = sat_u8(v);
+  }
+}
+
+// INTER_LANCZOS4, 8-bit: HResizeLanczos4 (int32 sums of 11-bit weights, replicated border) then VResizeLanczos4 with
+// FixedPtCast<int, uchar, 22>; one thread per output element (64 taps)
+__global__ void lanczos4_kernel(const uint8_t* __restrict__ src, int sh, int sw, int c, uint8_t* __restrict__ dst, int dh, int dw,
+                                const int* __restrict__ xofs, const int* __restrict__ xw, const int* __restrict__ yofs, const int* __restrict__ yw) {
+  const long long total = (long long)dh * dw * c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const int dx = (int)((i / c) % dw), dy = (int)(i / ((long long)c * dw));
+    const int sx = xofs[dx] - 3, sy = yofs[dy] - 3;
+    int wx[8], cx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wx[k] = xw[8 * dx + k];
+      cx[k] = min(max(sx + k, 0), sw - 1) * c + ch;
+    }
+    int v = 0;
+#pragma unroll
+    for (int ky = 0; ky < 8; ++ky) {
+      const uint8_t* row = src + (size_t)min(max(sy + ky, 0), sh - 1) * sw * c;
+      int h = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h += row[cx[k]] * wx[k];
+      v += h * yw[8 * dy + ky];
+    }
+    dst[i] = sat_u8((v + (1 << 21)) >> 22);
   }
 }
 
@@ -205,6 +273,44 @@ extern "C" int saspa_resize_area_u8(const uint8_t* src, int sh, int sw, int c, u
     SASPA_CUDA(cudaGetLastError());
     area_linear_kernel<<<grid, 256, 0, stream>>>(src, sh, sw, c, dst, dh, dw, xofs, xw, tx.dmax, yofs, yw);
   }
+  SASPA_LAUNCH_CHECK();
+  return SASPA_OK;
+}
+
+extern "C" size_t saspa_resize_lanczos4_workspace_bytes(int dh, int dw) {
+  if (dh <= 0 || dw <= 0) return 256;
+  return align256((size_t)(dw + dh) * 9 * 4 + 256);
+}
+
+extern "C" int saspa_resize_lanczos4_u8(const uint8_t* src, int sh, int sw, int c, uint8_t* dst, int dh, int dw, void* workspace, size_t ws_bytes,
+                                        cudaStream_t stream) {
+  SASPA_CHECK_ARG(sh > 0 && sw > 0 && dh > 0 && dw > 0 && c >= 1 && c <= 4, "saspa_resize_lanczos4_u8: bad shape (%d x %d x %d -> %d x %d)", sh, sw, c, dh, dw);
+  SASPA_CHECK_ARG(src && dst, "saspa_resize_lanczos4_u8: null pointer");
+  const long long total = (long long)dh * dw * c;
+  if (sh == dh && sw == dw) {
+    SASPA_CUDA(cudaMemcpyAsync(dst, src, (size_t)total, cudaMemcpyDeviceToDevice, stream));
+    return SASPA_OK;
+  }
+  SASPA_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "saspa_resize_lanczos4_u8: workspace must be 256-byte aligned");
+  if (ws_bytes < saspa_resize_lanczos4_workspace_bytes(dh, dw)) {
+    saspa_set_error("saspa_resize_lanczos4_u8: workspace too small (%zu < %zu bytes)", ws_bytes, saspa_resize_lanczos4_workspace_bytes(dh, dw));
+    return SASPA_ERR_WORKSPACE;
+  }
+  const LanczosTab tx = lanczos_tab(sw, dw), ty = lanczos_tab(sh, dh);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto put = [&](const void* host, size_t bytes) -> const int* {
+    void* d = ws;
+    cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream);
+    ws += (bytes + 15) / 16 * 16;
+    return static_cast<const int*>(d);
+  };
+  const int* xofs = put(tx.ofs.data(), tx.ofs.size() * 4);
+  const int* xw = put(tx.w.data(), tx.w.size() * 4);
+  const int* yofs = put(ty.ofs.data(), ty.ofs.size() * 4);
+  const int* yw = put(ty.w.data(), ty.w.size() * 4);
+  SASPA_CUDA(cudaGetLastError());
+  const long long cap = (long long)saspa_num_sms() * 32, g = ceil_div_ll(total, 256);
+  lanczos4_kernel<<<(int)(g < cap ? g : cap), 256, 0, stream>>>(src, sh, sw, c, dst, dh, dw, xofs, xw, yofs, yw);
   SASPA_LAUNCH_CHECK();
   return SASPA_OK;
 }

@@ -608,3 +608,17 @@ def resize_area(img: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
     check(lib.saspa_resize_area_u8(_ptr(img), sh, sw, c, _ptr(out), int(dh), int(dw), _ptr(ws), ws_bytes, _stream()), "saspa_resize_area_u8")
     _count()
     return out
+
+
+def resize_lanczos4(img: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LANCZOS4) for ONE u8 HWC image on the device (bit-exact, csrc/resize_area.cu)."""
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    sh, sw, c = img.shape
+    lib = _lib.load()
+    ws_bytes = lib.saspa_resize_lanczos4_workspace_bytes(int(dh), int(dw))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+    out = torch.empty((int(dh), int(dw), c), dtype=torch.uint8, device=img.device)
+    check(lib.saspa_resize_lanczos4_u8(_ptr(img), sh, sw, c, _ptr(out), int(dh), int(dw), _ptr(ws), ws_bytes, _stream()), "saspa_resize_lanczos4_u8")
+    _count()
+    return out

@@ -60,7 +60,7 @@ class AugConfig:
     SAMPLER: str = "ddim"
     RNG_MODE: str = "per_item"  # "per_item" (partition independent) | "reference_order" (replays the global generator)
     MICRO_BATCH: int = 16
-    DEVICE_RESIZE: bool = False  # loader threads resize down-scaled sources on the GPU (bit-exact INTER_AREA) instead of with cv2
+    DEVICE_RESIZE: bool = False  # loader threads resize the sources on the GPU (bit-exact INTER_AREA / INTER_LANCZOS4) instead of with cv2
 
     def __post_init__(self):
         if self.USE_ARTISTIC_PROMPTS is None:
@@ -143,18 +143,14 @@ def resize_image(input_image: np.ndarray, smaller_side_res: int) -> np.ndarray:
 
 
 def resize_image_device(img_u8, smaller_side_res: int):
-    """``resize_image`` for a u8 HWC image that is already on the device (e.g. decoded there): same size rule; the INTER_AREA down-scale
-    (k <= 1: every source at least ``smaller_side_res`` px on its short side) runs on the GPU bit-exactly (saspa_resize_area_u8).  Smaller
-    sources need OpenCV's LANCZOS4 up-scale, which stays on the host (``resize_image``): this function refuses them instead of
-    approximating."""
+    """``resize_image`` for a u8 HWC image that is already on the device: same size rule, same pixels as cv2 -- INTER_AREA for k <= 1
+    (saspa_resize_area_u8), INTER_LANCZOS4 for k > 1 (saspa_resize_lanczos4_u8), both bit-exact against the installed OpenCV."""
     from . import ops
 
     H, W, k = resized_hw(int(img_u8.shape[0]), int(img_u8.shape[1]), smaller_side_res)
     if (H, W) == tuple(img_u8.shape[:2]):
         return img_u8
-    if k > 1:
-        raise NotImplementedError("up-scaling (cv2.INTER_LANCZOS4) is done on the host: run_aug.resize_image")
-    return ops.resize_area(img_u8.contiguous(), H, W)
+    return (ops.resize_lanczos4 if k > 1 else ops.resize_area)(img_u8.contiguous(), H, W)
 
 
 def HWC3(x: np.ndarray) -> np.ndarray:
@@ -535,7 +531,7 @@ def generate(cfg: AugConfig, ds_utils, pipe, prompts, out_dir: str, rank: int = 
 
     def load(path):
         img = np.array(Image.open(path).convert("RGB"))
-        if cfg.DEVICE_RESIZE and resized_hw(img.shape[0], img.shape[1], cfg.RESOLUTION)[2] <= 1:
+        if cfg.DEVICE_RESIZE:
             # same pixels as cv2 (saspa_resize_area_u8), on this loader thread's own stream so it never queues behind the denoising kernels
             side = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(side):

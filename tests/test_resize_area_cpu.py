@@ -29,3 +29,14 @@ def test_area_restatement_on_resize_image_shapes(hw):
     H, W, k = run_aug.resized_hw(hw[0], hw[1], 512)
     assert k <= 1
     assert np.array_equal(cv2_area.resize_area(src, W, H), want)
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(30, 40, 64, 64), (375, 500, 512, 704), (300, 400, 512, 704), (100, 100, 128, 192), (64, 64, 128, 128), (333, 250, 704, 512),
+                                         (200, 200, 512, 512), (97, 131, 256, 320)])
+def test_lanczos4_restatement_equals_cv2(sh, sw, dh, dw):
+    """INTER_LANCZOS4 (resize_image's k > 1 branch: sources under the resolution) restated and compared with the installed cv2 bit for bit."""
+    src = np.random.default_rng(sh * 1000 + sw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4)
+    assert np.array_equal(cv2_area.resize_lanczos4(src, dw, dh), want)
+    if min(sh, sw) < 512 and (dh, dw) == run_aug.resized_hw(sh, sw, 512)[:2]:
+        assert np.array_equal(run_aug.resize_image(src, 512), want)
